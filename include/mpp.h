@@ -1,0 +1,138 @@
+/*
+ * mpp.h -- C ABI of libmpp_b200.so: the B200 (sm_100a) implementation of the
+ * population-evaluation hot path of dvnam1605/MAACO-path-planing.
+ *
+ * The reference has no FFI of its own (pure Python); this header is the boundary a
+ * maintainer binds with ctypes underneath the reference's Python classes (see
+ * INTEGRATION.md for the stub).  Each entry point names the reference code it
+ * replaces (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MPP_E* code otherwise; nothing
+ *     throws across the ABI; mpp_last_error() returns a thread-local message.
+ *   - all pointers named *_dev are device pointers on the map's device; everything is
+ *     enqueued on `stream` (a cudaStream_t passed as void*) and is asynchronous unless
+ *     stated.  The caller owns every buffer; the library owns only map handles.
+ *   - cells are int32 `r*cols + c`; paths are int32 arrays; all reals are IEEE binary64.
+ *   - there is NO CPU fallback: with no sm_100 device the calls fail with MPP_ENODEVICE.
+ *   - RNG: counter-based Philox4x32-10 streams keyed (seed, class, iteration, individual)
+ *     with an in-stream cursor (DESIGN.md "RNG contract").
+ */
+#ifndef MPP_H_
+#define MPP_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPP_ABI_VERSION 1
+
+#define MPP_OK 0
+#define MPP_EINVAL (-1)
+#define MPP_ENODEVICE (-2)
+#define MPP_ECUDA (-3)
+#define MPP_ENOMEM (-4)
+#define MPP_EUNSUPPORTED (-5)
+
+/* stream classes of the RNG contract */
+#define MPP_CLS_MAACO_TOUR 1
+#define MPP_CLS_PSO_INIT 2
+#define MPP_CLS_PSO_PAD 3
+#define MPP_CLS_PSO_UPDATE 4
+#define MPP_CLS_GA_INIT 5
+#define MPP_CLS_GA_PAD 6
+#define MPP_CLS_GA_SELECT 7
+#define MPP_CLS_GA_BREED 8
+#define MPP_CLS_MPA_PHASE 9
+#define MPP_CLS_MPA_FADS 10
+
+typedef struct mpp_map mpp_map; /* opaque: bit-packed occupancy grid + per-map tables on one device */
+
+int mpp_abi_version(void);
+const char *mpp_last_error(void);
+/* number of sm_100 devices visible (0 => every compute entry point fails) */
+int mpp_device_count(void);
+
+/* ---- grid map: env.py grid convention (0 free, 1 obstacle, 2 start, 3 target) ------------
+ * replaces: np.array(grid) + argwhere(grid==2/3) in every constructor
+ * (MAACO.py:15-41, helper.py:121-125, astar.py:17-22, pso.py:17-22, ga_solver.py:17-22, MPA.py:20-43).
+ * grid_host: rows*cols bytes, row-major.  Start/target = first row-major 2 / 3; pass
+ * start=-1/target=-1 to mpp_map_create_ex to take them from the grid.  Synchronous. */
+int mpp_map_create(const uint8_t *grid_host, int rows, int cols, int device, mpp_map **out);
+void mpp_map_destroy(mpp_map *map);
+int mpp_map_rows(const mpp_map *map);
+int mpp_map_cols(const mpp_map *map);
+int mpp_map_start(const mpp_map *map);  /* cell id or -1 */
+int mpp_map_target(const mpp_map *map); /* cell id or -1 */
+int mpp_map_device(const mpp_map *map);
+/* device pointer to the border-padded bit-packed occupancy grid ((rows+2) x pitch_words uint32,
+ * bit (r+1, c+1); the border is marked occupied) and its row pitch in 32-bit words */
+const uint32_t *mpp_map_occ_bits(const mpp_map *map, int *pitch_words);
+
+/* ---- MAACO (MAACO.py) -------------------------------------------------------------------- */
+typedef struct {
+    double alpha, beta, rho, Q, a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial, C0_initial_pheromone;
+    int num_iterations;
+} mpp_maaco_params;
+
+/* replaces MAACO._initialize_pheromones_maaco (MAACO.py:58-84), _precompute_dist_to_target
+ * (:86-91) and the per-candidate heuristic eta'**beta (:197-210, :238) folded into two per-cell
+ * tables E[c][cell], c = turn flag.  exp/pow are evaluated on the host with libm (the same
+ * functions CPython/NumPy call) so the tables are bit-identical to the reference; outputs are
+ * device arrays of rows*cols doubles (dist_t_dev may be NULL).  Synchronous. */
+int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, double *tau0_dev, double *E0_dev,
+                     double *E1_dev, double *dist_t_dev, void *stream);
+
+/* replaces MAACO._calculate_adaptive_q0 (MAACO.py:212-226); pure host function */
+double mpp_maaco_q0(int num_iterations, int iteration, double q0_initial);
+
+/* replaces the ant loop MAACO.py:340-342 -> _construct_ant_solution_maaco (:278-302) with the
+ * orientation filter + crossing-prohibition (:100-181) and pseudo-random-proportional selection
+ * (:228-262).  Ant i of this call is global ant `ant_offset + i` (its RNG stream id).
+ *   tau/E0/E1      rows*cols doubles
+ *   visitT_dev     word-major visited bitmaps: word w of ant i at [w*n_ants + i], ceil(rows*cols/32)
+ *                  words per ant; MUST be zero on entry; holds each ant's visited set on return
+ *   cells_dev      n_ants x max_cells path cells (cells beyond max_cells are dropped; n_cells still
+ *                  counts them); n_cells=0, length=+inf, turns=-1 for a failed ant (:288,:292,:302)
+ *   lanes_per_ant  8 or 32 (0 = choose)                                                          */
+int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E0_dev, const double *E1_dev,
+                    int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
+                    uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, int32_t *n_cells_dev,
+                    double *length_dev, int32_t *turns_dev, unsigned long long *steps_dev, int lanes_per_ant,
+                    void *stream);
+
+/* colony state kept on the device so an entire solve can be enqueued without host syncs */
+typedef struct {
+    double best_len;       /* best_path_length_overall (+inf = none) */
+    int32_t best_turns;    /* -1 = inf */
+    int32_t best_n_cells;
+    int32_t best_iter;     /* iteration that set best_path (0 = none) */
+    int32_t best_ant;
+    double iter_best_len;  /* last iteration */
+    int32_t iter_best_turns;
+    int32_t iter_best_ant; /* -1 = all ants failed */
+} mpp_maaco_state;
+
+/* replaces the order-dependent best tracking MAACO.py:343-358 for one iteration over all
+ * n_ants (in global ant order) and prepares the per-ant deposit Q/length (:307-308; 0 for ants
+ * that do not deposit).  Updates *state_dev, copies the new overall-best path into
+ * best_cells_dev (capacity max_cells) and appends to the per-iteration logs
+ * log_dev[4*(iteration-1) + {0: iter best len, 1: iter best turns, 2: overall len, 3: overall turns}]
+ * (log_dev may be NULL). */
+int mpp_maaco_best(const double *length_dev, const int32_t *turns_dev, const int32_t *n_cells_dev,
+                   const int32_t *cells_dev, int max_cells, int n_ants, double Q, int iteration,
+                   mpp_maaco_state *state_dev, int32_t *best_cells_dev, double *deposit_dev, double *log_dev,
+                   void *stream);
+
+/* replaces MAACO._update_pheromone_trails_maaco (MAACO.py:304-332): evaporate, deposit in global
+ * ant order (bit-exact, atomics-free: one warp per 32 cells walks the visited words of all ants),
+ * MMAS clip with tau_max from state->best_len, obstacles <- 1e-9.  Clears visitT_dev behind itself
+ * when clear_visit != 0. */
+int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t *visitT_dev, const double *deposit_dev,
+                        int n_ants, double rho, const mpp_maaco_state *state_dev, int clear_visit, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPP_H_ */

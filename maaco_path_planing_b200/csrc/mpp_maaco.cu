@@ -1,0 +1,549 @@
+// mpp_maaco.cu -- MAACO colony pass on B200: tour construction (one warp or one 8-lane
+// group per ant), order-dependent best tracking, and the atomics-free ordered pheromone update.
+// Reference semantics: MAACO.py:58-91 (tables), :100-181 (filter), :197-262 (selection),
+// :278-302 (tour), :304-332 (pheromone), :343-358 (best tracking).
+#include <cmath>
+#include <thread>
+#include <vector>
+
+#include "mpp_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// host: tables (libm exp/pow == what CPython / NumPy call, so the tables are bit-identical)
+// ---------------------------------------------------------------------------------------------
+static inline double hdist(int r0, int c0, int r1, int c1) {
+    long long dr = r0 - r1, dc = c0 - c1;
+    return std::sqrt((double)(dr * dr + dc * dc));
+}
+
+extern "C" double mpp_maaco_q0(int K, int k, double q0_initial) {  // MAACO.py:212-226
+    double k0 = 0.7 * (double)K, q0;
+    if ((double)k < k0) {
+        if (std::fabs((double)K - k0) < 1e-6) q0 = q0_initial;
+        else q0 = ((double)(K - k) / (double)K) * q0_initial;
+    } else {
+        double q0_at_k0 = (((double)K - k0) / (double)K) * q0_initial;
+        q0 = q0_at_k0 +
+             (((double)k - k0) / ((double)K - k0 + 1e-9)) * (q0_initial * (1 - ((double)K - k0) / (double)K) / 2.0);
+    }
+    q0 = q0 > 0.01 ? q0 : 0.01;
+    return q0 < 0.99 ? q0 : 0.99;
+}
+
+extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, double *tau0_dev, double *E0_dev,
+                                double *E1_dev, double *dist_t_dev, void *stream) {
+    MPP_REQUIRE(map && p && tau0_dev && E0_dev && E1_dev, "mpp_maaco_tables: null argument");
+    MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_tables: map has no start/target");
+    const int R = map->rows, C = map->cols;
+    const size_t n = (size_t)R * C;
+    const int sr = map->start / C, sc = map->start % C, tr = map->target / C, tc = map->target % C;
+    double dsT = hdist(sr, sc, tr, tc);
+    if (dsT < 1e-9) dsT = 1e-9;  // MAACO.py:43-45
+    std::vector<double> buf(4 * n);
+    double *tau0 = buf.data(), *E0 = tau0 + n, *E1 = E0 + n, *dt = E1 + n;
+    const uint8_t *grid = map->grid_host;
+    auto work = [&](int r_lo, int r_hi) {
+        for (int r = r_lo; r < r_hi; ++r)
+            for (int c = 0; c < C; ++c) {
+                const size_t i = (size_t)r * C + c;
+                const double diT = hdist(r, c, tr, tc);
+                const double dsi = hdist(sr, sc, r, c);
+                dt[i] = diT;
+                if (grid[i] == 1) {
+                    tau0[i] = 1e-9;
+                } else {
+                    const double den = dsi + diT;
+                    double factor;
+                    if (den < 1e-9) factor = (dsi < 1e-6 || diT < 1e-6) ? 1.0 : 0.1;
+                    else factor = dsT / den;
+                    const double v = factor * p->C0_initial_pheromone;
+                    tau0[i] = v < 1e-9 ? 1e-9 : v;
+                }
+                double h;
+                if (dsT < 1e-9) h = p->wh_min;
+                else h = p->wh_max - (p->wh_max - p->wh_min) * std::exp(-p->k_h_adaptive * diT / dsT);
+                const double g = 1.0 - h;
+                const double base = g * dsi + h * diT;
+                double d0 = base + p->a_turn_coef * 0.0, d1 = base + p->a_turn_coef * 1.0;
+                d0 = d0 > 1e-9 ? d0 : 1e-9;
+                d1 = d1 > 1e-9 ? d1 : 1e-9;
+                E0[i] = std::pow(1.0 / d0, p->beta);
+                E1[i] = std::pow(1.0 / d1, p->beta);
+            }
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt > 16) nt = 16;
+    if (nt < 2 || n < 65536) {
+        work(0, R);
+    } else {
+        std::vector<std::thread> th;
+        int per = (R + (int)nt - 1) / (int)nt;
+        for (unsigned t = 0; t < nt; ++t) {
+            int lo = (int)t * per, hi = lo + per > R ? R : lo + per;
+            if (lo < hi) th.emplace_back(work, lo, hi);
+        }
+        for (auto &t : th) t.join();
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    MPP_CUDA(cudaSetDevice(map->device));
+    MPP_CUDA(cudaMemcpyAsync(tau0_dev, tau0, n * 8, cudaMemcpyHostToDevice, s));
+    MPP_CUDA(cudaMemcpyAsync(E0_dev, E0, n * 8, cudaMemcpyHostToDevice, s));
+    MPP_CUDA(cudaMemcpyAsync(E1_dev, E1, n * 8, cudaMemcpyHostToDevice, s));
+    if (dist_t_dev) MPP_CUDA(cudaMemcpyAsync(dist_t_dev, dt, n * 8, cudaMemcpyHostToDevice, s));
+    MPP_CUDA(cudaStreamSynchronize(s));  // buf is freed on return
+    return MPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: tour construction
+// ---------------------------------------------------------------------------------------------
+struct TourArgs {
+    const uint32_t *occ;  // padded occupancy bits (global)
+    int occ_words, pitch;
+    int R, C, start, target;
+    const double *tau, *E0, *E1;
+    uint32_t it;
+    double q0, alpha;
+    int n_ants, ant_offset;
+    uint32_t k0, k1;
+    uint32_t *visitT;
+    int32_t *cells;
+    int max_cells;
+    int32_t *n_cells;
+    double *length;
+    int32_t *turns;
+    unsigned long long *steps;
+};
+
+#define MPP_TOUR_THREADS 256
+#define MPP_SQRT2 1.4142135623730951  // sqrt(2.0) correctly rounded == math.sqrt(2)
+
+
+// Full roulette branch MAACO.py:255-262 (rare; kept out of line so it does not cost registers
+// in the step loop).  Returns the rank (among candidates, in move order) of the selected move.
+__device__ __noinline__ int roulette_rank(double attr, uint32_t cand, uint32_t gmask, int gshift, double S, double u1) {
+    double at[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) at[i] = __shfl_sync(gmask, attr, gshift + i);
+    const int n = __popc(cand);
+    double pr[8], ps = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        pr[i] = at[i] / S;                                            // :255
+        if ((cand >> i) & 1u) ps += pr[i];
+    }
+    if (fabs(ps - 1.0) > 1e-6) {                                      // :257-258
+        const double ps0 = ps;
+        ps = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            pr[i] = pr[i] / ps0;
+            if ((cand >> i) & 1u) ps += pr[i];
+        }
+    }
+    int k;
+    if (!(fabs(ps - 1.0) <= 1.4901161193847656e-08)) {                // np.random.choice ValueError -> :262
+        k = (int)(u1 * (double)n);
+    } else {
+        // RandomState.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, side='right')
+        double acc = 0.0, cdf[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if ((cand >> i) & 1u) acc += pr[i];
+            cdf[i] = acc;
+        }
+        k = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (((cand >> i) & 1u) && (cdf[i] / acc <= u1)) ++k;
+    }
+    return k < n ? k : n - 1;
+}
+
+__device__ __noinline__ double pow_slow(double x, double y) { return pow(x, y); }
+
+template <int LPA>
+__device__ __forceinline__ uint32_t group_ballot(uint32_t gmask, int gshift, bool pred) {
+    uint32_t b = __ballot_sync(gmask, pred);
+    return (LPA == 32) ? (b & 0xffu) : ((b >> gshift) & 0xffu);
+}
+
+template <int LPA, bool OCC_SMEM>
+__global__ void __launch_bounds__(MPP_TOUR_THREADS, 4) mpp_maaco_tour_kernel(const TourArgs A) {
+    extern __shared__ __align__(16) uint32_t s_occ[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t *occ = A.occ;
+    if (OCC_SMEM) {
+        // occupancy grid: HBM -> shared memory as TMA bulk copies (UBLKCP), one per block
+        mpp_stage_bulk(s_occ, A.occ, (uint32_t)A.occ_words * 4u, &s_bar);
+        occ = s_occ;
+    }
+    const int lane = threadIdx.x & 31;
+    const int m = lane % LPA;                      // move index handled by this lane (m < 8 active)
+    const int gshift = (LPA == 32) ? 0 : (lane / LPA) * LPA;
+    const uint32_t gmask = (LPA == 32) ? 0xffffffffu : (0xffu << gshift);
+    const int a = (blockIdx.x * MPP_TOUR_THREADS + threadIdx.x) / LPA;
+    if (a >= A.n_ants) return;
+    const bool mv = m < 8;
+    // move order MAACO.py:98: (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1)
+    const int i9 = m + (m >= 4);
+    const int mr = mv ? i9 / 3 - 1 : 0, mc = mv ? i9 % 3 - 1 : 0;
+    const int R = A.R, C = A.C;
+    const int tr = A.target / C, tc = A.target % C;
+    int cr = A.start / C, cc = A.start % C;
+    // strategy-1 orientation mask (Start->Target), MAACO.py:146-150
+    auto orient_mask = [](int dR, int dC) -> uint32_t {
+        uint32_t k = 0xffu;
+        if (dC > 0) k &= ~0x29u;  // moves with dc<0: m0,m3,m5
+        if (dC < 0) k &= ~0x94u;  // dc>0: m2,m4,m7
+        if (dR > 0) k &= ~0x07u;  // dr<0: m0,m1,m2
+        if (dR < 0) k &= ~0xE0u;  // dr>0: m5,m6,m7
+        return k;
+    };
+    const uint32_t P1 = orient_mask(tr - cr, tc - cc);
+    const uint32_t ant_global = (uint32_t)(A.ant_offset + a);
+    const size_t n_ants = (size_t)A.n_ants;
+    int n_path = 1, prev_m = -1, turns = 0;
+    double len = 0.0;
+    long long steps = 0;
+    const long long max_steps = 2ll * R * C;
+    bool failed = false;
+    if (m == 0) {
+        const int s = A.start;
+        A.visitT[(size_t)(s >> 5) * n_ants + a] = 1u << (s & 31);
+        if (A.max_cells > 0) A.cells[(size_t)a * A.max_cells] = s;
+    }
+    __syncwarp(gmask);
+    while (!(cr == tr && cc == tc) && steps < max_steps) {
+        // ---- candidate generation: bounds/obstacle (shared-memory bits), tabu (HBM/L2 bits) ----
+        const int nr = cr + mr, nc = cc + mc;
+        bool blocked = true;
+        if (mv) {
+            const int pb = nc + 1;
+            blocked = (occ[(nr + 1) * A.pitch + (pb >> 5)] >> (pb & 31)) & 1u;
+        }
+        const int j = nr * C + nc;
+        uint32_t tw = 0;
+        double tv = 0.0, ev = 0.0;
+        const bool turn = (n_path >= 2) && (m != prev_m);   // MAACO.py:184-195
+        if (!blocked) {
+            tw = A.visitT[(size_t)(j >> 5) * n_ants + a];
+            tv = A.tau[j];
+            ev = turn ? A.E1[j] : A.E0[j];
+        }
+        // uniforms for this step: draws 2s (q-test) and 2s+1 (selection) of stream (seed, TOUR, it, ant)
+        const mpp_u4 rb = mpp_philox((uint32_t)steps, ant_global, A.it, MPP_CLS_MAACO_TOUR, A.k0, A.k1);
+        const double u0 = mpp_u53(rb.x, rb.y), u1 = mpp_u53(rb.z, rb.w);
+        const uint32_t o = group_ballot<LPA>(gmask, gshift, blocked);
+        const bool tabu = (!blocked) && ((tw >> (j & 31)) & 1u);
+        const uint32_t tb = group_ballot<LPA>(gmask, gshift, tabu);
+        // crossing prohibition MAACO.py:100-120: diagonal banned if either orthogonal cell is an obstacle
+        const uint32_t o1 = (o >> 1) & 1u, o3 = (o >> 3) & 1u, o4 = (o >> 4) & 1u, o6 = (o >> 6) & 1u;
+        const uint32_t cut = ((o1 | o3) << 0) | ((o1 | o4) << 2) | ((o6 | o3) << 5) | ((o6 | o4) << 7);
+        const uint32_t valid = ~(o | tb | cut) & 0xffu;
+        uint32_t cand = valid & P1;                                   // strategy 1 :165
+        if (!cand) cand = valid & orient_mask(tr - cr, tc - cc);      // strategy 2 :169
+        if (!cand) cand = valid;                                      // strategy 3 :172-180
+        if (!cand) { failed = true; break; }                          // :287-288
+        const bool in_c = mv && ((cand >> m) & 1u);
+        const double ta = (A.alpha == 1.0) ? tv : pow_slow(tv, A.alpha);   // tau**alpha (x**1.0 == x exactly)
+        const double attr = ta * ev;                                  // :238
+        const uint32_t below_me = cand & ((1u << m) - 1u);
+        int pick;
+        if (u0 <= A.q0) {
+            // greedy :241-250.  Sequential rule == {first arg-max r} U {i>r : |attr_i - max| < 1e-9}
+            const unsigned long long key = in_c ? (unsigned long long)__double_as_longlong(attr) : 0ull;
+            const uint32_t hi = (uint32_t)(key >> 32);
+            const uint32_t mhi = __reduce_max_sync(gmask, hi);
+            const uint32_t lo = (in_c && hi == mhi) ? (uint32_t)key : 0u;
+            const uint32_t mlo = __reduce_max_sync(gmask, lo);
+            const double mx = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+            const uint32_t eq = group_ballot<LPA>(gmask, gshift, in_c && attr == mx);
+            const int r = __ffs(eq) - 1;
+            const uint32_t el =
+                group_ballot<LPA>(gmask, gshift, in_c && (m == r || (m > r && fabs(attr - mx) < 1e-9)));
+            const int ne = __popc(el);
+            int k = (int)(u1 * (double)ne);
+            k = k < ne ? k : ne - 1;
+            const uint32_t sel = group_ballot<LPA>(gmask, gshift, ((el >> m) & 1u) && mv && __popc(el & ((1u << m) - 1u)) == k);
+            pick = __ffs(sel) - 1;
+        } else {
+            // :251-262.  sum() over np.float64 items == plain left-to-right
+            double S = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double v = __shfl_sync(gmask, attr, gshift + i);
+                if ((cand >> i) & 1u) S += v;
+            }
+            const int n = __popc(cand);
+            int k;
+            if (S < 1e-9) {
+                k = (int)(u1 * (double)n);                            // random.choice(all) :253-254
+                k = k < n ? k : n - 1;
+            } else {
+                k = roulette_rank(attr, cand, gmask, gshift, S, u1);  // rare: only within a few cells of T
+            }
+            const uint32_t sel = group_ballot<LPA>(gmask, gshift, in_c && __popc(below_me) == k);
+            pick = __ffs(sel) - 1;
+        }
+        // ---- advance :293-297 ----
+        const int p9 = pick + (pick >= 4);
+        const int pr_ = p9 / 3 - 1, pc_ = p9 % 3 - 1;
+        len += (pr_ != 0 && pc_ != 0) ? MPP_SQRT2 : 1.0;
+        if (n_path >= 2 && pick != prev_m) ++turns;                   // :264-276 counted on the fly
+        prev_m = pick;
+        if (m == pick) {
+            A.visitT[(size_t)(j >> 5) * n_ants + a] = tw | (1u << (j & 31));
+            if (n_path < A.max_cells) A.cells[(size_t)a * A.max_cells + n_path] = j;
+        }
+        cr += pr_;
+        cc += pc_;
+        ++n_path;
+        ++steps;
+        __syncwarp(gmask);
+    }
+    if (m == 0) {
+        const bool ok = !failed && cr == tr && cc == tc;
+        A.n_cells[a] = ok ? n_path : 0;
+        A.length[a] = ok ? len : __longlong_as_double(0x7ff0000000000000ll);
+        A.turns[a] = ok ? turns : -1;
+        if (A.steps) atomicAdd(A.steps, (unsigned long long)steps);
+    }
+}
+
+extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E0_dev, const double *E1_dev,
+                               int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
+                               uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, int32_t *n_cells_dev,
+                               double *length_dev, int32_t *turns_dev, unsigned long long *steps_dev,
+                               int lanes_per_ant, void *stream) {
+    MPP_REQUIRE(map && tau_dev && E0_dev && E1_dev && visitT_dev && cells_dev && n_cells_dev && length_dev && turns_dev,
+                "mpp_maaco_tours: null argument");
+    MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_tours: map has no start/target");
+    MPP_REQUIRE(n_ants > 0 && max_cells > 0, "mpp_maaco_tours: n_ants=%d max_cells=%d", n_ants, max_cells);
+    if (lanes_per_ant == 0) lanes_per_ant = (n_ants <= 64 * map->sm_count) ? 32 : 8;
+    MPP_REQUIRE(lanes_per_ant == 8 || lanes_per_ant == 32, "mpp_maaco_tours: lanes_per_ant must be 8 or 32");
+    MPP_CUDA(cudaSetDevice(map->device));
+    TourArgs A;
+    A.occ = map->occ_dev; A.occ_words = map->occ_words; A.pitch = map->pitch_words;
+    A.R = map->rows; A.C = map->cols; A.start = map->start; A.target = map->target;
+    A.tau = tau_dev; A.E0 = E0_dev; A.E1 = E1_dev;
+    A.it = (uint32_t)iteration; A.q0 = q0; A.alpha = alpha;
+    A.n_ants = n_ants; A.ant_offset = ant_offset;
+    A.k0 = (uint32_t)seed; A.k1 = (uint32_t)(seed >> 32);
+    A.visitT = visitT_dev; A.cells = cells_dev; A.max_cells = max_cells;
+    A.n_cells = n_cells_dev; A.length = length_dev; A.turns = turns_dev; A.steps = steps_dev;
+    const size_t smem = (size_t)map->occ_words * 4;
+    const bool in_smem = smem <= 200 * 1024;
+    const int ants_per_block = MPP_TOUR_THREADS / lanes_per_ant;
+    const int blocks = (n_ants + ants_per_block - 1) / ants_per_block;
+    cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH(LPA, SM)                                                                                         \
+    do {                                                                                                        \
+        if (SM) MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour_kernel<LPA, SM>,                                   \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        mpp_maaco_tour_kernel<LPA, SM><<<blocks, MPP_TOUR_THREADS, SM ? smem : 0, s>>>(A);                      \
+    } while (0)
+    if (lanes_per_ant == 32) { if (in_smem) LAUNCH(32, true); else LAUNCH(32, false); }
+    else { if (in_smem) LAUNCH(8, true); else LAUNCH(8, false); }
+#undef LAUNCH
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: iteration-best / overall-best (MAACO.py:343-358) + deposits (:307-308)
+// ---------------------------------------------------------------------------------------------
+#define MPP_BEST_THREADS 1024
+__device__ __forceinline__ bool lt_len_idx(double la, int ia, double lb, int ib) {
+    return la < lb || (la == lb && ia < ib);
+}
+
+__global__ void __launch_bounds__(MPP_BEST_THREADS)
+mpp_maaco_best_kernel(const double *__restrict__ length, const int32_t *__restrict__ turns,
+                      const int32_t *__restrict__ n_cells, const int32_t *__restrict__ cells, int max_cells, int n,
+                      double Q, int iteration, mpp_maaco_state *state, int32_t *best_cells, double *deposit,
+                      double *log) {
+    __shared__ double s_len[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_t[32];
+    __shared__ double b_len;
+    __shared__ int b_r, b_ant, b_turns, b_copy;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double INF = __longlong_as_double(0x7ff0000000000000ll);
+    // phase 1: global min length and its first index r (the last strict record of the scan)
+    double ml = INF;
+    int mi = 0x7fffffff;
+    for (int i = tid; i < n; i += MPP_BEST_THREADS) {
+        const double l = length[i];
+        if (lt_len_idx(l, i, ml, mi)) { ml = l; mi = i; }
+        // deposit amount MAACO.py:307-308 (0.0 == "does not deposit"; x + 0.0 is exact anyway)
+        deposit[i] = (l != INF && n_cells[i] > 0 && l > 1e-6) ? Q / l : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double ol = __shfl_xor_sync(0xffffffffu, ml, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (lt_len_idx(ol, oi, ml, mi)) { ml = ol; mi = oi; }
+    }
+    if (lane == 0) { s_len[wid] = ml; s_idx[wid] = mi; }
+    __syncthreads();
+    if (wid == 0) {
+        ml = s_len[lane]; mi = s_idx[lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ol = __shfl_xor_sync(0xffffffffu, ml, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (lt_len_idx(ol, oi, ml, mi)) { ml = ol; mi = oi; }
+        }
+        if (lane == 0) { b_len = ml; b_r = mi; }
+    }
+    __syncthreads();
+    const double L = b_len;
+    const int r = b_r;
+    // phase 2: among {r} U {i>r : |len_i - L| < 1e-9} the first index with the fewest turns
+    int bt = 0x7fffffff, bi = 0x7fffffff;
+    if (L != INF) {
+        for (int i = tid; i < n; i += MPP_BEST_THREADS) {
+            if (i < r) continue;
+            const double l = length[i];
+            if (i == r || fabs(l - L) < 1e-9) {
+                const int t = turns[i];
+                if (t >= 0 && (t < bt || (t == bt && i < bi))) { bt = t; bi = i; }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const int ot = __shfl_xor_sync(0xffffffffu, bt, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ot < bt || (ot == bt && oi < bi)) { bt = ot; bi = oi; }
+    }
+    if (lane == 0) { s_t[wid] = bt; s_idx[wid] = bi; }
+    __syncthreads();
+    if (wid == 0) {
+        bt = s_t[lane]; bi = s_idx[lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const int ot = __shfl_xor_sync(0xffffffffu, bt, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ot < bt || (ot == bt && oi < bi)) { bt = ot; bi = oi; }
+        }
+        if (lane == 0) {
+            const bool any = (L != INF);
+            b_ant = any ? bi : -1;
+            b_turns = any ? bt : -1;
+            // overall best MAACO.py:351-358
+            mpp_maaco_state st = *state;
+            int copy = 0;
+            if (any) {
+                if (L < st.best_len) {
+                    st.best_len = L; st.best_turns = bt; copy = 1;
+                } else if (fabs(L - st.best_len) < 1e-9) {
+                    if (bt < st.best_turns) { st.best_turns = bt; copy = 1; }
+                }
+            }
+            if (copy) { st.best_n_cells = n_cells[bi]; st.best_iter = iteration; st.best_ant = bi; }
+            st.iter_best_len = L; st.iter_best_turns = b_turns; st.iter_best_ant = b_ant;
+            *state = st;
+            b_copy = copy;
+            if (log) {
+                double *lg = log + 4 * (size_t)(iteration - 1);
+                lg[0] = L; lg[1] = (double)b_turns; lg[2] = st.best_len; lg[3] = (double)st.best_turns;
+            }
+        }
+    }
+    __syncthreads();
+    if (b_copy) {
+        const int a = b_ant;
+        int nc = n_cells[a];
+        if (nc > max_cells) nc = max_cells;
+        const int32_t *src = cells + (size_t)a * max_cells;
+        for (int k = tid; k < nc; k += MPP_BEST_THREADS) best_cells[k] = src[k];
+    }
+}
+
+extern "C" int mpp_maaco_best(const double *length_dev, const int32_t *turns_dev, const int32_t *n_cells_dev,
+                              const int32_t *cells_dev, int max_cells, int n_ants, double Q, int iteration,
+                              mpp_maaco_state *state_dev, int32_t *best_cells_dev, double *deposit_dev,
+                              double *log_dev, void *stream) {
+    MPP_REQUIRE(length_dev && turns_dev && n_cells_dev && cells_dev && state_dev && best_cells_dev && deposit_dev,
+                "mpp_maaco_best: null argument");
+    MPP_REQUIRE(n_ants > 0 && iteration >= 1, "mpp_maaco_best: n_ants=%d iteration=%d", n_ants, iteration);
+    mpp_maaco_best_kernel<<<1, MPP_BEST_THREADS, 0, (cudaStream_t)stream>>>(
+        length_dev, turns_dev, n_cells_dev, cells_dev, max_cells, n_ants, Q, iteration, state_dev, best_cells_dev,
+        deposit_dev, log_dev);
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: pheromone evaporate + ordered deposit + MMAS clip (MAACO.py:304-332)
+// One warp owns 32 consecutive cells (one bitmap word); it streams that word of every ant
+// (word-major layout => 128-B coalesced loads of 32 ants) and adds deposits in ant order.
+// ---------------------------------------------------------------------------------------------
+#define MPP_PHER_THREADS 256
+__global__ void __launch_bounds__(MPP_PHER_THREADS)
+mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
+                           uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_ants, double rho,
+                           const mpp_maaco_state *__restrict__ state, int clear_visit, int n_words) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * MPP_PHER_THREADS + threadIdx.x) >> 5;
+    if (w >= n_words) return;
+    const int RC = R * C;
+    const int cell = w * 32 + lane;
+    const bool live = cell < RC;
+    double t = 0.0;
+    if (live) t = tau[cell] * (1.0 - rho);                                   // :305
+    uint32_t *row = visitT + (size_t)w * n_ants;
+    for (int a0 = 0; a0 < n_ants; a0 += 128) {
+        uint32_t wd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * 32 + lane;
+            wd[u] = (a < n_ants) ? row[a] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint32_t nz = __ballot_sync(0xffffffffu, wd[u] != 0u);
+            if (nz) {
+                const int a = a0 + u * 32 + lane;
+                const double d = (a < n_ants) ? deposit[a] : 0.0;
+                if (clear_visit && wd[u] != 0u) row[a] = 0u;
+                while (nz) {                                                  // ants in index order :306
+                    const int l = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const uint32_t wv = __shfl_sync(0xffffffffu, wd[u], l);
+                    const double dv = __shfl_sync(0xffffffffu, d, l);
+                    if (((wv >> lane) & 1u) && dv != 0.0) t += dv;            // :311
+                }
+            }
+        }
+    }
+    if (!live) return;
+    double b = state->best_len;                                               // :312-316
+    if (b == __longlong_as_double(0x7ff0000000000000ll)) b = (double)(R + C);
+    if (b < 1e-6) b = 1e-6;
+    const double tmax = (1.0 / (1.0 - rho)) * (1.0 / b);                      // :317
+    int mx = C > R ? C : R;
+    if (mx < 1) mx = 1;
+    const double tmin = tmax / (2.0 * (double)mx);                            // :323
+    const int r = cell / C, c = cell % C, pb = c + 1;
+    const bool obst = (occ[(r + 1) * pitch + (pb >> 5)] >> (pb & 31)) & 1u;
+    if (obst) t = 1e-9;                                                       // :332
+    else { t = t > tmin ? t : tmin; t = t < tmax ? t : tmax; }                // :327-331 np.clip
+    tau[cell] = t;
+}
+
+extern "C" int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t *visitT_dev,
+                                   const double *deposit_dev, int n_ants, double rho,
+                                   const mpp_maaco_state *state_dev, int clear_visit, void *stream) {
+    MPP_REQUIRE(map && tau_dev && visitT_dev && deposit_dev && state_dev, "mpp_maaco_pheromone: null argument");
+    MPP_REQUIRE(n_ants > 0, "mpp_maaco_pheromone: n_ants=%d", n_ants);
+    MPP_CUDA(cudaSetDevice(map->device));
+    const int n_words = (map->rows * map->cols + 31) / 32;
+    const int warps_per_block = MPP_PHER_THREADS / 32;
+    const int blocks = (n_words + warps_per_block - 1) / warps_per_block;
+    mpp_maaco_pheromone_kernel<<<blocks, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
+        map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_ants, rho, state_dev,
+        clear_visit, n_words);
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}

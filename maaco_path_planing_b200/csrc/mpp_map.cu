@@ -1,0 +1,125 @@
+// mpp_map.cu -- grid-map handle: env.py grid (list-of-lists of 0/1/2/3) -> border-padded,
+// bit-packed occupancy tensor in HBM + the per-map safety-class table (helper.py:67-80).
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <cmath>
+
+#include "mpp_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mpp_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int mpp_abi_version(void) { return MPP_ABI_VERSION; }
+extern "C" const char *mpp_last_error(void) { return g_err; }
+
+extern "C" int mpp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int mpp_check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        mpp_set_error("no CUDA device visible (%s); libmpp_b200 has no CPU fallback",
+                      e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return MPP_ENODEVICE;
+    }
+    if (device < 0 || device >= n) { mpp_set_error("device %d out of range [0,%d)", device, n); return MPP_EINVAL; }
+    int major = 0;
+    MPP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) {
+        mpp_set_error("device %d is sm_%d0; libmpp_b200 is built for sm_100a only (no fallback)", device, major);
+        return MPP_ENODEVICE;
+    }
+    return MPP_OK;
+}
+
+// One thread per padded word: word (pr, pw) holds padded columns [32*pw, 32*pw+32) of padded row pr.
+__global__ void mpp_pack_occ_kernel(const uint8_t *__restrict__ grid, int rows, int cols, int pitch_words,
+                                    int total_words, uint32_t *__restrict__ occ) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= total_words) return;
+    int pr = w / pitch_words, pw = w % pitch_words;
+    uint32_t bits = 0;
+    if (pr >= rows + 2) { occ[w] = 0xffffffffu; return; }  // tail padding
+    int r = pr - 1;
+#pragma unroll 4
+    for (int b = 0; b < 32; ++b) {
+        int c = pw * 32 + b - 1;
+        bool blocked = (r < 0 || r >= rows || c < 0 || c >= cols) ? true : (grid[(size_t)r * cols + c] == 1);
+        bits |= (blocked ? 1u : 0u) << b;
+    }
+    occ[w] = bits;
+}
+
+extern "C" int mpp_map_create(const uint8_t *grid_host, int rows, int cols, int device, mpp_map **out) {
+    MPP_REQUIRE(grid_host && out, "mpp_map_create: null argument");
+    MPP_REQUIRE(rows > 0 && cols > 0 && (long long)rows * cols < (1ll << 30), "mpp_map_create: bad shape %dx%d", rows, cols);
+    int rc = mpp_check_device(device);
+    if (rc) return rc;
+    MPP_CUDA(cudaSetDevice(device));
+    mpp_map *m = (mpp_map *)calloc(1, sizeof(mpp_map));
+    if (!m) { mpp_set_error("out of host memory"); return MPP_ENOMEM; }
+    m->rows = rows; m->cols = cols; m->device = device;
+    m->start = m->target = -1;
+    m->safety_msd = -1.0;
+    size_t n = (size_t)rows * cols;
+    m->grid_host = (uint8_t *)malloc(n);
+    memcpy(m->grid_host, grid_host, n);
+    for (size_t i = 0; i < n; ++i) {
+        uint8_t v = grid_host[i];
+        if (v == 2 && m->start < 0) m->start = (int)i;   // first row-major hit, MAACO.py:32-41
+        if (v == 3 && m->target < 0) m->target = (int)i;
+        if (v == 1) m->n_obstacles++;
+    }
+    m->pitch_words = (cols + 2 + 31) / 32;
+    int words = (rows + 2) * m->pitch_words;
+    m->occ_words = (words + 3) & ~3;
+    MPP_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
+    uint8_t *gdev = nullptr;
+    MPP_CUDA(cudaMalloc(&gdev, n));
+    MPP_CUDA(cudaMalloc(&m->occ_dev, (size_t)m->occ_words * 4));
+    MPP_CUDA(cudaMemcpy(gdev, grid_host, n, cudaMemcpyHostToDevice));
+    mpp_pack_occ_kernel<<<(m->occ_words + 255) / 256, 256>>>(gdev, rows, cols, m->pitch_words, m->occ_words, m->occ_dev);
+    MPP_CUDA(cudaGetLastError());
+    MPP_CUDA(cudaDeviceSynchronize());
+    MPP_CUDA(cudaFree(gdev));
+    *out = m;
+    return MPP_OK;
+}
+
+extern "C" void mpp_map_destroy(mpp_map *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->occ_dev) cudaFree(m->occ_dev);
+    if (m->safety_d2_dev) cudaFree(m->safety_d2_dev);
+    if (m->safety_lut_dev) cudaFree(m->safety_lut_dev);
+    free(m->grid_host);
+    free(m);
+}
+
+extern "C" int mpp_map_rows(const mpp_map *m) { return m ? m->rows : -1; }
+extern "C" int mpp_map_cols(const mpp_map *m) { return m ? m->cols : -1; }
+extern "C" int mpp_map_start(const mpp_map *m) { return m ? m->start : -1; }
+extern "C" int mpp_map_target(const mpp_map *m) { return m ? m->target : -1; }
+extern "C" int mpp_map_device(const mpp_map *m) { return m ? m->device : -1; }
+extern "C" const uint32_t *mpp_map_occ_bits(const mpp_map *m, int *pitch_words) {
+    if (!m) return nullptr;
+    if (pitch_words) *pitch_words = m->pitch_words;
+    return m->occ_dev;
+}

@@ -1,0 +1,221 @@
+"""MAACO -- drop-in for the reference class ``MAACO.MAACO`` (MAACO.py:10-377) whose colony pass
+(tour construction, best tracking, pheromone update) runs as sm_100a kernels behind the C ABI.
+
+Same constructor arguments, attributes and return values as the reference; additive keyword-only
+arguments select the RNG stream seed, the device and the (optional) ``torch.distributed`` group
+over which the colony is sharded.  No CPU fallback: without libmpp_b200.so or a B200 this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import _lib
+from .gridmap import GridMap, START_NODE_VAL, TARGET_NODE_VAL
+
+INF = float("inf")
+
+
+def _fresh_seed():
+    return int.from_bytes(os.urandom(8), "little")
+
+
+class MAACO:
+    def __init__(self, grid, num_ants, num_iterations,
+                 alpha, beta, rho, Q,
+                 a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
+                 C0_initial_pheromone=0.1, *,
+                 rng_seed=None, device=None, max_cells=None, lanes_per_ant=0, group=None, verbose=True):
+        import torch
+        self.grid = np.array(grid, dtype=int)                       # MAACO.py:15
+        self.rows, self.cols = self.grid.shape
+        self.num_ants = num_ants
+        self.num_iterations = num_iterations
+        self.alpha, self.beta, self.rho, self.Q = alpha, beta, rho, Q
+        self.a_turn_coef, self.wh_max, self.wh_min = a_turn_coef, wh_max, wh_min
+        self.k_h_adaptive, self.q0_initial = k_h_adaptive, q0_initial
+        self.k0_iter_threshold_factor = 0.7
+        self.C0_base = C0_initial_pheromone
+        s = np.argwhere(self.grid == START_NODE_VAL)
+        t = np.argwhere(self.grid == TARGET_NODE_VAL)
+        if not s.size > 0:
+            raise ValueError("MAACO: Start node not found.")       # MAACO.py:35-36
+        if not t.size > 0:
+            raise ValueError("MAACO: Target node not found.")      # MAACO.py:37-38
+        self.start_node = (int(s[0][0]), int(s[0][1]))
+        self.target_node = (int(t[0][0]), int(t[0][1]))
+        d = math.sqrt((self.start_node[0] - self.target_node[0]) ** 2 + (self.start_node[1] - self.target_node[1]) ** 2)
+        self.dist_S_to_T_overall = d if d >= 1e-9 else 1e-9
+        self.rng_seed = _fresh_seed() if rng_seed is None else int(rng_seed)
+        self.verbose = verbose
+        self.lanes_per_ant = lanes_per_ant
+
+        # ---- sharding of the colony over the process group (ants are independent given tau) ----
+        self.group = group
+        if group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        else:
+            self.world, self.rank = 1, 0
+        if num_ants % self.world:
+            raise ValueError("num_ants must be divisible by the group size")
+        self.n_local = num_ants // self.world
+        self.ant_offset = self.rank * self.n_local
+
+        L = _lib.lib()
+        self.map = GridMap(self.grid, device=device)
+        self.device = torch.device("cuda", self.map.device)
+        n = self.rows * self.cols
+        self.n_words = (n + 31) // 32
+        if max_cells is None:
+            max_cells = n
+            if self.n_local * n * 4 > (8 << 30):                    # keep the path buffer under 8 GiB
+                max_cells = max(1024, min(n, (8 << 30) // (4 * self.n_local)))
+        self.max_cells = int(max_cells)
+        dev = self.device
+        f64, i32 = torch.float64, torch.int32
+        self._tau = torch.empty(n, dtype=f64, device=dev)
+        self._E0 = torch.empty(n, dtype=f64, device=dev)
+        self._E1 = torch.empty(n, dtype=f64, device=dev)
+        self._dist_t = torch.empty(n, dtype=f64, device=dev)
+        self._params = _lib.MaacoParams(alpha, beta, rho, Q, a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
+                                        C0_initial_pheromone, num_iterations)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.mpp_maaco_tables(self.map.handle, C.byref(self._params), _lib.ptr(self._tau), _lib.ptr(self._E0),
+                                      _lib.ptr(self._E1), _lib.ptr(self._dist_t), C.c_void_p(stream)),
+                   "mpp_maaco_tables")
+        # word-major visited bitmaps for ALL ants of the colony (remote ants are filled by the exchange)
+        self._visitT = torch.zeros(self.n_words * num_ants, dtype=i32, device=dev)
+        self._cells = torch.zeros(self.n_local * self.max_cells, dtype=i32, device=dev)
+        self._n_cells = torch.zeros(num_ants, dtype=i32, device=dev)
+        self._length = torch.zeros(num_ants, dtype=f64, device=dev)
+        self._turns = torch.zeros(num_ants, dtype=i32, device=dev)
+        self._deposit = torch.zeros(num_ants, dtype=f64, device=dev)
+        self._best_cells = torch.zeros(self.max_cells, dtype=i32, device=dev)
+        self._steps = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._log = torch.zeros(max(1, num_iterations) * 4, dtype=f64, device=dev)
+        st = _lib.MaacoState(INF, -1, 0, 0, -1, INF, -1, -1)
+        self._state = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(dev)
+
+        self.best_path_overall = []
+        self.best_path_length_overall = INF
+        self.best_path_turns_overall = INF
+        self.convergence_curve_data = []
+        self._iter_done = 0
+
+    # ---- reference attributes materialised from device state ------------------------------
+    @property
+    def pheromone_matrix(self):
+        return self._tau.cpu().numpy().reshape(self.rows, self.cols)
+
+    @property
+    def dist_to_target_matrix(self):
+        return self._dist_t.cpu().numpy().reshape(self.rows, self.cols)
+
+    def _calculate_adaptive_q0(self, current_iteration_num):
+        return _lib.lib().mpp_maaco_q0(self.num_iterations, int(current_iteration_num), self.q0_initial)
+
+    # ---- one colony pass (MAACO.py:336-359), fully asynchronous ----------------------------
+    def _enqueue_iteration(self, it):
+        import torch
+        L = _lib.lib()
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        q0 = self._calculate_adaptive_q0(it)
+        nl, off = self.n_local, self.ant_offset
+        if self.world == 1:
+            visit_local = self._visitT
+        else:
+            visit_local = self._visit_local
+        _lib.check(L.mpp_maaco_tours(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E0), _lib.ptr(self._E1),
+                                     it, q0, self.alpha, nl, off, C.c_uint64(self.rng_seed),
+                                     _lib.ptr(visit_local), _lib.ptr(self._cells), self.max_cells,
+                                     C.c_void_p(self._n_cells.data_ptr() + 4 * off),
+                                     C.c_void_p(self._length.data_ptr() + 8 * off),
+                                     C.c_void_p(self._turns.data_ptr() + 4 * off),
+                                     _lib.ptr(self._steps), self.lanes_per_ant, stream), "mpp_maaco_tours")
+        if self.world > 1:
+            self._exchange()
+        _lib.check(L.mpp_maaco_best(_lib.ptr(self._length), _lib.ptr(self._turns), _lib.ptr(self._n_cells),
+                                    _lib.ptr(self._cells_all()), self.max_cells, self.num_ants, self.Q, it,
+                                    _lib.ptr(self._state), _lib.ptr(self._best_cells), _lib.ptr(self._deposit),
+                                    _lib.ptr(self._log), stream), "mpp_maaco_best")
+        _lib.check(L.mpp_maaco_pheromone(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._visitT),
+                                         _lib.ptr(self._deposit), self.num_ants, self.rho, _lib.ptr(self._state), 1,
+                                         stream), "mpp_maaco_pheromone")
+
+    def _cells_all(self):
+        return self._cells
+
+    def _exchange(self):  # overridden by the sharded colony (dist.py)
+        raise NotImplementedError
+
+    def _read_state(self):
+        st = _lib.MaacoState.from_buffer_copy(self._state.cpu().numpy().tobytes())
+        return st
+
+    def solve_path_planning(self):
+        import torch
+        K = self.num_iterations
+        for it in range(self._iter_done + 1, K + 1):
+            self._enqueue_iteration(it)
+        torch.cuda.synchronize(self.device)
+        self._iter_done = K
+        st = self._read_state()
+        log = self._log.cpu().numpy().reshape(-1, 4)[:K]
+        if st.best_n_cells > self.max_cells:
+            raise _lib.MppError(f"best path has {st.best_n_cells} cells but max_cells={self.max_cells}; "
+                                "re-run with a larger max_cells")
+        cells = self._best_cells[:st.best_n_cells].cpu().numpy()
+        self.best_path_overall = [(int(c) // self.cols, int(c) % self.cols) for c in cells]
+        self.best_path_length_overall = float(st.best_len)
+        self.best_path_turns_overall = int(st.best_turns) if st.best_turns >= 0 else INF
+        self.convergence_curve_data = [float(r[2]) if r[2] != INF else None for r in log]  # MAACO.py:360-362
+        if self.verbose and self.rank == 0:
+            tfmt = lambda v: int(v) if v >= 0 else INF
+            for it in range(1, K + 1):                               # MAACO.py:363-366 (printed after the run)
+                if it % 10 == 0 or it == 1 or it == K:
+                    r = log[it - 1]
+                    print(f"MAACO Iter {it}/{K}: Iter Best L={r[0]:.2f}, T={tfmt(r[1])}, "
+                          f"Overall Best L={r[2]:.2f}, T={tfmt(r[3])}")
+            if self.best_path_overall:
+                print(f"\nMAACO Solved: Length={self.best_path_length_overall:.2f}, "
+                      f"Turns={self.best_path_turns_overall}")
+            else:
+                print("\nMAACO: No solution found.")
+        return self.best_path_overall, self.best_path_length_overall, self.best_path_turns_overall
+
+    # ---- per-iteration access used by the parity tests and the benchmark -------------------
+    def run_iteration(self, it):
+        """Enqueue one colony pass; returns nothing (read results with `last_tours`)."""
+        self._enqueue_iteration(it)
+        self._iter_done = max(self._iter_done, it)
+
+    def last_tours(self):
+        """(n_cells, length, turns, cells[n_local, max_cells]) of the last pass, as numpy arrays."""
+        import torch
+        torch.cuda.synchronize(self.device)
+        return (self._n_cells.cpu().numpy(), self._length.cpu().numpy(), self._turns.cpu().numpy(),
+                self._cells.cpu().numpy().reshape(self.n_local, self.max_cells))
+
+    def total_steps(self):
+        return int(self._steps.cpu().item())
+
+    # ---- plotting hooks of the reference (MAACO.py:373-377): out of scope, forwarded if possible --
+    def visualize_pheromone_matrix(self, title="Mức Pheromone MAACO"):
+        try:
+            from visualization import visualize_pheromone_matrix as viz
+        except Exception:
+            print("visualization/matplotlib not available; pheromone_matrix is exposed as an ndarray")
+            return
+        viz(self.grid, self.pheromone_matrix, title)
+
+    def plot_convergence_curve(self):
+        try:
+            from visualization import plot_convergence_curve as viz
+        except Exception:
+            print("visualization/matplotlib not available; convergence_curve_data is exposed as a list")
+            return
+        viz(self.convergence_curve_data, "MAACO", color='orangered')
