@@ -57,8 +57,7 @@ int mpp_device_count(void);
 /* ---- grid map: env.py grid convention (0 free, 1 obstacle, 2 start, 3 target) ------------
  * replaces: np.array(grid) + argwhere(grid==2/3) in every constructor
  * (MAACO.py:15-41, helper.py:121-125, astar.py:17-22, pso.py:17-22, ga_solver.py:17-22, MPA.py:20-43).
- * grid_host: rows*cols bytes, row-major.  Start/target = first row-major 2 / 3; pass
- * start=-1/target=-1 to mpp_map_create_ex to take them from the grid.  Synchronous. */
+ * grid_host: rows*cols bytes, row-major.  Start/target = first row-major 2 / 3.  Synchronous. */
 int mpp_map_create(const uint8_t *grid_host, int rows, int cols, int device, mpp_map **out);
 void mpp_map_destroy(mpp_map *map);
 int mpp_map_rows(const mpp_map *map);
@@ -87,6 +86,13 @@ int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, double *tau0
 /* replaces MAACO._calculate_adaptive_q0 (MAACO.py:212-226); pure host function */
 double mpp_maaco_q0(int num_iterations, int iteration, double q0_initial);
 
+/* per-ant outcome of one tour (MAACO.py:300-302): failed ants have n_cells=0, length=+inf, turns=-1 */
+typedef struct {
+    double length;
+    int32_t n_cells;
+    int32_t turns;
+} mpp_ant_result;
+
 /* replaces the ant loop MAACO.py:340-342 -> _construct_ant_solution_maaco (:278-302) with the
  * orientation filter + crossing-prohibition (:100-181) and pseudo-random-proportional selection
  * (:228-262).  Ant i of this call is global ant `ant_offset + i` (its RNG stream id).
@@ -94,13 +100,14 @@ double mpp_maaco_q0(int num_iterations, int iteration, double q0_initial);
  *   visitT_dev     word-major visited bitmaps: word w of ant i at [w*n_ants + i], ceil(rows*cols/32)
  *                  words per ant; MUST be zero on entry; holds each ant's visited set on return
  *   cells_dev      n_ants x max_cells path cells (cells beyond max_cells are dropped; n_cells still
- *                  counts them); n_cells=0, length=+inf, turns=-1 for a failed ant (:288,:292,:302)
+ *                  counts them)
+ *   result_dev     n_ants x mpp_ant_result (:288,:292,:300-302)
+ *   steps_dev      optional counter, += number of ant steps taken
  *   lanes_per_ant  8 or 32 (0 = choose)                                                          */
 int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E0_dev, const double *E1_dev,
                     int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
-                    uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, int32_t *n_cells_dev,
-                    double *length_dev, int32_t *turns_dev, unsigned long long *steps_dev, int lanes_per_ant,
-                    void *stream);
+                    uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, mpp_ant_result *result_dev,
+                    unsigned long long *steps_dev, int lanes_per_ant, void *stream);
 
 /* colony state kept on the device so an entire solve can be enqueued without host syncs */
 typedef struct {
@@ -115,22 +122,26 @@ typedef struct {
 } mpp_maaco_state;
 
 /* replaces the order-dependent best tracking MAACO.py:343-358 for one iteration over all
- * n_ants (in global ant order) and prepares the per-ant deposit Q/length (:307-308; 0 for ants
- * that do not deposit).  Updates *state_dev, copies the new overall-best path into
- * best_cells_dev (capacity max_cells) and appends to the per-iteration logs
+ * n_ants results (in global ant order) and prepares the per-ant deposit Q/length (:307-308; 0 for
+ * ants that do not deposit).  Updates *state_dev and appends to the per-iteration log
  * log_dev[4*(iteration-1) + {0: iter best len, 1: iter best turns, 2: overall len, 3: overall turns}]
- * (log_dev may be NULL). */
-int mpp_maaco_best(const double *length_dev, const int32_t *turns_dev, const int32_t *n_cells_dev,
-                   const int32_t *cells_dev, int max_cells, int n_ants, double Q, int iteration,
-                   mpp_maaco_state *state_dev, int32_t *best_cells_dev, double *deposit_dev, double *log_dev,
-                   void *stream);
+ * (log_dev may be NULL).  cells_dev holds the paths of ants [cells_ant_offset, cells_ant_offset +
+ * cells_n_ants) (a sharded colony keeps only its own); the new overall-best path is copied into
+ * best_cells_dev (capacity max_cells) when the best ant lies in that range. */
+int mpp_maaco_best(const mpp_ant_result *result_dev, const int32_t *cells_dev, int max_cells, int cells_ant_offset,
+                   int cells_n_ants, int n_ants, double Q, int iteration, mpp_maaco_state *state_dev,
+                   int32_t *best_cells_dev, double *deposit_dev, double *log_dev, void *stream);
 
-/* replaces MAACO._update_pheromone_trails_maaco (MAACO.py:304-332): evaporate, deposit in global
- * ant order (bit-exact, atomics-free: one warp per 32 cells walks the visited words of all ants),
- * MMAS clip with tau_max from state->best_len, obstacles <- 1e-9.  Clears visitT_dev behind itself
- * when clear_visit != 0. */
+/* replaces MAACO._update_pheromone_trails_maaco (MAACO.py:304-332) for the cells of bitmap words
+ * [word0, word0 + n_words): evaporate, deposit in global ant order (bit-exact, atomics-free: one warp
+ * per 32 cells streams the visited words of every ant), MMAS clip with tau_max from state->best_len,
+ * obstacles <- 1e-9.  visitT_dev is [n_seg][n_words][seg_ants] (word-major per segment; global ant =
+ * seg*seg_ants + a; one segment per source rank in a sharded colony; n_seg=1, word0=0,
+ * n_words=ceil(rows*cols/32) on a single GPU); deposit_dev is indexed by global ant.  Clears
+ * visitT_dev behind itself when clear_visit != 0. */
 int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t *visitT_dev, const double *deposit_dev,
-                        int n_ants, double rho, const mpp_maaco_state *state_dev, int clear_visit, void *stream);
+                        int n_seg, int seg_ants, int word0, int n_words, double rho,
+                        const mpp_maaco_state *state_dev, int clear_visit, void *stream);
 
 #ifdef __cplusplus
 }

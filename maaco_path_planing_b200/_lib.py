@@ -52,12 +52,11 @@ _SIGS = {
     "mpp_maaco_tables": (c_int, [c_void_p, C.POINTER(MaacoParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpp_maaco_q0": (c_double, [c_int, c_int, c_double]),
     "mpp_maaco_tours": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_int, c_int,
-                                c_u64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                c_void_p]),
-    "mpp_maaco_best": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_void_p,
+                                c_u64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "mpp_maaco_best": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mpp_maaco_pheromone": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_int,
-                                    c_void_p]),
+    "mpp_maaco_pheromone": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double,
+                                    c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

@@ -109,9 +109,7 @@ struct TourArgs {
     uint32_t *visitT;
     int32_t *cells;
     int max_cells;
-    int32_t *n_cells;
-    double *length;
-    int32_t *turns;
+    mpp_ant_result *result;
     unsigned long long *steps;
 };
 
@@ -304,19 +302,20 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, 4) mpp_maaco_tour_kernel(con
     }
     if (m == 0) {
         const bool ok = !failed && cr == tr && cc == tc;
-        A.n_cells[a] = ok ? n_path : 0;
-        A.length[a] = ok ? len : __longlong_as_double(0x7ff0000000000000ll);
-        A.turns[a] = ok ? turns : -1;
+        mpp_ant_result res;
+        res.length = ok ? len : __longlong_as_double(0x7ff0000000000000ll);
+        res.n_cells = ok ? n_path : 0;
+        res.turns = ok ? turns : -1;
+        A.result[a] = res;
         if (A.steps) atomicAdd(A.steps, (unsigned long long)steps);
     }
 }
 
 extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E0_dev, const double *E1_dev,
                                int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
-                               uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, int32_t *n_cells_dev,
-                               double *length_dev, int32_t *turns_dev, unsigned long long *steps_dev,
-                               int lanes_per_ant, void *stream) {
-    MPP_REQUIRE(map && tau_dev && E0_dev && E1_dev && visitT_dev && cells_dev && n_cells_dev && length_dev && turns_dev,
+                               uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, mpp_ant_result *result_dev,
+                               unsigned long long *steps_dev, int lanes_per_ant, void *stream) {
+    MPP_REQUIRE(map && tau_dev && E0_dev && E1_dev && visitT_dev && cells_dev && result_dev,
                 "mpp_maaco_tours: null argument");
     MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_tours: map has no start/target");
     MPP_REQUIRE(n_ants > 0 && max_cells > 0, "mpp_maaco_tours: n_ants=%d max_cells=%d", n_ants, max_cells);
@@ -331,7 +330,7 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
     A.n_ants = n_ants; A.ant_offset = ant_offset;
     A.k0 = (uint32_t)seed; A.k1 = (uint32_t)(seed >> 32);
     A.visitT = visitT_dev; A.cells = cells_dev; A.max_cells = max_cells;
-    A.n_cells = n_cells_dev; A.length = length_dev; A.turns = turns_dev; A.steps = steps_dev;
+    A.result = result_dev; A.steps = steps_dev;
     const size_t smem = (size_t)map->occ_words * 4;
     const bool in_smem = smem <= 200 * 1024;
     const int ants_per_block = MPP_TOUR_THREADS / lanes_per_ant;
@@ -359,10 +358,9 @@ __device__ __forceinline__ bool lt_len_idx(double la, int ia, double lb, int ib)
 }
 
 __global__ void __launch_bounds__(MPP_BEST_THREADS)
-mpp_maaco_best_kernel(const double *__restrict__ length, const int32_t *__restrict__ turns,
-                      const int32_t *__restrict__ n_cells, const int32_t *__restrict__ cells, int max_cells, int n,
-                      double Q, int iteration, mpp_maaco_state *state, int32_t *best_cells, double *deposit,
-                      double *log) {
+mpp_maaco_best_kernel(const mpp_ant_result *__restrict__ res, const int32_t *__restrict__ cells, int max_cells,
+                      int cells_ant_offset, int cells_n_ants, int n, double Q, int iteration, mpp_maaco_state *state,
+                      int32_t *best_cells, double *deposit, double *log) {
     __shared__ double s_len[32];
     __shared__ int s_idx[32];
     __shared__ int s_t[32];
@@ -374,10 +372,11 @@ mpp_maaco_best_kernel(const double *__restrict__ length, const int32_t *__restri
     double ml = INF;
     int mi = 0x7fffffff;
     for (int i = tid; i < n; i += MPP_BEST_THREADS) {
-        const double l = length[i];
+        const mpp_ant_result ri = res[i];
+        const double l = ri.length;
         if (lt_len_idx(l, i, ml, mi)) { ml = l; mi = i; }
         // deposit amount MAACO.py:307-308 (0.0 == "does not deposit"; x + 0.0 is exact anyway)
-        deposit[i] = (l != INF && n_cells[i] > 0 && l > 1e-6) ? Q / l : 0.0;
+        deposit[i] = (l != INF && ri.n_cells > 0 && l > 1e-6) ? Q / l : 0.0;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -405,9 +404,10 @@ mpp_maaco_best_kernel(const double *__restrict__ length, const int32_t *__restri
     if (L != INF) {
         for (int i = tid; i < n; i += MPP_BEST_THREADS) {
             if (i < r) continue;
-            const double l = length[i];
+            const mpp_ant_result ri = res[i];
+            const double l = ri.length;
             if (i == r || fabs(l - L) < 1e-9) {
-                const int t = turns[i];
+                const int t = ri.turns;
                 if (t >= 0 && (t < bt || (t == bt && i < bi))) { bt = t; bi = i; }
             }
         }
@@ -440,7 +440,7 @@ mpp_maaco_best_kernel(const double *__restrict__ length, const int32_t *__restri
                     if (bt < st.best_turns) { st.best_turns = bt; copy = 1; }
                 }
             }
-            if (copy) { st.best_n_cells = n_cells[bi]; st.best_iter = iteration; st.best_ant = bi; }
+            if (copy) { st.best_n_cells = res[bi].n_cells; st.best_iter = iteration; st.best_ant = bi; }
             st.iter_best_len = L; st.iter_best_turns = b_turns; st.iter_best_ant = b_ant;
             *state = st;
             b_copy = copy;
@@ -451,25 +451,26 @@ mpp_maaco_best_kernel(const double *__restrict__ length, const int32_t *__restri
         }
     }
     __syncthreads();
-    if (b_copy) {
-        const int a = b_ant;
-        int nc = n_cells[a];
+    // the path is copied only by the rank that owns the ant (sharded colony: cells holds ants
+    // [cells_ant_offset, cells_ant_offset + cells_n_ants)); the owner broadcasts it after the solve
+    if (b_copy && b_ant >= cells_ant_offset && b_ant < cells_ant_offset + cells_n_ants) {
+        const int a = b_ant - cells_ant_offset;
+        int nc = res[b_ant].n_cells;
         if (nc > max_cells) nc = max_cells;
         const int32_t *src = cells + (size_t)a * max_cells;
         for (int k = tid; k < nc; k += MPP_BEST_THREADS) best_cells[k] = src[k];
     }
 }
 
-extern "C" int mpp_maaco_best(const double *length_dev, const int32_t *turns_dev, const int32_t *n_cells_dev,
-                              const int32_t *cells_dev, int max_cells, int n_ants, double Q, int iteration,
+extern "C" int mpp_maaco_best(const mpp_ant_result *result_dev, const int32_t *cells_dev, int max_cells,
+                              int cells_ant_offset, int cells_n_ants, int n_ants, double Q, int iteration,
                               mpp_maaco_state *state_dev, int32_t *best_cells_dev, double *deposit_dev,
                               double *log_dev, void *stream) {
-    MPP_REQUIRE(length_dev && turns_dev && n_cells_dev && cells_dev && state_dev && best_cells_dev && deposit_dev,
-                "mpp_maaco_best: null argument");
+    MPP_REQUIRE(result_dev && cells_dev && state_dev && best_cells_dev && deposit_dev, "mpp_maaco_best: null argument");
     MPP_REQUIRE(n_ants > 0 && iteration >= 1, "mpp_maaco_best: n_ants=%d iteration=%d", n_ants, iteration);
     mpp_maaco_best_kernel<<<1, MPP_BEST_THREADS, 0, (cudaStream_t)stream>>>(
-        length_dev, turns_dev, n_cells_dev, cells_dev, max_cells, n_ants, Q, iteration, state_dev, best_cells_dev,
-        deposit_dev, log_dev);
+        result_dev, cells_dev, max_cells, cells_ant_offset, cells_n_ants, n_ants, Q, iteration, state_dev,
+        best_cells_dev, deposit_dev, log_dev);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
@@ -482,17 +483,23 @@ extern "C" int mpp_maaco_best(const double *length_dev, const int32_t *turns_dev
 #define MPP_PHER_THREADS 256
 __global__ void __launch_bounds__(MPP_PHER_THREADS)
 mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
-                           uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_ants, double rho,
-                           const mpp_maaco_state *__restrict__ state, int clear_visit, int n_words) {
+                           uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg, int seg_ants,
+                           int word0, int n_words, double rho, const mpp_maaco_state *__restrict__ state,
+                           int clear_visit) {
+    // visitT is [n_seg][n_words][seg_ants]; global ant = seg*seg_ants + a; this launch owns the
+    // cells of words [word0, word0 + n_words)
     const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * MPP_PHER_THREADS + threadIdx.x) >> 5;
-    if (w >= n_words) return;
+    const int wl = (blockIdx.x * MPP_PHER_THREADS + threadIdx.x) >> 5;
+    if (wl >= n_words) return;
     const int RC = R * C;
-    const int cell = w * 32 + lane;
+    const int cell = (word0 + wl) * 32 + lane;
     const bool live = cell < RC;
+    const int n_ants = seg_ants;
     double t = 0.0;
     if (live) t = tau[cell] * (1.0 - rho);                                   // :305
-    uint32_t *row = visitT + (size_t)w * n_ants;
+    for (int seg = 0; seg < n_seg; ++seg) {
+    uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
+    const double *dep = deposit + (size_t)seg * seg_ants;
     for (int a0 = 0; a0 < n_ants; a0 += 128) {
         uint32_t wd[4];
 #pragma unroll
@@ -505,7 +512,7 @@ mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, i
             uint32_t nz = __ballot_sync(0xffffffffu, wd[u] != 0u);
             if (nz) {
                 const int a = a0 + u * 32 + lane;
-                const double d = (a < n_ants) ? deposit[a] : 0.0;
+                const double d = (a < n_ants) ? dep[a] : 0.0;
                 if (clear_visit && wd[u] != 0u) row[a] = 0u;
                 while (nz) {                                                  // ants in index order :306
                     const int l = __ffs(nz) - 1;
@@ -516,6 +523,7 @@ mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, i
                 }
             }
         }
+    }
     }
     if (!live) return;
     double b = state->best_len;                                               // :312-316
@@ -533,17 +541,16 @@ mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, i
 }
 
 extern "C" int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t *visitT_dev,
-                                   const double *deposit_dev, int n_ants, double rho,
-                                   const mpp_maaco_state *state_dev, int clear_visit, void *stream) {
+                                   const double *deposit_dev, int n_seg, int seg_ants, int word0, int n_words,
+                                   double rho, const mpp_maaco_state *state_dev, int clear_visit, void *stream) {
     MPP_REQUIRE(map && tau_dev && visitT_dev && deposit_dev && state_dev, "mpp_maaco_pheromone: null argument");
-    MPP_REQUIRE(n_ants > 0, "mpp_maaco_pheromone: n_ants=%d", n_ants);
+    MPP_REQUIRE(n_seg > 0 && seg_ants > 0 && word0 >= 0 && n_words > 0, "mpp_maaco_pheromone: bad shape");
     MPP_CUDA(cudaSetDevice(map->device));
-    const int n_words = (map->rows * map->cols + 31) / 32;
     const int warps_per_block = MPP_PHER_THREADS / 32;
     const int blocks = (n_words + warps_per_block - 1) / warps_per_block;
     mpp_maaco_pheromone_kernel<<<blocks, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
-        map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_ants, rho, state_dev,
-        clear_visit, n_words);
+        map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants, word0,
+        n_words, rho, state_dev, clear_visit);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }

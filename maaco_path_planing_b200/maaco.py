@@ -14,6 +14,8 @@ import os
 import numpy as np
 
 from . import _lib
+from . import dist as dist_mod
+from .dist import padded_words
 from .gridmap import GridMap, START_NODE_VAL, TARGET_NODE_VAL
 
 INF = float("inf")
@@ -69,15 +71,17 @@ class MAACO:
         self.map = GridMap(self.grid, device=device)
         self.device = torch.device("cuda", self.map.device)
         n = self.rows * self.cols
-        self.n_words = (n + 31) // 32
+        self.n_words = padded_words(n, self.world)                  # bitmap words per ant (padded to split evenly)
+        self.words_per_rank = self.n_words // self.world
         if max_cells is None:
             max_cells = n
             if self.n_local * n * 4 > (8 << 30):                    # keep the path buffer under 8 GiB
                 max_cells = max(1024, min(n, (8 << 30) // (4 * self.n_local)))
         self.max_cells = int(max_cells)
         dev = self.device
-        f64, i32 = torch.float64, torch.int32
-        self._tau = torch.empty(n, dtype=f64, device=dev)
+        f64, i32, i64 = torch.float64, torch.int32, torch.int64
+        npad = self.n_words * 32
+        self._tau = torch.zeros(npad, dtype=f64, device=dev)        # padded so tau slices all-gather evenly
         self._E0 = torch.empty(n, dtype=f64, device=dev)
         self._E1 = torch.empty(n, dtype=f64, device=dev)
         self._dist_t = torch.empty(n, dtype=f64, device=dev)
@@ -87,15 +91,16 @@ class MAACO:
         _lib.check(L.mpp_maaco_tables(self.map.handle, C.byref(self._params), _lib.ptr(self._tau), _lib.ptr(self._E0),
                                       _lib.ptr(self._E1), _lib.ptr(self._dist_t), C.c_void_p(stream)),
                    "mpp_maaco_tables")
-        # word-major visited bitmaps for ALL ants of the colony (remote ants are filled by the exchange)
-        self._visitT = torch.zeros(self.n_words * num_ants, dtype=i32, device=dev)
+        # word-major visited bitmaps of the local ants: [n_words][n_local]
+        self._visit_local = torch.zeros(self.n_words * self.n_local, dtype=i32, device=dev)
+        if self.world > 1:
+            self._visit_recv = torch.empty(self.n_words * self.n_local, dtype=i32, device=dev)  # [G][Wn][n_local]
+            self._tau_slice = torch.empty(self.words_per_rank * 32, dtype=f64, device=dev)
         self._cells = torch.zeros(self.n_local * self.max_cells, dtype=i32, device=dev)
-        self._n_cells = torch.zeros(num_ants, dtype=i32, device=dev)
-        self._length = torch.zeros(num_ants, dtype=f64, device=dev)
-        self._turns = torch.zeros(num_ants, dtype=i32, device=dev)
+        self._result = torch.zeros((num_ants, 2), dtype=i64, device=dev)   # mpp_ant_result per global ant
         self._deposit = torch.zeros(num_ants, dtype=f64, device=dev)
         self._best_cells = torch.zeros(self.max_cells, dtype=i32, device=dev)
-        self._steps = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._steps = torch.zeros(1, dtype=i64, device=dev)
         self._log = torch.zeros(max(1, num_iterations) * 4, dtype=f64, device=dev)
         st = _lib.MaacoState(INF, -1, 0, 0, -1, INF, -1, -1)
         self._state = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(dev)
@@ -105,11 +110,13 @@ class MAACO:
         self.best_path_turns_overall = INF
         self.convergence_curve_data = []
         self._iter_done = 0
+        self.kernel_launches = 0
 
     # ---- reference attributes materialised from device state ------------------------------
     @property
     def pheromone_matrix(self):
-        return self._tau.cpu().numpy().reshape(self.rows, self.cols)
+        n = self.rows * self.cols
+        return self._tau[:n].cpu().numpy().reshape(self.rows, self.cols)
 
     @property
     def dist_to_target_matrix(self):
@@ -119,38 +126,49 @@ class MAACO:
         return _lib.lib().mpp_maaco_q0(self.num_iterations, int(current_iteration_num), self.q0_initial)
 
     # ---- one colony pass (MAACO.py:336-359), fully asynchronous ----------------------------
+    def _enqueue_tours(self, it, stream):
+        nl, off = self.n_local, self.ant_offset
+        _lib.check(_lib.lib().mpp_maaco_tours(
+            self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E0), _lib.ptr(self._E1), it,
+            self._calculate_adaptive_q0(it), self.alpha, nl, off, C.c_uint64(self.rng_seed),
+            _lib.ptr(self._visit_local), _lib.ptr(self._cells), self.max_cells,
+            C.c_void_p(self._result.data_ptr() + 16 * off), _lib.ptr(self._steps), self.lanes_per_ant, stream),
+            "mpp_maaco_tours")
+
+    def _enqueue_best(self, it, stream):
+        _lib.check(_lib.lib().mpp_maaco_best(
+            _lib.ptr(self._result), _lib.ptr(self._cells), self.max_cells, self.ant_offset, self.n_local,
+            self.num_ants, self.Q, it, _lib.ptr(self._state), _lib.ptr(self._best_cells), _lib.ptr(self._deposit),
+            _lib.ptr(self._log), stream), "mpp_maaco_best")
+
+    def _enqueue_pheromone(self, stream):
+        L = _lib.lib()
+        if self.world == 1:
+            _lib.check(L.mpp_maaco_pheromone(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._visit_local),
+                                             _lib.ptr(self._deposit), 1, self.num_ants, 0, self.n_words, self.rho,
+                                             _lib.ptr(self._state), 1, stream), "mpp_maaco_pheromone")
+        else:
+            wn = self.words_per_rank
+            _lib.check(L.mpp_maaco_pheromone(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._visit_recv),
+                                             _lib.ptr(self._deposit), self.world, self.n_local, self.rank * wn, wn,
+                                             self.rho, _lib.ptr(self._state), 0, stream), "mpp_maaco_pheromone")
+
     def _enqueue_iteration(self, it):
         import torch
-        L = _lib.lib()
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        q0 = self._calculate_adaptive_q0(it)
-        nl, off = self.n_local, self.ant_offset
-        if self.world == 1:
-            visit_local = self._visitT
-        else:
-            visit_local = self._visit_local
-        _lib.check(L.mpp_maaco_tours(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E0), _lib.ptr(self._E1),
-                                     it, q0, self.alpha, nl, off, C.c_uint64(self.rng_seed),
-                                     _lib.ptr(visit_local), _lib.ptr(self._cells), self.max_cells,
-                                     C.c_void_p(self._n_cells.data_ptr() + 4 * off),
-                                     C.c_void_p(self._length.data_ptr() + 8 * off),
-                                     C.c_void_p(self._turns.data_ptr() + 4 * off),
-                                     _lib.ptr(self._steps), self.lanes_per_ant, stream), "mpp_maaco_tours")
+        self._enqueue_tours(it, stream)
         if self.world > 1:
-            self._exchange()
-        _lib.check(L.mpp_maaco_best(_lib.ptr(self._length), _lib.ptr(self._turns), _lib.ptr(self._n_cells),
-                                    _lib.ptr(self._cells_all()), self.max_cells, self.num_ants, self.Q, it,
-                                    _lib.ptr(self._state), _lib.ptr(self._best_cells), _lib.ptr(self._deposit),
-                                    _lib.ptr(self._log), stream), "mpp_maaco_best")
-        _lib.check(L.mpp_maaco_pheromone(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._visitT),
-                                         _lib.ptr(self._deposit), self.num_ants, self.rho, _lib.ptr(self._state), 1,
-                                         stream), "mpp_maaco_pheromone")
-
-    def _cells_all(self):
-        return self._cells
-
-    def _exchange(self):  # overridden by the sharded colony (dist.py)
-        raise NotImplementedError
+            nl, off = self.n_local, self.ant_offset
+            dist_mod.exchange_results(self._result, self._result[off:off + nl].clone(), self.group)
+            dist_mod.exchange_visit_slices(self._visit_recv, self._visit_local, self.group)
+            self._visit_local.zero_()
+        self._enqueue_best(it, stream)
+        self._enqueue_pheromone(stream)
+        if self.world > 1:
+            wn32 = self.words_per_rank * 32
+            self._tau_slice.copy_(self._tau[self.rank * wn32:(self.rank + 1) * wn32])
+            dist_mod.gather_tau(self._tau, self._tau_slice, self.group)
+        self.kernel_launches += 3
 
     def _read_state(self):
         st = _lib.MaacoState.from_buffer_copy(self._state.cpu().numpy().tobytes())
@@ -168,6 +186,11 @@ class MAACO:
         if st.best_n_cells > self.max_cells:
             raise _lib.MppError(f"best path has {st.best_n_cells} cells but max_cells={self.max_cells}; "
                                 "re-run with a larger max_cells")
+        if self.world > 1 and st.best_n_cells > 0:
+            import torch.distributed as dist
+            owner = st.best_ant // self.n_local                     # rank that constructed the best ant
+            dist.broadcast(self._best_cells, src=dist.get_global_rank(self.group, owner), group=self.group)
+            torch.cuda.synchronize(self.device)
         cells = self._best_cells[:st.best_n_cells].cpu().numpy()
         self.best_path_overall = [(int(c) // self.cols, int(c) % self.cols) for c in cells]
         self.best_path_length_overall = float(st.best_len)
@@ -193,12 +216,19 @@ class MAACO:
         self._enqueue_iteration(it)
         self._iter_done = max(self._iter_done, it)
 
-    def last_tours(self):
-        """(n_cells, length, turns, cells[n_local, max_cells]) of the last pass, as numpy arrays."""
+    def last_results(self):
+        """(n_cells, length, turns) of every ant of the colony in the last pass (numpy)."""
         import torch
         torch.cuda.synchronize(self.device)
-        return (self._n_cells.cpu().numpy(), self._length.cpu().numpy(), self._turns.cpu().numpy(),
-                self._cells.cpu().numpy().reshape(self.n_local, self.max_cells))
+        raw = self._result.cpu().numpy()
+        rec = raw.view(np.dtype([("length", "<f8"), ("n_cells", "<i4"), ("turns", "<i4")])).reshape(-1)
+        return rec["n_cells"].copy(), rec["length"].copy(), rec["turns"].copy()
+
+    def last_tours(self):
+        """(n_cells, length, turns, cells[n_local, max_cells]) of this rank's ants in the last pass."""
+        nc, ln, tn = self.last_results()
+        sl = slice(self.ant_offset, self.ant_offset + self.n_local)
+        return nc[sl], ln[sl], tn[sl], self._cells.cpu().numpy().reshape(self.n_local, self.max_cells)
 
     def total_steps(self):
         return int(self._steps.cpu().item())

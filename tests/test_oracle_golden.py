@@ -1,0 +1,47 @@
+"""The C oracle (oracle/mpp_oracle.c) against golden vectors produced by the unmodified reference
+under the injected Philox streams (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+import pyoracle as O
+from conftest import MAACO_CASES, load_golden
+
+KAT = [  # Random123 known-answer vectors for Philox4x32-10
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+def test_philox_known_answers():
+    for ctr, key, want in KAT:
+        assert O.philox(ctr, key) == want
+
+
+def test_uniform_mapping_in_unit_interval():
+    us = [O.stream_uniform(7, 1, it, ind, d) for it in range(3) for ind in range(5) for d in range(8)]
+    assert all(0.0 <= u < 1.0 for u in us) and len(set(us)) == len(us)
+
+
+@pytest.mark.parametrize("name", MAACO_CASES)
+def test_maaco_oracle_reproduces_reference(name):
+    g = load_golden("maaco_" + name)
+    N, K = int(g["N"]), int(g["K"])
+    o = O.MaacoOracle(g["grid"].astype(int), N, K, seed=int(g["seed"]), **g["params"])
+    assert np.array_equal(o.tau.reshape(g["tau0"].shape), g["tau0"])
+    pos = 0
+    for it in range(1, K + 1):
+        cells, ncell, length, turns, _ = o.iterate(it)
+        assert np.array_equal(ncell, g["n_cells"][it - 1])
+        assert np.array_equal(length, g["length"][it - 1])          # bit-exact fp64 (inf == inf)
+        assert np.array_equal(turns, g["turns"][it - 1])
+        for a in range(N):
+            n = ncell[a]
+            assert np.array_equal(cells[a, :n], g["cells"][pos:pos + n])
+            pos += n
+        assert np.array_equal(o.tau.reshape(g["tau0"].shape), g["tau"][it - 1])
+    assert np.array_equal(o.best_path, g["best_cells"])
+    assert o.best_len == float(g["best_len"]) and o.best_turns == int(g["best_turns"])
+    curve = np.array([np.inf if v is None else v for v in o.curve])
+    assert np.array_equal(curve, g["curve"])
