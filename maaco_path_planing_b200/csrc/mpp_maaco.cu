@@ -113,7 +113,12 @@ struct TourArgs {
     unsigned long long *steps;
 };
 
+#ifndef MPP_TOUR_THREADS
 #define MPP_TOUR_THREADS 256
+#endif
+#ifndef MPP_TOUR_MIN_BLOCKS
+#define MPP_TOUR_MIN_BLOCKS 4
+#endif
 #define MPP_SQRT2 1.4142135623730951  // sqrt(2.0) correctly rounded == math.sqrt(2)
 
 
@@ -166,8 +171,12 @@ __device__ __forceinline__ uint32_t group_ballot(uint32_t gmask, int gshift, boo
     return (LPA == 32) ? (b & 0xffu) : ((b >> gshift) & 0xffu);
 }
 
+// Per step each group (LPA lanes; lane m < 8 owns move m) does: occupancy bits from shared memory,
+// one round of global loads (visited word, tau, E), two ballots, a REDUX max, and the literal
+// selection rules.  Philox blocks are generated LPA steps at a time (lane m computes the block of
+// step base+m) so the per-step cost is two double shuffles instead of ten Philox rounds.
 template <int LPA, bool OCC_SMEM>
-__global__ void __launch_bounds__(MPP_TOUR_THREADS, 4) mpp_maaco_tour_kernel(const TourArgs A) {
+__global__ void __launch_bounds__(MPP_TOUR_THREADS, MPP_TOUR_MIN_BLOCKS) mpp_maaco_tour_kernel(const TourArgs A) {
     extern __shared__ __align__(16) uint32_t s_occ[];
     __shared__ __align__(8) uint64_t s_bar;
     const uint32_t *occ = A.occ;
@@ -183,13 +192,13 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, 4) mpp_maaco_tour_kernel(con
     const int a = (blockIdx.x * MPP_TOUR_THREADS + threadIdx.x) / LPA;
     if (a >= A.n_ants) return;
     const bool mv = m < 8;
-    // move order MAACO.py:98: (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1)
-    const int i9 = m + (m >= 4);
-    const int mr = mv ? i9 / 3 - 1 : 0, mc = mv ? i9 % 3 - 1 : 0;
-    const int R = A.R, C = A.C;
+    // move order MAACO.py:98: (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1); (delta+1) packed 2 bits/move
+    const int mr = mv ? (int)((0xA940u >> (2 * m)) & 3u) - 1 : 0;
+    const int mc = mv ? (int)((0x9224u >> (2 * m)) & 3u) - 1 : 0;
+    const int C = A.C;
     const int tr = A.target / C, tc = A.target % C;
     int cr = A.start / C, cc = A.start % C;
-    // strategy-1 orientation mask (Start->Target), MAACO.py:146-150
+    // orientation masks MAACO.py:146-157
     auto orient_mask = [](int dR, int dC) -> uint32_t {
         uint32_t k = 0xffu;
         if (dC > 0) k &= ~0x29u;  // moves with dc<0: m0,m3,m5
@@ -201,15 +210,21 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, 4) mpp_maaco_tour_kernel(con
     const uint32_t P1 = orient_mask(tr - cr, tc - cc);
     const uint32_t ant_global = (uint32_t)(A.ant_offset + a);
     const size_t n_ants = (size_t)A.n_ants;
+    uint32_t *const visit_a = A.visitT + a;                      // word w of this ant at visit_a[w * n_ants]
+    int32_t *const cells_a = A.cells + (size_t)a * A.max_cells;
+    const double *const __restrict__ tau = A.tau;
+    const double *const __restrict__ E0 = A.E0;
+    const double *const __restrict__ E1 = A.E1;
     int n_path = 1, prev_m = -1, turns = 0;
     double len = 0.0;
-    long long steps = 0;
-    const long long max_steps = 2ll * R * C;
+    uint32_t steps = 0;
+    const uint32_t max_steps = 2u * (uint32_t)A.R * (uint32_t)C;  // R*C < 2^30
     bool failed = false;
+    double u0_l = 0.0, u1_l = 0.0;
     if (m == 0) {
         const int s = A.start;
-        A.visitT[(size_t)(s >> 5) * n_ants + a] = 1u << (s & 31);
-        if (A.max_cells > 0) A.cells[(size_t)a * A.max_cells] = s;
+        visit_a[(size_t)(s >> 5) * n_ants] = 1u << (s & 31);
+        cells_a[0] = s;
     }
     __syncwarp(gmask);
     while (!(cr == tr && cc == tc) && steps < max_steps) {
@@ -225,15 +240,21 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, 4) mpp_maaco_tour_kernel(con
         double tv = 0.0, ev = 0.0;
         const bool turn = (n_path >= 2) && (m != prev_m);   // MAACO.py:184-195
         if (!blocked) {
-            tw = A.visitT[(size_t)(j >> 5) * n_ants + a];
-            tv = A.tau[j];
-            ev = turn ? A.E1[j] : A.E0[j];
+            tw = visit_a[(size_t)(j >> 5) * n_ants];
+            tv = tau[j];
+            ev = turn ? E1[j] : E0[j];
         }
-        // uniforms for this step: draws 2s (q-test) and 2s+1 (selection) of stream (seed, TOUR, it, ant)
-        const mpp_u4 rb = mpp_philox((uint32_t)steps, ant_global, A.it, MPP_CLS_MAACO_TOUR, A.k0, A.k1);
-        const double u0 = mpp_u53(rb.x, rb.y), u1 = mpp_u53(rb.z, rb.w);
+        // uniforms: draws 2s (q-test) and 2s+1 (selection) of stream (seed, TOUR, it, ant); block s
+        const uint32_t sub = steps & (uint32_t)(LPA - 1);
+        if (sub == 0) {
+            const mpp_u4 rb = mpp_philox(steps + (uint32_t)m, ant_global, A.it, MPP_CLS_MAACO_TOUR, A.k0, A.k1);
+            u0_l = mpp_u53(rb.x, rb.y);
+            u1_l = mpp_u53(rb.z, rb.w);
+        }
+        const double u0 = __shfl_sync(gmask, u0_l, gshift + (int)sub);
+        const double u1 = __shfl_sync(gmask, u1_l, gshift + (int)sub);
         const uint32_t o = group_ballot<LPA>(gmask, gshift, blocked);
-        const bool tabu = (!blocked) && ((tw >> (j & 31)) & 1u);
+        const bool tabu = (tw >> (j & 31)) & 1u;            // tw == 0 for blocked lanes
         const uint32_t tb = group_ballot<LPA>(gmask, gshift, tabu);
         // crossing prohibition MAACO.py:100-120: diagonal banned if either orthogonal cell is an obstacle
         const uint32_t o1 = (o >> 1) & 1u, o3 = (o >> 3) & 1u, o4 = (o >> 4) & 1u, o6 = (o >> 6) & 1u;
@@ -243,56 +264,52 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, 4) mpp_maaco_tour_kernel(con
         if (!cand) cand = valid & orient_mask(tr - cr, tc - cc);      // strategy 2 :169
         if (!cand) cand = valid;                                      // strategy 3 :172-180
         if (!cand) { failed = true; break; }                          // :287-288
-        const bool in_c = mv && ((cand >> m) & 1u);
+        const bool in_c = (cand >> m) & 1u;                           // cand has 8 bits -> false for m >= 8
         const double ta = (A.alpha == 1.0) ? tv : pow_slow(tv, A.alpha);   // tau**alpha (x**1.0 == x exactly)
         const double attr = ta * ev;                                  // :238
-        const uint32_t below_me = cand & ((1u << m) - 1u);
-        int pick;
+        // group max of attr over the candidates (attr >= 0: IEEE order == unsigned bit order)
+        const unsigned long long key = in_c ? (unsigned long long)__double_as_longlong(attr) : 0ull;
+        const uint32_t hi = (uint32_t)(key >> 32);
+        const uint32_t mhi = __reduce_max_sync(gmask, hi);
+        const uint32_t lo = (in_c && hi == mhi) ? (uint32_t)key : 0u;
+        const uint32_t mlo = __reduce_max_sync(gmask, lo);
+        const double mx = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+        uint32_t pool;   // the set the final uniform index is taken from
+        int k = -1;      // >= 0: rank already decided by the roulette
         if (u0 <= A.q0) {
             // greedy :241-250.  Sequential rule == {first arg-max r} U {i>r : |attr_i - max| < 1e-9}
-            const unsigned long long key = in_c ? (unsigned long long)__double_as_longlong(attr) : 0ull;
-            const uint32_t hi = (uint32_t)(key >> 32);
-            const uint32_t mhi = __reduce_max_sync(gmask, hi);
-            const uint32_t lo = (in_c && hi == mhi) ? (uint32_t)key : 0u;
-            const uint32_t mlo = __reduce_max_sync(gmask, lo);
-            const double mx = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
             const uint32_t eq = group_ballot<LPA>(gmask, gshift, in_c && attr == mx);
             const int r = __ffs(eq) - 1;
-            const uint32_t el =
-                group_ballot<LPA>(gmask, gshift, in_c && (m == r || (m > r && fabs(attr - mx) < 1e-9)));
-            const int ne = __popc(el);
-            int k = (int)(u1 * (double)ne);
-            k = k < ne ? k : ne - 1;
-            const uint32_t sel = group_ballot<LPA>(gmask, gshift, ((el >> m) & 1u) && mv && __popc(el & ((1u << m) - 1u)) == k);
-            pick = __ffs(sel) - 1;
+            pool = group_ballot<LPA>(gmask, gshift, in_c && (m == r || (m > r && fabs(attr - mx) < 1e-9)));
         } else {
-            // :251-262.  sum() over np.float64 items == plain left-to-right
-            double S = 0.0;
+            pool = cand;
+            // :251-262.  sum() over np.float64 items == plain left-to-right.  n <= 8 terms <= mx, so
+            // 8*mx < 0.9e-9 already implies S < 1e-9 (the common case on large maps: attr ~ 1e-20)
+            if (!(mx * 8.0 < 0.9e-9)) {
+                double S = 0.0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const double v = __shfl_sync(gmask, attr, gshift + i);
-                if ((cand >> i) & 1u) S += v;
+                for (int i = 0; i < 8; ++i) {
+                    const double v = __shfl_sync(gmask, attr, gshift + i);
+                    if ((cand >> i) & 1u) S += v;
+                }
+                if (!(S < 1e-9)) k = roulette_rank(attr, cand, gmask, gshift, S, u1);  // rare: near T only
             }
-            const int n = __popc(cand);
-            int k;
-            if (S < 1e-9) {
-                k = (int)(u1 * (double)n);                            // random.choice(all) :253-254
-                k = k < n ? k : n - 1;
-            } else {
-                k = roulette_rank(attr, cand, gmask, gshift, S, u1);  // rare: only within a few cells of T
-            }
-            const uint32_t sel = group_ballot<LPA>(gmask, gshift, in_c && __popc(below_me) == k);
-            pick = __ffs(sel) - 1;
         }
+        if (k < 0) {                                                  // random.choice(pool) -> pool[floor(u*n)]
+            const int n = __popc(pool);
+            k = (int)(u1 * (double)n);
+            k = k < n ? k : n - 1;
+        }
+        const uint32_t sel = group_ballot<LPA>(gmask, gshift, ((pool >> m) & 1u) && __popc(pool & ((1u << m) - 1u)) == k);
+        const int pick = __ffs(sel) - 1;
         // ---- advance :293-297 ----
-        const int p9 = pick + (pick >= 4);
-        const int pr_ = p9 / 3 - 1, pc_ = p9 % 3 - 1;
+        const int pr_ = (int)((0xA940u >> (2 * pick)) & 3u) - 1, pc_ = (int)((0x9224u >> (2 * pick)) & 3u) - 1;
         len += (pr_ != 0 && pc_ != 0) ? MPP_SQRT2 : 1.0;
         if (n_path >= 2 && pick != prev_m) ++turns;                   // :264-276 counted on the fly
         prev_m = pick;
         if (m == pick) {
-            A.visitT[(size_t)(j >> 5) * n_ants + a] = tw | (1u << (j & 31));
-            if (n_path < A.max_cells) A.cells[(size_t)a * A.max_cells + n_path] = j;
+            visit_a[(size_t)(j >> 5) * n_ants] = tw | (1u << (j & 31));
+            if (n_path < A.max_cells) cells_a[n_path] = j;
         }
         cr += pr_;
         cc += pc_;
@@ -514,12 +531,23 @@ mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, i
                 const int a = a0 + u * 32 + lane;
                 const double d = (a < n_ants) ? dep[a] : 0.0;
                 if (clear_visit && wd[u] != 0u) row[a] = 0u;
-                while (nz) {                                                  // ants in index order :306
-                    const int l = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    const uint32_t wv = __shfl_sync(0xffffffffu, wd[u], l);
-                    const double dv = __shfl_sync(0xffffffffu, d, l);
-                    if (((wv >> lane) & 1u) && dv != 0.0) t += dv;            // :311
+                if (__popc(nz) >= 6) {
+                    // dense word (cells near S/T are visited by most ants): branch-free walk over the
+                    // 32 ants in index order; only the dependent DADD chain remains.  t + 0.0 == t exactly.
+#pragma unroll
+                    for (int l = 0; l < 32; ++l) {
+                        const uint32_t wv = __shfl_sync(0xffffffffu, wd[u], l);
+                        const double dv = __shfl_sync(0xffffffffu, d, l);
+                        if ((wv >> lane) & 1u) t += dv;                       // :311
+                    }
+                } else {
+                    while (nz) {                                              // ants in index order :306
+                        const int l = __ffs(nz) - 1;
+                        nz &= nz - 1;
+                        const uint32_t wv = __shfl_sync(0xffffffffu, wd[u], l);
+                        const double dv = __shfl_sync(0xffffffffu, d, l);
+                        if ((wv >> lane) & 1u) t += dv;                       // :311
+                    }
                 }
             }
         }
