@@ -143,6 +143,53 @@ int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t *visitT_de
                         int n_seg, int seg_ants, int word0, int n_words, double rho,
                         const mpp_maaco_state *state_dev, int clear_visit, void *stream);
 
+/* ---- A* connectors, waypoint-chain fitness, path statistics (astar.py, MPA.py, helper.py, pso.py, ga_solver.py) ---- */
+typedef struct {
+    double turn_penalty_factor, safety_penalty_factor, min_safe_distance, diagonal_obstacle_penalty_value;
+    int restrict_policy;  /* restrict_diagonal_near_obstacle_policy: connector bans corner cutting; stats charge it */
+    int allow_diagonal;   /* allow_diagonal_moves */
+    int mode;             /* 0 = helper.calculate_path_stats, 1 = MPA._calculate_path_stats (safety hard-wired 0.0) */
+} mpp_policy;
+
+/* replaces calculate_path_safety_penalty's O(len x n_obstacles) scan (helper.py:67-80) by a per-cell class
+ * table (min squared distance to an obstacle within floor(msd)) + a 256-entry LUT of (msd - d)**2 evaluated
+ * with libm on the host.  Cached in the map for one msd at a time; called implicitly by the stats entry points. */
+int mpp_map_safety_table(mpp_map *map, double min_safe_distance, void *stream);
+
+/* replaces helper.calculate_path_stats (helper.py:98-113; count_turns :58-65, safety :67-80, diagonal
+ * penalty :82-96) and MPA._calculate_path_stats (MPA.py:215-229) for n_paths paths, one warp each.
+ * length uses CPython 3.12's Neumaier-compensated sum().  stats_dev: n_paths x 5 doubles =
+ * (length, turns, safety_penalty, diag_penalty, fitness); empty path -> (inf, 0, 0, 0, inf). */
+int mpp_path_stats(mpp_map *map, const int32_t *cells_dev, int max_cells, const int32_t *n_cells_dev, int n_paths,
+                   const mpp_policy *policy, double *stats_dev, void *stream);
+
+/* scratch sizing for the search entry points: n_slots concurrent searches (one warp each; mpp_astar_max_slots
+ * = the number that are resident at once), each with a heap of heap_cap entries.  The scratch buffer must be
+ * zero-filled once before its first use (search stamps live in it). */
+size_t mpp_astar_scratch_bytes(const mpp_map *map, int n_slots, int heap_cap);
+int mpp_astar_max_slots(const mpp_map *map);
+
+/* replaces n independent calls of AStarSolver.solve (variant 0, astar.py:33-101, with get_valid_neighbors
+ * helper.py:18-53) or MPA._a_star (variant 1, MPA.py:106-151).  avoid_bits_dev: optional n x ceil(rows*cols/32)
+ * bitmaps (nodes_to_avoid).  cells_dev: n x max_cells; n_cells_dev[i] = path length (0 = no path / invalid
+ * endpoint, -1 = heap_cap overflow, > max_cells = truncated); g_dev[i] = g of the popped target (nullable).
+ * counters_dev: optional [2] = (node expansions, successful relaxations), accumulated. */
+int mpp_astar_batch(mpp_map *map, int variant, const int32_t *src_dev, const int32_t *dst_dev,
+                    const uint32_t *avoid_bits_dev, int n, int allow_diagonal, int restrict_corner,
+                    int32_t *cells_dev, int max_cells, int32_t *n_cells_dev, double *g_dev, void *scratch_dev,
+                    size_t scratch_bytes, int n_slots, int heap_cap, unsigned long long *counters_dev, void *stream);
+
+/* replaces PSOSolver._reconstruct_path_from_position (pso.py:56-94, after rounding/clamping) /
+ * GASolver._reconstruct_path_from_chromosome (ga_solver.py:58-93) followed by
+ * BasePathfinder._calculate_stats_for_path (helper.py:138-147) for a whole population: one warp per
+ * individual runs its W+1 connector searches with the growing avoid set and the statistics of the joined
+ * path.  waypoints_dev: N x W cells.  visited_dev: N x ceil(rows*cols/32) words of scratch.
+ * n_cells_dev[i]: 0 = invalid individual ([]), -1 = heap overflow, > max_cells = truncated. */
+int mpp_waypoint_fitness(mpp_map *map, const int32_t *waypoints_dev, int n_individuals, int n_waypoints,
+                         const mpp_policy *policy, int32_t *cells_dev, int max_cells, int32_t *n_cells_dev,
+                         double *stats_dev, uint32_t *visited_dev, void *scratch_dev, size_t scratch_bytes,
+                         int n_slots, int heap_cap, unsigned long long *counters_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

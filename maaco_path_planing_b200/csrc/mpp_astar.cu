@@ -1,0 +1,390 @@
+// mpp_astar.cu -- batched A* connectors, waypoint-chain fitness (PSO/GA) and path statistics.
+// Reference semantics: astar.py:33-101, MPA.py:106-151, helper.py:58-113, MPA.py:176-229,
+// pso.py:56-94, ga_solver.py:58-93.
+#include <cmath>
+
+#include "mpp_astar.cuh"
+
+#define MPP_AS_THREADS 256
+#define MPP_AS_WARPS (MPP_AS_THREADS / 32)
+
+// ---------------------------------------------------------------------------------------------
+// K1b: safety-class table (helper.py:67-80 as a per-cell function of the map)
+//   class[cell] = min squared distance to an obstacle within radius floor(msd), capped at 255; 0 = none.
+//   lut[d2]     = (msd - sqrt(d2))**2 if sqrt(d2) < msd else 0   -- evaluated on the host with libm pow.
+// Out-of-bounds is NOT an obstacle here (obstacle_nodes = argwhere(grid == 1), helper.py:125).
+// ---------------------------------------------------------------------------------------------
+__global__ void mpp_safety_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, int radius,
+                                  uint8_t *__restrict__ cls) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * C) return;
+    const int r = i / C, c = i % C;
+    int best = 1 << 30;
+    for (int dr = -radius; dr <= radius; ++dr) {
+        const int rr = r + dr;
+        if (rr < 0 || rr >= R) continue;
+        for (int dc = -radius; dc <= radius; ++dc) {
+            const int c2 = c + dc;
+            if (c2 < 0 || c2 >= C) continue;
+            const int pb = c2 + 1;
+            if ((occ[(rr + 1) * pitch + (pb >> 5)] >> (pb & 31)) & 1u) {
+                const int d2 = dr * dr + dc * dc;
+                best = d2 < best ? d2 : best;
+            }
+        }
+    }
+    cls[i] = (best == (1 << 30)) ? 0 : (uint8_t)(best > 255 ? 255 : best);
+}
+
+extern "C" int mpp_map_safety_table(mpp_map *map, double msd, void *stream) {
+    MPP_REQUIRE(map, "mpp_map_safety_table: null map");
+    MPP_REQUIRE(msd >= 0.0 && msd < 15.9, "mpp_map_safety_table: min_safe_distance %g unsupported (0 <= msd < 15.9)", msd);
+    if (map->safety_msd == msd && map->safety_d2_dev) return MPP_OK;
+    MPP_CUDA(cudaSetDevice(map->device));
+    const int n = map->rows * map->cols;
+    if (!map->safety_d2_dev) MPP_CUDA(cudaMalloc(&map->safety_d2_dev, (size_t)n));
+    if (!map->safety_lut_dev) MPP_CUDA(cudaMalloc(&map->safety_lut_dev, 256 * sizeof(double)));
+    double lut[256];
+    lut[0] = 0.0;
+    for (int d2 = 1; d2 < 256; ++d2) {
+        const double d = std::sqrt((double)d2);
+        lut[d2] = (d < msd) ? std::pow(msd - d, 2.0) : 0.0;     // helper.py:77-78 (float ** 2 -> libm pow)
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    MPP_CUDA(cudaMemcpyAsync(map->safety_lut_dev, lut, sizeof(lut), cudaMemcpyHostToDevice, s));
+    MPP_CUDA(cudaStreamSynchronize(s));
+    const int radius = (int)msd;
+    mpp_safety_kernel<<<(n + 255) / 256, 256, 0, s>>>(map->occ_dev, map->pitch_words, map->rows, map->cols, radius,
+                                                      map->safety_d2_dev);
+    MPP_CUDA(cudaGetLastError());
+    map->safety_msd = msd;
+    return MPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: path statistics by one warp (helper.py:98-113 / MPA.py:215-229)
+// out[5] = length, turns, safety penalty, diagonal penalty, fitness
+// ---------------------------------------------------------------------------------------------
+struct StatsCtx {
+    const uint32_t *occ;
+    int pitch, R, C;
+    const uint8_t *cls;     // safety classes (may be null when mode == 1 or spf table not needed)
+    const double *lut;
+    mpp_policy pol;
+};
+
+__device__ void path_stats_warp(const StatsCtx &X, const int32_t *cells, int n, double *out) {
+    const int lane = threadIdx.x & 31;
+    const double INF = __longlong_as_double(MPP_INF_BITS);
+    if (n <= 0) {                                                        // helper.py:104-105
+        if (lane == 0) { out[0] = INF; out[1] = 0.0; out[2] = 0.0; out[3] = 0.0; out[4] = INF; }
+        return;
+    }
+    const int C = X.C;
+    double f = 0.0, comp = 0.0, saf = 0.0;
+    int turns = 0, ndiag = 0;
+    const bool want_safety = (X.pol.mode == 0) && X.cls != nullptr;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const int c0 = i < n ? cells[i] : 0;
+        const int c1 = (i + 1) < n ? cells[i + 1] : c0;
+        const int c2 = (i + 2) < n ? cells[i + 2] : c1;
+        const int r0 = c0 / C, q0 = c0 % C, r1 = c1 / C, q1 = c1 % C, r2 = c2 / C, q2 = c2 % C;
+        const int dr1 = r1 - r0, dc1 = q1 - q0, dr2 = r2 - r1, dc2 = q2 - q1;
+        double x = 0.0;
+        if (i + 1 < n) x = hdist_dev(r0, q0, r1, q1);                   // helper.py:106
+        const bool is_turn = (i + 2 < n) && (dr1 != dr2 || dc1 != dc2);  // helper.py:58-65
+        bool is_diag_cut = false;                                       // helper.py:82-96
+        if (i + 1 < n && (dr1 == 1 || dr1 == -1) && (dc1 == 1 || dc1 == -1)) {
+            const int pb0 = q0 + 1, pb1 = q1 + 1;
+            const bool b1 = (X.occ[(r1 + 1) * X.pitch + (pb0 >> 5)] >> (pb0 & 31)) & 1u;   // (next_r, curr_c)
+            const bool b2 = (X.occ[(r0 + 1) * X.pitch + (pb1 >> 5)] >> (pb1 & 31)) & 1u;   // (curr_r, next_c)
+            is_diag_cut = b1 || b2;
+        }
+        double pen = 0.0;
+        if (want_safety && i < n) pen = X.lut[X.cls[c0]];               // helper.py:70-79
+        turns += __popc(__ballot_sync(0xffffffffu, is_turn));
+        ndiag += __popc(__ballot_sync(0xffffffffu, is_diag_cut));
+        // sequential folds in path order (fp64 addition is not associative)
+        const int cnt = (n - base) < 32 ? (n - base) : 32;
+        for (int l = 0; l < cnt; ++l) {
+            const double xl = __shfl_sync(0xffffffffu, x, l);
+            const double pl = __shfl_sync(0xffffffffu, pen, l);
+            const int gi = base + l;
+            if (gi + 1 < n) {
+                if (gi == 0) f = xl;                                    // 0 + x0 leaves CPython's int fast path
+                else {                                                  // Neumaier step (CPython 3.12 sum())
+                    const double t = f + xl;
+                    if (fabs(f) >= fabs(xl)) comp += (f - t) + xl; else comp += (xl - t) + f;
+                    f = t;
+                }
+            }
+            saf += pl;                                                  // + 0.0 is exact
+        }
+    }
+    if (comp != 0.0 && comp == comp && fabs(comp) != INF) f += comp;
+    const double length = (n > 1) ? f : 0.0;
+    const double safety = want_safety ? saf / (double)n : 0.0;          // helper.py:80 ; MPA.py:173 -> 0.0
+    double diag = 0.0;
+    if (n >= 2 && X.pol.restrict_policy)
+        for (int k = 0; k < ndiag; ++k) diag += X.pol.diagonal_obstacle_penalty_value;
+    if (lane == 0) {
+        out[0] = length; out[1] = (double)turns; out[2] = safety; out[3] = diag;
+        out[4] = length + X.pol.turn_penalty_factor * (double)turns + X.pol.safety_penalty_factor * safety + diag;
+    }
+}
+
+__global__ void __launch_bounds__(MPP_AS_THREADS)
+mpp_path_stats_kernel(StatsCtx X, const int32_t *__restrict__ cells, int max_cells, const int32_t *__restrict__ n_cells,
+                      int n_paths, double *stats) {
+    const int w = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) >> 5;
+    if (w >= n_paths) return;
+    int n = n_cells[w];
+    if (n > max_cells) n = max_cells;
+    path_stats_warp(X, cells + (size_t)w * max_cells, n, stats + (size_t)w * 5);
+}
+
+static int make_stats_ctx(mpp_map *map, const mpp_policy *pol, void *stream, StatsCtx *X) {
+    X->occ = map->occ_dev; X->pitch = map->pitch_words; X->R = map->rows; X->C = map->cols;
+    X->pol = *pol;
+    X->cls = nullptr; X->lut = nullptr;
+    if (pol->mode == 0 && map->n_obstacles > 0) {
+        int rc = mpp_map_safety_table(map, pol->min_safe_distance, stream);
+        if (rc) return rc;
+        X->cls = map->safety_d2_dev; X->lut = map->safety_lut_dev;
+    }
+    return MPP_OK;
+}
+
+extern "C" int mpp_path_stats(mpp_map *map, const int32_t *cells_dev, int max_cells, const int32_t *n_cells_dev,
+                              int n_paths, const mpp_policy *policy, double *stats_dev, void *stream) {
+    MPP_REQUIRE(map && cells_dev && n_cells_dev && policy && stats_dev, "mpp_path_stats: null argument");
+    MPP_REQUIRE(n_paths > 0 && max_cells > 0, "mpp_path_stats: bad sizes");
+    MPP_CUDA(cudaSetDevice(map->device));
+    StatsCtx X;
+    int rc = make_stats_ctx(map, policy, stream, &X);
+    if (rc) return rc;
+    const int blocks = (n_paths + MPP_AS_WARPS - 1) / MPP_AS_WARPS;
+    mpp_path_stats_kernel<<<blocks, MPP_AS_THREADS, 0, (cudaStream_t)stream>>>(X, cells_dev, max_cells, n_cells_dev,
+                                                                             n_paths, stats_dev);
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scratch layout: [0,256) work counter + error flag; then n_slots search slots
+// ---------------------------------------------------------------------------------------------
+static size_t slot_bytes_host(int rc, int heap_cap) {
+    size_t b = 256;
+    b += ((size_t)rc * 8 + 255) & ~(size_t)255;
+    b += ((size_t)rc * 4 + 255) & ~(size_t)255;
+    size_t hs = (size_t)heap_cap + 64;
+    b += 2 * ((hs * 8 + 255) & ~(size_t)255);
+    b += (hs * 4 + 255) & ~(size_t)255;
+    return b;
+}
+
+extern "C" size_t mpp_astar_scratch_bytes(const mpp_map *map, int n_slots, int heap_cap) {
+    if (!map || n_slots <= 0 || heap_cap <= 0) return 0;
+    return 256 + (size_t)n_slots * slot_bytes_host(map->rows * map->cols, heap_cap);
+}
+
+extern "C" int mpp_astar_max_slots(const mpp_map *map) { return map ? map->sm_count * 4 * MPP_AS_WARPS : 0; }
+
+struct BatchArgs {
+    AStarGrid G;
+    int occ_words;
+    int variant;
+    const int32_t *src, *dst;
+    const uint32_t *avoid;  // n x words or null
+    int n, words;
+    int32_t *cells;
+    int max_cells;
+    int32_t *n_cells;
+    double *g;
+    char *scratch;
+    int n_slots, heap_cap;
+    unsigned long long *counters;
+};
+
+template <bool OCC_SMEM>
+__global__ void __launch_bounds__(MPP_AS_THREADS, 4) mpp_astar_batch_kernel(BatchArgs A) {
+    extern __shared__ __align__(16) uint32_t s_occ[];
+    __shared__ __align__(8) uint64_t s_bar;
+    AStarGrid G = A.G;
+    if (OCC_SMEM) {
+        mpp_stage_bulk(s_occ, A.G.occ, (uint32_t)A.occ_words * 4u, &s_bar);
+        G.occ = s_occ;
+    }
+    const int lane = threadIdx.x & 31;
+    const int slot = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) >> 5;
+    if (slot >= A.n_slots) return;
+    const int rc = G.R * G.C;
+    AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap);
+    unsigned int *next = (unsigned int *)A.scratch;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(next, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= A.n) break;
+        double g;
+        const int len = astar_search(G, S, A.variant, A.src[i], A.dst[i], A.avoid ? A.avoid + (size_t)i * A.words : nullptr,
+                                     A.cells + (size_t)i * A.max_cells, A.max_cells, &g,
+                                     A.counters ? A.counters : nullptr, A.counters ? A.counters + 1 : nullptr);
+        if (lane == 0) { A.n_cells[i] = len; if (A.g) A.g[i] = g; }
+    }
+}
+
+static int check_scratch(const mpp_map *map, size_t scratch_bytes, int n_slots, int heap_cap) {
+    MPP_REQUIRE(n_slots > 0 && heap_cap >= 64, "A*: n_slots=%d heap_cap=%d", n_slots, heap_cap);
+    MPP_REQUIRE(scratch_bytes >= mpp_astar_scratch_bytes(map, n_slots, heap_cap),
+                "A*: scratch too small (%zu < %zu)", scratch_bytes, mpp_astar_scratch_bytes(map, n_slots, heap_cap));
+    return MPP_OK;
+}
+
+extern "C" int mpp_astar_batch(mpp_map *map, int variant, const int32_t *src_dev, const int32_t *dst_dev,
+                               const uint32_t *avoid_bits_dev, int n, int allow_diagonal, int restrict_corner,
+                               int32_t *cells_dev, int max_cells, int32_t *n_cells_dev, double *g_dev,
+                               void *scratch_dev, size_t scratch_bytes, int n_slots, int heap_cap,
+                               unsigned long long *counters_dev, void *stream) {
+    MPP_REQUIRE(map && src_dev && dst_dev && cells_dev && n_cells_dev && scratch_dev, "mpp_astar_batch: null argument");
+    MPP_REQUIRE(variant == 0 || variant == 1, "mpp_astar_batch: variant must be 0 (astar.py) or 1 (MPA.py)");
+    MPP_REQUIRE(n > 0 && max_cells > 0, "mpp_astar_batch: bad sizes");
+    int rc = check_scratch(map, scratch_bytes, n_slots, heap_cap);
+    if (rc) return rc;
+    MPP_CUDA(cudaSetDevice(map->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    MPP_CUDA(cudaMemsetAsync(scratch_dev, 0, 256, s));
+    BatchArgs A;
+    A.G.occ = map->occ_dev; A.G.pitch = map->pitch_words; A.G.R = map->rows; A.G.C = map->cols;
+    A.G.allow_diag = allow_diagonal; A.G.restrict_corner = restrict_corner;
+    A.occ_words = map->occ_words; A.variant = variant; A.src = src_dev; A.dst = dst_dev; A.avoid = avoid_bits_dev;
+    A.n = n; A.words = (map->rows * map->cols + 31) / 32; A.cells = cells_dev; A.max_cells = max_cells;
+    A.n_cells = n_cells_dev; A.g = g_dev; A.scratch = (char *)scratch_dev; A.n_slots = n_slots; A.heap_cap = heap_cap;
+    A.counters = counters_dev;
+    const size_t smem = (size_t)map->occ_words * 4;
+    const int blocks = (n_slots + MPP_AS_WARPS - 1) / MPP_AS_WARPS;
+    if (smem <= 48 * 1024) {
+        mpp_astar_batch_kernel<true><<<blocks, MPP_AS_THREADS, smem, s>>>(A);
+    } else if (smem <= 56 * 1024) {
+        MPP_CUDA(cudaFuncSetAttribute(mpp_astar_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mpp_astar_batch_kernel<true><<<blocks, MPP_AS_THREADS, smem, s>>>(A);
+    } else {
+        mpp_astar_batch_kernel<false><<<blocks, MPP_AS_THREADS, 0, s>>>(A);
+    }
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 + K7: waypoint chain -> path -> fitness (pso.py:56-94 / ga_solver.py:58-93 + helper.py:98-113)
+// One warp per individual: W+1 sequential connector searches with the growing avoid set
+// (nodes_in_path_so_far - {current_start, waypoint}), then the statistics of the joined path.
+// n_cells: 0 = invalid individual ([]), -1 = heap overflow, > max_cells = path truncated.
+// ---------------------------------------------------------------------------------------------
+struct ChainArgs {
+    AStarGrid G;
+    int occ_words;
+    StatsCtx X;
+    int start, target;
+    const int32_t *wps;  // N x W cells
+    int N, W, words;
+    int32_t *cells;
+    int max_cells;
+    int32_t *n_cells;
+    double *stats;
+    uint32_t *visited;  // N x words
+    char *scratch;
+    int n_slots, heap_cap;
+    unsigned long long *counters;
+};
+
+template <bool OCC_SMEM>
+__global__ void __launch_bounds__(MPP_AS_THREADS, 4) mpp_waypoint_fitness_kernel(ChainArgs A) {
+    extern __shared__ __align__(16) uint32_t s_occ[];
+    __shared__ __align__(8) uint64_t s_bar;
+    AStarGrid G = A.G;
+    StatsCtx X = A.X;
+    if (OCC_SMEM) {
+        mpp_stage_bulk(s_occ, A.G.occ, (uint32_t)A.occ_words * 4u, &s_bar);
+        G.occ = s_occ;
+        X.occ = s_occ;
+    }
+    const int lane = threadIdx.x & 31;
+    const int slot = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) >> 5;
+    if (slot >= A.n_slots) return;
+    const int rc = G.R * G.C;
+    AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap);
+    unsigned int *next = (unsigned int *)A.scratch;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(next, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= A.N) break;
+        uint32_t *vis = A.visited + (size_t)i * A.words;
+        int32_t *path = A.cells + (size_t)i * A.max_cells;
+        for (int w = lane; w < A.words; w += 32) vis[w] = 0u;
+        __syncwarp();
+        int n = 1, cur = A.start, status = 1;
+        if (lane == 0) { path[0] = A.start; vis[A.start >> 5] |= 1u << (A.start & 31); }   // pso.py:63-65
+        __syncwarp();
+        for (int k = 0; k <= A.W; ++k) {
+            const int goal = (k < A.W) ? A.wps[(size_t)i * A.W + k] : A.target;
+            // the segment is written over the tail cell of the path (segment[0] == current_start)
+            const int cap = A.max_cells - (n - 1);
+            const int sl = astar_search(G, S, 0, cur, goal, vis, path + (n - 1), cap, nullptr,
+                                        A.counters ? A.counters : nullptr, A.counters ? A.counters + 1 : nullptr);
+            if (sl < 0) { status = -1; break; }
+            if (sl == 0 || (sl == 1 && cur != goal)) { status = 0; break; }          // pso.py:77,87 -> []
+            if (sl > cap) { status = 2; n += sl - 1; break; }                        // truncated
+            for (int t = 1 + lane; t < sl; t += 32) {                                // nodes_in_path_so_far.update
+                const int c = path[n - 1 + t];
+                atomicOr(&vis[c >> 5], 1u << (c & 31));
+            }
+            __syncwarp();
+            n += sl - 1;
+            cur = goal;
+        }
+        // (consecutive duplicates cannot occur: a segment never repeats its first cell; pso.py:91-93 is a no-op)
+        int n_out = status == 1 ? n : (status == 2 ? n : status);
+        if (lane == 0) A.n_cells[i] = n_out;
+        path_stats_warp(X, path, status == 1 ? n : 0, A.stats + (size_t)i * 5);
+    }
+}
+
+extern "C" int mpp_waypoint_fitness(mpp_map *map, const int32_t *waypoints_dev, int n_individuals, int n_waypoints,
+                                    const mpp_policy *policy, int32_t *cells_dev, int max_cells, int32_t *n_cells_dev,
+                                    double *stats_dev, uint32_t *visited_dev, void *scratch_dev, size_t scratch_bytes,
+                                    int n_slots, int heap_cap, unsigned long long *counters_dev, void *stream) {
+    MPP_REQUIRE(map && policy && cells_dev && n_cells_dev && stats_dev && visited_dev && scratch_dev,
+                "mpp_waypoint_fitness: null argument");
+    MPP_REQUIRE(n_individuals > 0 && n_waypoints >= 0 && max_cells > 1, "mpp_waypoint_fitness: bad sizes");
+    MPP_REQUIRE(n_waypoints == 0 || waypoints_dev, "mpp_waypoint_fitness: null waypoints");
+    MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_waypoint_fitness: map has no start/target");
+    int rc = check_scratch(map, scratch_bytes, n_slots, heap_cap);
+    if (rc) return rc;
+    MPP_CUDA(cudaSetDevice(map->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    ChainArgs A;
+    rc = make_stats_ctx(map, policy, stream, &A.X);
+    if (rc) return rc;
+    MPP_CUDA(cudaMemsetAsync(scratch_dev, 0, 256, s));
+    A.G.occ = map->occ_dev; A.G.pitch = map->pitch_words; A.G.R = map->rows; A.G.C = map->cols;
+    A.G.allow_diag = policy->allow_diagonal; A.G.restrict_corner = policy->restrict_policy;
+    A.occ_words = map->occ_words; A.start = map->start; A.target = map->target;
+    A.wps = waypoints_dev; A.N = n_individuals; A.W = n_waypoints; A.words = (map->rows * map->cols + 31) / 32;
+    A.cells = cells_dev; A.max_cells = max_cells; A.n_cells = n_cells_dev; A.stats = stats_dev; A.visited = visited_dev;
+    A.scratch = (char *)scratch_dev; A.n_slots = n_slots; A.heap_cap = heap_cap; A.counters = counters_dev;
+    const size_t smem = (size_t)map->occ_words * 4;
+    const int blocks = (n_slots + MPP_AS_WARPS - 1) / MPP_AS_WARPS;
+    if (smem <= 48 * 1024) {
+        mpp_waypoint_fitness_kernel<true><<<blocks, MPP_AS_THREADS, smem, s>>>(A);
+    } else if (smem <= 56 * 1024) {
+        MPP_CUDA(cudaFuncSetAttribute(mpp_waypoint_fitness_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mpp_waypoint_fitness_kernel<true><<<blocks, MPP_AS_THREADS, smem, s>>>(A);
+    } else {
+        mpp_waypoint_fitness_kernel<false><<<blocks, MPP_AS_THREADS, 0, s>>>(A);
+    }
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}

@@ -1,0 +1,144 @@
+"""SearchEngine -- host-side owner of the device buffers behind the connector / fitness entry points
+(mpp_astar_batch, mpp_waypoint_fitness, mpp_path_stats).  Populations are torch tensors in HBM; the
+engine only moves pointers across the C ABI.  No CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .gridmap import GridMap
+
+INF = float("inf")
+
+
+def make_policy(turn_penalty_factor, safety_penalty_factor, min_safe_distance, diagonal_obstacle_penalty_value,
+                restrict_policy=True, allow_diagonal=True, mode=0):
+    return _lib.Policy(float(turn_penalty_factor), float(safety_penalty_factor), float(min_safe_distance),
+                       float(diagonal_obstacle_penalty_value), int(bool(restrict_policy)), int(bool(allow_diagonal)),
+                       int(mode))
+
+
+class SearchEngine:
+    def __init__(self, gridmap: GridMap, max_cells=None, heap_cap=None, n_slots=None):
+        import torch
+        self.torch = torch
+        self.map = gridmap
+        self.rows, self.cols = gridmap.rows, gridmap.cols
+        self.n = self.rows * self.cols
+        self.words = (self.n + 31) // 32
+        self.device = torch.device("cuda", gridmap.device)
+        L = _lib.lib()
+        self.max_slots = L.mpp_astar_max_slots(gridmap.handle)
+        self.n_slots = int(n_slots or self.max_slots)
+        # a search's open set is a frontier: a few thousand entries on the largest maps; overflow is
+        # reported (n_cells = -1) and the call is repeated with a larger heap
+        self.heap_cap = int(heap_cap or min(8 * self.n, max(4096, self.n // 4)))
+        self.max_cells = int(max_cells or min(self.n, max(4096, 16 * (self.rows + self.cols))))
+        self._scratch = None
+        self._scratch_key = None
+        self.counters = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.launches = 0
+
+    # -- buffers ---------------------------------------------------------------------------------
+    def _scratch_for(self, n_work):
+        slots = max(1, min(self.n_slots, n_work))
+        key = (slots, self.heap_cap)
+        if self._scratch_key != key:
+            nbytes = _lib.lib().mpp_astar_scratch_bytes(self.map.handle, slots, self.heap_cap)
+            self._scratch = self.torch.zeros(nbytes, dtype=self.torch.uint8, device=self.device)
+            self._scratch_key = key
+        return self._scratch, slots
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev_i32(self, a):
+        t = self.torch
+        if isinstance(a, t.Tensor):
+            return a.to(device=self.device, dtype=t.int32).contiguous()
+        return t.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=self.device)
+
+    def expansions(self):
+        c = self.counters.cpu().numpy()
+        return int(c[0]), int(c[1])
+
+    # -- K5 ---------------------------------------------------------------------------------------
+    def astar_batch(self, variant, src, dst, avoid_bits=None, allow_diagonal=True, restrict_corner=True):
+        """n independent searches.  Returns (cells[n,max_cells], n_cells[n], g[n]) as device tensors."""
+        t = self.torch
+        src, dst = self._dev_i32(src), self._dev_i32(dst)
+        n = src.numel()
+        if avoid_bits is not None:
+            avoid_bits = t.as_tensor(avoid_bits, device=self.device).contiguous()
+            assert avoid_bits.numel() == n * self.words
+        while True:
+            scratch, slots = self._scratch_for(n)
+            cells = t.empty((n, self.max_cells), dtype=t.int32, device=self.device)
+            ncell = t.empty(n, dtype=t.int32, device=self.device)
+            g = t.empty(n, dtype=t.float64, device=self.device)
+            _lib.check(_lib.lib().mpp_astar_batch(
+                self.map.handle, int(variant), _lib.ptr(src), _lib.ptr(dst), _lib.ptr(avoid_bits), n,
+                int(bool(allow_diagonal)), int(bool(restrict_corner)), _lib.ptr(cells), self.max_cells, _lib.ptr(ncell),
+                _lib.ptr(g), _lib.ptr(scratch), scratch.numel(), slots, self.heap_cap, _lib.ptr(self.counters),
+                self._stream()), "mpp_astar_batch")
+            self.launches += 1
+            if not self._grow_if_needed(ncell):
+                return cells, ncell, g
+
+    # -- K6 + K7 ----------------------------------------------------------------------------------
+    def waypoint_fitness(self, waypoints, policy):
+        """waypoints: [N, W] int32 cells.  Returns (cells, n_cells, stats[N,5]) device tensors."""
+        t = self.torch
+        wps = self._dev_i32(waypoints)
+        N, W = wps.shape
+        while True:
+            scratch, slots = self._scratch_for(N)
+            cells = t.empty((N, self.max_cells), dtype=t.int32, device=self.device)
+            ncell = t.empty(N, dtype=t.int32, device=self.device)
+            stats = t.empty((N, 5), dtype=t.float64, device=self.device)
+            visited = t.empty((N, self.words), dtype=t.int32, device=self.device)
+            _lib.check(_lib.lib().mpp_waypoint_fitness(
+                self.map.handle, _lib.ptr(wps), N, W, C.byref(policy), _lib.ptr(cells), self.max_cells,
+                _lib.ptr(ncell), _lib.ptr(stats), _lib.ptr(visited), _lib.ptr(scratch), scratch.numel(), slots,
+                self.heap_cap, _lib.ptr(self.counters), self._stream()), "mpp_waypoint_fitness")
+            self.launches += 1
+            if not self._grow_if_needed(ncell):
+                return cells, ncell, stats
+
+    def _grow_if_needed(self, ncell):
+        """Heap overflow (-1) or truncated paths (> max_cells) -> enlarge and tell the caller to repeat."""
+        mn, mx = int(ncell.min().item()), int(ncell.max().item())
+        grew = False
+        if mn < 0:
+            if self.heap_cap >= 8 * self.n:
+                raise _lib.MppError("A* heap overflow at maximum capacity")
+            self.heap_cap = min(8 * self.n, self.heap_cap * 4)
+            grew = True
+        if mx > self.max_cells:
+            self.max_cells = min(2 * self.n, max(mx, 2 * self.max_cells))
+            grew = True
+        return grew
+
+    # -- K7 ---------------------------------------------------------------------------------------
+    def path_stats(self, cells, n_cells, policy):
+        """cells [P, max_cells] int32, n_cells [P] -> stats [P,5] device tensor."""
+        t = self.torch
+        cells = cells if isinstance(cells, t.Tensor) else t.as_tensor(np.ascontiguousarray(cells, np.int32), device=self.device)
+        ncell = self._dev_i32(n_cells)
+        P, mc = cells.shape
+        stats = t.empty((P, 5), dtype=t.float64, device=self.device)
+        _lib.check(_lib.lib().mpp_path_stats(self.map.handle, _lib.ptr(cells.contiguous()), mc, _lib.ptr(ncell), P,
+                                             C.byref(policy), _lib.ptr(stats), self._stream()), "mpp_path_stats")
+        self.launches += 1
+        return stats
+
+    def stats_of_path(self, path, policy):
+        """helper.calculate_path_stats for one python path (list of (r,c)) -> 6-tuple like the reference."""
+        if not path:
+            return [], INF, 0, 0.0, 0.0, INF                              # helper.py:104-105
+        cells = np.array([[r * self.cols + c for r, c in path]], np.int32)
+        st = self.path_stats(cells, np.array([len(path)], np.int32), policy).cpu().numpy()[0]
+        length = float(st[0]) if len(path) > 1 else 0
+        return path, length, int(st[1]), float(st[2]), float(st[3]), float(st[4])

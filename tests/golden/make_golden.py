@@ -56,7 +56,136 @@ def maaco_case(name, grid, N, K, seed, params):
     print(name, "tours", N * K, "succ", int((ncell > 0).sum()), "best", res[1], res[2])
 
 
+def rand_grid(rng, n, m, dens):
+    g = (rng.random((n, m)) < dens).astype(int)
+    free = np.argwhere(g == 0)
+    s = free[rng.integers(len(free))]
+    g[s[0], s[1]] = 2
+    free = np.argwhere(g == 0)
+    t = free[rng.integers(len(free))]
+    g[t[0], t[1]] = 3
+    return g
+
+
+def astar_cases(n_cases=240):
+    """Reference outputs of AStarSolver.solve (variant 0) and MPA._a_star (variant 1) on random
+    (grid, src, dst, avoid-set) tuples incl. unreachable targets, src==dst, obstacle endpoints."""
+    ref = H.load_reference()
+    rng = np.random.default_rng(77)
+    rec = dict(grid=[], shape=[], src=[], dst=[], avoid=[], avoid_off=[0], flags=[], path0=[], off0=[0], path1=[],
+               off1=[0], g1=[])
+    for case in range(n_cases):
+        n, m = int(rng.integers(5, 30)), int(rng.integers(5, 30))
+        g = rand_grid(rng, n, m, rng.uniform(0.05, 0.35))
+        allow_diag, restrict = bool(rng.random() < 0.9), bool(rng.random() < 0.8)
+        cells_all = [(r, c) for r in range(n) for c in range(m)]
+
+        def pick():
+            if rng.random() < 0.08:
+                return cells_all[rng.integers(len(cells_all))]
+            fr = np.argwhere(g != 1)
+            q = fr[rng.integers(len(fr))]
+            return (int(q[0]), int(q[1]))
+        src, dst = pick(), pick()
+        if rng.random() < 0.04:
+            dst = src
+        avoid = {cells_all[rng.integers(len(cells_all))] for _ in range(int(rng.integers(0, n + m)))}
+        if rng.random() < 0.1:
+            avoid.add(dst)
+        if rng.random() < 0.1:
+            avoid.add(src)
+        with H.quiet():
+            solver = ref.astar.AStarSolver(grid=g, turn_penalty_factor=0, safety_penalty_factor=0, min_safe_distance=0,
+                                           allow_diagonal_moves=allow_diag,
+                                           restrict_diagonal_near_obstacle_policy=restrict,
+                                           diagonal_obstacle_penalty_value=0)
+            p0 = solver.solve(start_node_override=src, target_node_override=dst, nodes_to_avoid=set(avoid))[0]
+        mpa = ref.MPA.MPA.__new__(ref.MPA.MPA)
+        mpa.grid = np.array(g, dtype=int)
+        mpa.rows, mpa.cols = n, m
+        mpa.allow_diagonal_moves, mpa.restrict_diagonal_near_obstacle = allow_diag, restrict
+        p1, g1 = mpa._a_star(src, dst, set(avoid))
+        rec["grid"].append(g.astype(np.uint8).ravel())
+        rec["shape"].append((n, m))
+        rec["src"].append(src[0] * m + src[1])
+        rec["dst"].append(dst[0] * m + dst[1])
+        av = sorted(r * m + c for r, c in avoid)
+        rec["avoid"].extend(av)
+        rec["avoid_off"].append(len(rec["avoid"]))
+        rec["flags"].append((int(allow_diag), int(restrict)))
+        rec["path0"].extend(int(r) * m + int(c) for r, c in p0)
+        rec["off0"].append(len(rec["path0"]))
+        rec["path1"].extend(int(r) * m + int(c) for r, c in p1)
+        rec["off1"].append(len(rec["path1"]))
+        rec["g1"].append(float(g1))
+    np.savez_compressed(os.path.join(HERE, "astar_cases.npz"), grid=np.concatenate(rec["grid"]),
+                        shape=np.array(rec["shape"], np.int32), src=np.array(rec["src"], np.int32),
+                        dst=np.array(rec["dst"], np.int32), avoid=np.array(rec["avoid"], np.int32),
+                        avoid_off=np.array(rec["avoid_off"], np.int64), flags=np.array(rec["flags"], np.int32),
+                        path0=np.array(rec["path0"], np.int32), off0=np.array(rec["off0"], np.int64),
+                        path1=np.array(rec["path1"], np.int32), off1=np.array(rec["off1"], np.int64),
+                        g1=np.array(rec["g1"]))
+    print("astar cases", n_cases, "variant0 fails", sum(1 for i in range(n_cases) if rec["off0"][i] == rec["off0"][i + 1]))
+
+
+POLICY = dict(turn_penalty_factor=0.3, safety_penalty_factor=0.8, min_safe_distance=1.8,
+              diagonal_obstacle_penalty_value=100.0)                                # main.py:21-24
+
+
+def fitness_cases():
+    """Reference GA-style waypoint chains + stats (ga_solver.py:58-93, helper.py:98-113) and MPA-mode stats."""
+    ref = H.load_reference()
+    rng = np.random.default_rng(78)
+    grids = {"fig7": env_grids()["fig7"].astype(int), "blocks40": H.blocks_map(40, 0.2, 21),
+             "blocks64": H.blocks_map(64, 0.2, 22), "rect": H.blocks_map(0, 0.18, 23, rows=30, cols=48)}
+    out = {}
+    for name, g in grids.items():
+        R, Cc = g.shape
+        for msd in (1.8, 2.5):
+            pol = dict(POLICY, min_safe_distance=msd)
+            with H.quiet():
+                ga = ref.ga_solver.GASolver(grid=g, num_generations=1, population_size=2, num_waypoints_per_chromosome=5,
+                                            mutation_rate=0.1, crossover_rate=0.8, tournament_size=3,
+                                            allow_diagonal_moves=True, restrict_diagonal_near_obstacle_policy=True, **pol)
+            free = np.argwhere(g != 1)
+            N, W = 12, 5
+            wps = np.zeros((N, W), np.int32)
+            paths, offs, stats, mstats = [], [0], [], []
+            for i in range(N):
+                wp = [tuple(int(x) for x in free[rng.integers(len(free))]) for _ in range(W)]
+                if i % 5 == 4:
+                    wp[2] = (int(rng.integers(R)), int(rng.integers(Cc)))              # may be an obstacle (PSO style)
+                if i % 6 == 5:
+                    wp[1] = wp[0]                                                    # duplicate waypoint
+                wps[i] = [r * Cc + c for r, c in wp]
+                with H.quiet():
+                    path = ga._reconstruct_path_from_chromosome(list(wp))
+                    st = ga._calculate_stats_for_path(path)
+                paths.extend(int(r) * Cc + int(c) for r, c in path)
+                offs.append(len(paths))
+                stats.append([float(st[1]), float(st[2]), float(st[3]), float(st[4]), float(st[5])])
+                mpa = ref.MPA.MPA.__new__(ref.MPA.MPA)
+                mpa.grid = np.array(g, dtype=int)
+                mpa.rows, mpa.cols = R, Cc
+                mpa.restrict_diagonal_near_obstacle = True
+                mpa.diagonal_obstacle_penalty_val = 100.0
+                mpa.turn_penalty_factor_mpa, mpa.safety_penalty_factor_mpa = 0.1, 0.8
+                ms = mpa._calculate_path_stats(path)
+                mstats.append([float(x) for x in ms[1:]])
+            key = f"{name}_msd{msd}"
+            out[key + "_grid"] = g.astype(np.uint8)
+            out[key + "_wps"] = wps
+            out[key + "_paths"] = np.array(paths, np.int32)
+            out[key + "_offs"] = np.array(offs, np.int64)
+            out[key + "_stats"] = np.array(stats)
+            out[key + "_mpastats"] = np.array(mstats)
+            print(key, "valid", sum(1 for i in range(N) if offs[i + 1] > offs[i]), "/", N)
+    np.savez_compressed(os.path.join(HERE, "fitness_cases.npz"), **out)
+
+
 def main():
+    astar_cases()
+    fitness_cases()
     grids = env_grids()
     np.savez_compressed(os.path.join(HERE, "env_grids.npz"), **grids)
     maaco_case("fig7", grids["fig7"].astype(int), 20, 8, 101, MAACO_DEFAULT)

@@ -45,3 +45,46 @@ def test_maaco_oracle_reproduces_reference(name):
     assert o.best_len == float(g["best_len"]) and o.best_turns == int(g["best_turns"])
     curve = np.array([np.inf if v is None else v for v in o.curve])
     assert np.array_equal(curve, g["curve"])
+
+
+def _astar_golden():
+    g = load_golden("astar_cases")
+    pos = 0
+    for i in range(len(g["src"])):
+        n, m = g["shape"][i]
+        grid = g["grid"][pos:pos + n * m].reshape(n, m).astype(int)
+        pos += n * m
+        avoid = g["avoid"][g["avoid_off"][i]:g["avoid_off"][i + 1]]
+        yield (i, grid, int(g["src"][i]), int(g["dst"][i]), avoid, bool(g["flags"][i][0]), bool(g["flags"][i][1]),
+               g["path0"][g["off0"][i]:g["off0"][i + 1]], g["path1"][g["off1"][i]:g["off1"][i + 1]], float(g["g1"][i]))
+
+
+def test_astar_oracle_reproduces_reference():
+    n = 0
+    for i, grid, src, dst, avoid, ad, rs, p0, p1, g1 in _astar_golden():
+        orc = O.AStarOracle(grid, ad, rs)
+        bits = O.cells_to_bits(avoid, grid.size)
+        q0, _, _, _ = orc.solve(0, src, dst, bits)
+        q1, og1, _, _ = orc.solve(1, src, dst, bits)
+        assert np.array_equal(q0, p0), f"case {i} astar.py variant"
+        assert np.array_equal(q1, p1) and og1 == g1, f"case {i} MPA variant"
+        n += 1
+    assert n >= 200
+
+
+FIT_KEYS = [f"{m}_msd{d}" for m in ("fig7", "blocks40", "blocks64", "rect") for d in (1.8, 2.5)]
+
+
+@pytest.mark.parametrize("key", FIT_KEYS)
+def test_fitness_oracle_reproduces_reference(key):
+    g = load_golden("fitness_cases")
+    grid = g[key + "_grid"].astype(int)
+    msd = float(key.split("msd")[1])
+    cells, ncell, stats, _ = O.waypoint_fitness(grid, g[key + "_wps"], 0.3, 0.8, msd, 100.0)
+    offs = g[key + "_offs"]
+    for i in range(len(ncell)):
+        want = g[key + "_paths"][offs[i]:offs[i + 1]]
+        assert np.array_equal(cells[i, :ncell[i]], want)
+        assert np.array_equal(stats[i], g[key + "_stats"][i])              # bit-exact incl. inf
+        ms = O.path_stats(grid, want, 0.1, 0.8, msd, 100.0, True, mode=1)
+        assert np.array_equal(ms, g[key + "_mpastats"][i])
