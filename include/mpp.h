@@ -190,6 +190,36 @@ int mpp_waypoint_fitness(mpp_map *map, const int32_t *waypoints_dev, int n_indiv
                          double *stats_dev, uint32_t *visited_dev, void *scratch_dev, size_t scratch_bytes,
                          int n_slots, int heap_cap, unsigned long long *counters_dev, void *stream);
 
+/* ---- PSO / GA population updates (pso.py, ga_solver.py) ------------------------------------------- */
+
+/* replaces the velocity/position update of the particle loop (pso.py:183-206) for particles
+ * [particle_offset, particle_offset + n_particles) (device arrays start at that particle; a suffix is
+ * re-run when an earlier particle improved gbest -- the reference's loop is asynchronous, pso.py:222-229).
+ * pos/vel/pbest: n x W x 2 doubles (row, col); gbest: W x 2.  Exactly 4W uniforms per particle, stream
+ * (seed, PSO_UPDATE, iteration, particle).  Also writes the integer waypoints pso.py:61,69-70
+ * (round-half-even, clamped) as cells into waypoint_cells_dev (n x W). */
+int mpp_pso_update(const mpp_map *map, double *pos_dev, double *vel_dev, const double *pbest_pos_dev,
+                   const double *gbest_pos_dev, int n_particles, int particle_offset, int n_waypoints, double w,
+                   double c1, double c2, double max_vel, uint64_t seed, int iteration, int32_t *waypoint_cells_dev,
+                   void *stream);
+/* pso.py:61,69-70 alone (used for the initial particles) */
+int mpp_pso_round(const mpp_map *map, const double *pos_dev, int n_particles, int n_waypoints,
+                  int32_t *waypoint_cells_dev, void *stream);
+
+/* replaces GASolver._selection (ga_solver.py:136-142): n tournaments of min(tournament_size, n) individuals
+ * drawn with CPython's random.sample algorithm (randbelow(n) = floor(u*n)); winner = first minimum in sample
+ * order.  fitness_dev is in population (sorted) order; parents_dev receives n population indices.
+ * Stream (seed, GA_SELECT, generation, tournament). */
+int mpp_ga_select(const double *fitness_dev, int n, int tournament_size, uint64_t seed, int generation,
+                  int32_t *parents_dev, void *stream);
+
+/* replaces the breeding loop ga_solver.py:186-194 (_crossover :144-152, _mutate :154-160,
+ * _generate_random_waypoint :48-53): pair p = (parents[2p % n], parents[(2p+1) % n]) -> children 2p, 2p+1.
+ * chrom_dev: n x W cells in population order; children_dev: n x W.  Stream (seed, GA_BREED, generation, pair). */
+int mpp_ga_breed(const mpp_map *map, const int32_t *chrom_dev, const int32_t *parents_dev, int n, int n_waypoints,
+                 double crossover_rate, double mutation_rate, uint64_t seed, int generation, int32_t *children_dev,
+                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif

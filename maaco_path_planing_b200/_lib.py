@@ -65,6 +65,12 @@ _SIGS = {
                                 c_void_p, c_void_p, c_void_p, C.c_size_t, c_int, c_int, c_void_p, c_void_p]),
     "mpp_waypoint_fitness": (c_int, [c_void_p, c_void_p, c_int, c_int, C.POINTER(Policy), c_void_p, c_int, c_void_p,
                                      c_void_p, c_void_p, c_void_p, C.c_size_t, c_int, c_int, c_void_p, c_void_p]),
+    "mpp_pso_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double,
+                               c_double, c_double, c_double, c_u64, c_int, c_void_p, c_void_p]),
+    "mpp_pso_round": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "mpp_ga_select": (c_int, [c_void_p, c_int, c_int, c_u64, c_int, c_void_p, c_void_p]),
+    "mpp_ga_breed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_u64, c_int, c_void_p,
+                             c_void_p]),
 }
 
 _lib = None

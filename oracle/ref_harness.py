@@ -377,3 +377,58 @@ def blocks_map(n, frac=0.20, seed=0, rows=None, cols=None):
     g[0, 0] = 2
     g[rows - 1, cols - 1] = 3
     return g
+
+
+# ----------------------------------------------------------------------------
+# PSO / GA under the tape
+# ----------------------------------------------------------------------------
+def run_pso(grid, kwargs, seed):
+    """Reference PSOSolver.solve under the tape; returns result, curve and final particle state."""
+    ref = load_reference()
+    tape = TapeRandom(seed, locate=make_pso_locator())
+    with with_tape(ref.pso, tape):
+        with quiet():
+            s = ref.pso.PSOSolver(grid=np.array(grid), **kwargs)
+            init = {}
+            orig_init = s._initialize_particles
+
+            def init_hook():
+                ok = orig_init()
+                init["pos"] = np.array([p["position"] for p in s.particles], dtype=float)
+                init["vel"] = np.array([p["velocity"] for p in s.particles], dtype=float)
+                init["fit"] = np.array([p["current_fitness"] for p in s.particles], dtype=float)
+                init["gbest_fit"] = s.gbest_particle_data["fitness"]
+                return ok
+            s._initialize_particles = init_hook
+            res = s.solve()
+    C = np.array(grid).shape[1]
+    return {"result": res, "curve": list(s.convergence_curve), "init": init, "draws": dict(tape.counts),
+            "pos": np.array([p["position"] for p in s.particles], dtype=float),
+            "vel": np.array([p["velocity"] for p in s.particles], dtype=float),
+            "pbest_fit": np.array([p["pbest_fitness"] for p in s.particles], dtype=float),
+            "cur_fit": np.array([p["current_fitness"] for p in s.particles], dtype=float),
+            "best_cells": np.array([int(r) * C + int(c) for r, c in res[0]], np.int32)}
+
+
+def run_ga(grid, kwargs, seed):
+    """Reference GASolver.solve under the tape; returns result, curve, initial and final populations."""
+    ref = load_reference()
+    tape = TapeRandom(seed, locate=make_ga_locator())
+    C = np.array(grid).shape[1]
+    with with_tape(ref.ga_solver, tape):
+        with quiet():
+            s = ref.ga_solver.GASolver(grid=np.array(grid), **kwargs)
+            init = {}
+            orig_init = s._initialize_population
+
+            def init_hook():
+                ok = orig_init()
+                init["chrom"] = np.array([[r * C + c for r, c in ind["chromosome"]] for ind in s.population], np.int32)
+                init["fit"] = np.array([ind["fitness"] for ind in s.population], dtype=float)
+                return ok
+            s._initialize_population = init_hook
+            res = s.solve()
+    return {"result": res, "curve": list(s.convergence_curve), "init": init, "draws": dict(tape.counts),
+            "chrom": np.array([[r * C + c for r, c in ind["chromosome"]] for ind in s.population], np.int32),
+            "fit": np.array([ind["fitness"] for ind in s.population], dtype=float),
+            "best_cells": np.array([int(r) * C + int(c) for r, c in res[0]], np.int32)}

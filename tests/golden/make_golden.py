@@ -183,7 +183,48 @@ def fitness_cases():
     np.savez_compressed(os.path.join(HERE, "fitness_cases.npz"), **out)
 
 
+def solver_cases():
+    """Whole-solver trajectories of the reference PSO and GA under the tape (main.py:93-118 parameters,
+    reduced population / iteration counts so the pure-Python reference finishes in seconds)."""
+    grids = {"fig7": env_grids()["fig7"].astype(int), "blocks40": H.blocks_map(40, 0.2, 31)}
+    out = {}
+    for name, g in grids.items():
+        for N, K, seed in ((20, 6, 301), (33, 4, 302)):
+            kw = dict(num_iterations=K, num_particles=N, num_waypoints_per_particle=5, w=0.7, c1=1.5, c2=1.5,
+                      allow_diagonal_moves=True, restrict_diagonal_near_obstacle_policy=True, **POLICY)
+            r = H.run_pso(g, kw, seed)
+            k = f"pso_{name}_{N}"
+            out[k + "_grid"] = g.astype(np.uint8)
+            out[k + "_meta"] = np.array([N, K, seed])
+            out[k + "_curve"] = np.array(r["curve"])
+            out[k + "_stats"] = np.array([float(x) for x in r["result"][1:]])
+            out[k + "_best"] = r["best_cells"]
+            for f in ("pos", "vel", "pbest_fit", "cur_fit"):
+                out[k + "_" + f] = r[f]
+            out[k + "_init_pos"] = r["init"]["pos"]
+            out[k + "_init_vel"] = r["init"]["vel"]
+            out[k + "_init_fit"] = r["init"]["fit"]
+            print(k, "curve", r["curve"][0], "->", r["curve"][-1], "draws", r["draws"])
+            kw = dict(num_generations=K, population_size=N, num_waypoints_per_chromosome=5, mutation_rate=0.1,
+                      crossover_rate=0.8, tournament_size=3, allow_diagonal_moves=True,
+                      restrict_diagonal_near_obstacle_policy=True, **POLICY)
+            r = H.run_ga(g, kw, seed + 50)
+            k = f"ga_{name}_{N}"
+            out[k + "_grid"] = g.astype(np.uint8)
+            out[k + "_meta"] = np.array([N, K, seed + 50])
+            out[k + "_curve"] = np.array(r["curve"])
+            out[k + "_stats"] = np.array([float(x) for x in r["result"][1:]])
+            out[k + "_best"] = r["best_cells"]
+            out[k + "_chrom"] = r["chrom"]
+            out[k + "_fit"] = r["fit"]
+            out[k + "_init_chrom"] = r["init"]["chrom"]
+            out[k + "_init_fit"] = r["init"]["fit"]
+            print(k, "curve", r["curve"][0], "->", r["curve"][-1], "draws", r["draws"])
+    np.savez_compressed(os.path.join(HERE, "solver_cases.npz"), **out)
+
+
 def main():
+    solver_cases()
     astar_cases()
     fitness_cases()
     grids = env_grids()

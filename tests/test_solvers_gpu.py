@@ -1,0 +1,94 @@
+"""Whole-solver parity: PSOSolver / GASolver (CUDA update + fitness kernels, host control flow)
+against trajectories recorded from the unmodified reference under the injected Philox streams.
+Waypoints, positions, chosen individuals and paths bit-exact; fitness / stats bit-exact fp64."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+POLICY = dict(turn_penalty_factor=0.3, safety_penalty_factor=0.8, min_safe_distance=1.8,
+              diagonal_obstacle_penalty_value=100.0, allow_diagonal_moves=True,
+              restrict_diagonal_near_obstacle_policy=True)
+CASES = [(m, n) for m in ("fig7", "blocks40") for n in (20, 33)]
+
+
+@pytest.mark.parametrize("name,N", CASES)
+def test_pso_trajectory(name, N):
+    from maaco_path_planing_b200.pso import PSOSolver
+    g = load_golden("solver_cases")
+    k = f"pso_{name}_{N}"
+    _, K, seed = (int(x) for x in g[k + "_meta"])
+    grid = g[k + "_grid"].astype(int)
+    s = PSOSolver(grid, num_iterations=K, num_particles=N, num_waypoints_per_particle=5, w=0.7, c1=1.5, c2=1.5,
+                  rng_seed=seed, verbose=False, **POLICY)
+    assert s._initialize_particles()
+    S = s._state
+    assert np.array_equal(S["pos"].cpu().numpy(), g[k + "_init_pos"])
+    assert np.array_equal(S["vel"].cpu().numpy(), g[k + "_init_vel"])
+    assert np.array_equal(S["cur_stats"][:, 4].cpu().numpy(), g[k + "_init_fit"])
+    s2 = PSOSolver(grid, num_iterations=K, num_particles=N, num_waypoints_per_particle=5, w=0.7, c1=1.5, c2=1.5,
+                   rng_seed=seed, verbose=False, **POLICY)
+    res = s2.solve()
+    assert np.array_equal(np.array(s2.convergence_curve), g[k + "_curve"])
+    C = grid.shape[1]
+    assert np.array_equal(np.array([r * C + c for r, c in res[0]], np.int32), g[k + "_best"])
+    assert np.array_equal(np.array([float(x) for x in res[1:]]), g[k + "_stats"])
+    S = s2._state
+    assert np.array_equal(S["pos"].cpu().numpy(), g[k + "_pos"])          # every particle, bit-exact after K iterations
+    assert np.array_equal(S["vel"].cpu().numpy(), g[k + "_vel"])
+    assert np.array_equal(S["pbest_fit"].cpu().numpy(), g[k + "_pbest_fit"])
+    assert np.array_equal(S["cur_stats"][:, 4].cpu().numpy(), g[k + "_cur_fit"])
+    parts = s2.particles
+    assert len(parts) == N and parts[0]["pbest_path"][0] == s2.start_node
+
+
+@pytest.mark.parametrize("name,N", CASES)
+def test_ga_trajectory(name, N):
+    from maaco_path_planing_b200.ga_solver import GASolver
+    g = load_golden("solver_cases")
+    k = f"ga_{name}_{N}"
+    _, K, seed = (int(x) for x in g[k + "_meta"])
+    grid = g[k + "_grid"].astype(int)
+    mk = lambda: GASolver(grid, num_generations=K, population_size=N, num_waypoints_per_chromosome=5, mutation_rate=0.1,
+                          crossover_rate=0.8, tournament_size=3, rng_seed=seed, verbose=False, **POLICY)
+    s = mk()
+    assert s._initialize_population()
+    assert np.array_equal(s._pop["chrom"].cpu().numpy(), g[k + "_init_chrom"])
+    assert np.array_equal(s._pop["stats"][:, 4].cpu().numpy(), g[k + "_init_fit"])
+    s2 = mk()
+    res = s2.solve()
+    assert np.array_equal(np.array(s2.convergence_curve), g[k + "_curve"])
+    C = grid.shape[1]
+    assert np.array_equal(np.array([r * C + c for r, c in res[0]], np.int32), g[k + "_best"])
+    assert np.array_equal(np.array([float(x) for x in res[1:]]), g[k + "_stats"])
+    assert np.array_equal(s2._pop["chrom"].cpu().numpy(), g[k + "_chrom"])  # final population, sorted order
+    assert np.array_equal(s2._pop["stats"][:, 4].cpu().numpy(), g[k + "_fit"])
+    pop = s2.population
+    assert len(pop) == N and pop[0]["path"][-1] == s2.target_node
+
+
+def test_astar_solver_dropin_matches_reference_anchor():
+    """SURVEY 8(c) anchor: A* on fig7 with main.py's policy -> 28 cells, L=31.556349186104047, T=17,
+    SP=0.34870130201414323, fitness=36.93531022771536 (values printed by the unmodified reference)."""
+    from maaco_path_planing_b200.astar import AStarSolver
+    grid = load_golden("env_grids")["fig7"].astype(int)
+    a = AStarSolver(grid, **POLICY)
+    path, L, T, SP, DP, F = a.solve()
+    assert len(path) == 28 and L == 31.556349186104047 and T == 17
+    assert SP == 0.34870130201414323 and DP == 0.0 and F == 36.93531022771536
+    assert a.convergence_curve == [L] or abs(a.convergence_curve[0] - L) < 1e-9
+    p2, *_ = a.solve(start_node_override=(3, 3), target_node_override=(3, 3))
+    assert p2 == [(3, 3)]
+    assert a.solve(start_node_override=(0, 4), target_node_override=(5, 5))[0] == []   # obstacle start
+
+
+def test_solver_errors_like_reference():
+    from maaco_path_planing_b200.ga_solver import GASolver
+    from maaco_path_planing_b200.pso import PSOSolver
+    g = np.zeros((6, 6), int)
+    with pytest.raises(ValueError, match="PSO: Start node not found."):
+        PSOSolver(g, 2, 4, 2, 0.7, 1.5, 1.5)
+    with pytest.raises(ValueError, match="GA: Start node not found."):
+        GASolver(g, 2, 4, 2, 0.1, 0.8)
