@@ -153,7 +153,7 @@ __device__ __forceinline__ void heap_pop(AStarSlot &S, int &n, double &f, double
 // One search by one warp.  Returns number of path cells written to out[0..) in forward order
 // (0 = no path / invalid endpoints, -1 = heap overflow).  avoid: bitmap over cells or nullptr.
 // *g_out = g of the popped target entry (+inf when no path).
-__device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant, int src, int dst,
+static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant, int src, int dst,
                             const uint32_t *avoid, int32_t *out, int out_cap, double *g_out,
                             unsigned long long *n_exp, unsigned long long *n_rel) {
     const int lane = threadIdx.x & 31;

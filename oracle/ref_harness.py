@@ -432,3 +432,22 @@ def run_ga(grid, kwargs, seed):
             "chrom": np.array([[r * C + c for r, c in ind["chromosome"]] for ind in s.population], np.int32),
             "fit": np.array([ind["fitness"] for ind in s.population], dtype=float),
             "best_cells": np.array([int(r) * C + int(c) for r, c in res[0]], np.int32)}
+
+
+def run_mpa(grid, kwargs, seed):
+    """Reference MPA.solve_path_planning under the tape; returns result, curve, final population."""
+    ref = load_reference()
+    tape = TapeRandom(seed, locate=make_mpa_locator())
+    C = np.array(grid).shape[1]
+    with with_tape(ref.MPA, tape):
+        with quiet():
+            s = ref.MPA.MPA(grid=np.array(grid), **kwargs)
+            res = s.solve_path_planning()
+    flat, offs = [], [0]
+    for ind in s.population:
+        flat.extend(int(r) * C + int(c) for r, c in ind["path"])
+        offs.append(len(flat))
+    return {"result": res, "curve": [np.inf if v is None else v for v in s.convergence_curve_data],
+            "draws": dict(tape.counts), "pop_cells": np.array(flat, np.int32), "pop_offs": np.array(offs, np.int64),
+            "pop_fit": np.array([ind["fitness"] for ind in s.population], dtype=float),
+            "best_cells": np.array([int(r) * C + int(c) for r, c in res[0]], np.int32)}

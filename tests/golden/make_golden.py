@@ -220,6 +220,23 @@ def solver_cases():
             out[k + "_init_chrom"] = r["init"]["chrom"]
             out[k + "_init_fit"] = r["init"]["fit"]
             print(k, "curve", r["curve"][0], "->", r["curve"][-1], "draws", r["draws"])
+    # MPA (main.py:44-52 parameters; levy_beta=2.0 is the reference's degenerate Levy step, 1.5 a real one)
+    for name, g in grids.items():
+        for N, K, beta, seed in ((20, 12, 2.0, 401), (24, 9, 1.5, 402)):
+            kw = dict(num_predators=N, num_iterations=K, FADs_rate=0.2, P_const=0.5, levy_beta=beta,
+                      turn_penalty_factor=0.1, safety_penalty_factor=0.8, min_safe_distance=1.8,
+                      diagonal_obstacle_penalty=100.0, allow_diagonal_moves=True, restrict_diagonal_near_obstacle=True)
+            r = H.run_mpa(g, kw, seed)
+            k = f"mpa_{name}_{N}"
+            out[k + "_grid"] = g.astype(np.uint8)
+            out[k + "_meta"] = np.array([N, K, seed, int(beta * 10)])
+            out[k + "_curve"] = np.array(r["curve"])
+            out[k + "_stats"] = np.array([float(x) for x in r["result"][1:]])
+            out[k + "_best"] = r["best_cells"]
+            out[k + "_pop_cells"] = r["pop_cells"]
+            out[k + "_pop_offs"] = r["pop_offs"]
+            out[k + "_pop_fit"] = r["pop_fit"]
+            print(k, "curve", r["curve"][0], "->", r["curve"][-1], "draws", r["draws"])
     np.savez_compressed(os.path.join(HERE, "solver_cases.npz"), **out)
 
 

@@ -92,3 +92,43 @@ def test_solver_errors_like_reference():
         PSOSolver(g, 2, 4, 2, 0.7, 1.5, 1.5)
     with pytest.raises(ValueError, match="GA: Start node not found."):
         GASolver(g, 2, 4, 2, 0.1, 0.8)
+
+
+@pytest.mark.parametrize("name,N", [(m, n) for m in ("fig7", "blocks40") for n in (20, 24)])
+def test_mpa_trajectory(name, N):
+    """MPA: phases 1-3 (Brownian / Levy targets, private-A* reconstruction), memory, FADs, sorts and the
+    best cascade vs the reference.  Paths bit-exact; fitness bit-exact fp64.  (The Kinderman-Monahan
+    accept test uses the device log(): a draw within ~1 ulp of the boundary could differ -- p < 1e-12.)"""
+    from maaco_path_planing_b200.mpa import MPA
+    g = load_golden("solver_cases")
+    k = f"mpa_{name}_{N}"
+    _, K, seed, beta10 = (int(x) for x in g[k + "_meta"])
+    grid = g[k + "_grid"].astype(int)
+    s = MPA(grid, num_predators=N, num_iterations=K, FADs_rate=0.2, P_const=0.5, levy_beta=beta10 / 10.0,
+            turn_penalty_factor=0.1, safety_penalty_factor=0.8, min_safe_distance=1.8, diagonal_obstacle_penalty=100.0,
+            allow_diagonal_moves=True, restrict_diagonal_near_obstacle=True, rng_seed=seed, verbose=False)
+    res = s.solve_path_planning()
+    curve = np.array([np.inf if v is None else v for v in s.convergence_curve_data])
+    assert np.array_equal(curve, g[k + "_curve"])
+    C = grid.shape[1]
+    assert np.array_equal(np.array([r * C + c for r, c in res[0]], np.int32), g[k + "_best"])
+    assert np.array_equal(np.array([float(x) for x in res[1:]]), g[k + "_stats"])
+    assert np.array_equal(s._pop["stats"][:, 4].cpu().numpy(), g[k + "_pop_fit"])
+    offs = g[k + "_pop_offs"]
+    cells, ncell = s._pop["cells"].cpu().numpy(), s._pop["ncell"].cpu().numpy()
+    for i in range(N):
+        assert np.array_equal(cells[i, :ncell[i]], g[k + "_pop_cells"][offs[i]:offs[i + 1]]), f"predator {i}"
+
+
+def test_mpa_anchor_and_errors():
+    """the initial MPA population on fig7 is the private-A* S->T path: 28 cells,
+    L=31.556349186104047, fitness = L + 0.1*turns."""
+    from maaco_path_planing_b200.mpa import MPA
+    grid = load_golden("env_grids")["fig7"].astype(int)
+    s = MPA(grid, 8, 3, levy_beta=2.0, turn_penalty_factor=0.1, safety_penalty_factor=0.8, min_safe_distance=1.8,
+            diagonal_obstacle_penalty=100.0, rng_seed=1, verbose=False)
+    ind = s.population[0]
+    assert len(ind["path"]) == 28 and ind["length"] == 31.556349186104047 and ind["safety_penalty"] == 0.0
+    assert ind["fitness"] == ind["length"] + 0.1 * ind["turns"]
+    with pytest.raises(ValueError, match="MPA: Start node not found in grid."):
+        MPA(np.zeros((5, 5), int), 4, 2)
