@@ -1,0 +1,5 @@
+"""Drop-in for the reference module `MAACO` (same module and class names): put
+`maaco_path_planing_b200/dropin` on sys.path instead of the reference directory and
+`from MAACO import MAACO` resolves to the B200 implementation."""
+import _bootstrap  # noqa: F401
+from maaco_path_planing_b200.maaco import MAACO  # noqa: F401,E402
