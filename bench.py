@@ -283,9 +283,69 @@ def run_gpu(args):
                                "ant_steps_per_s": r["ant_steps"] / r["seconds"]}
         r1 = cpu_maaco(grid, args.ants, 4.0, 1)
         out["cpu_baseline"]["one_core_value"] = r1["evals"] / r1["seconds"]
+    if world == 1 and not args.no_extra:
+        del solver, flush
+        torch.cuda.empty_cache()
+        out["extra"] = side_workloads(args, dev, peak)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def side_workloads(args, dev, peak):
+    """The other components of the metric (reported under "extra"; the headline stays the MAACO colony):
+    PSO/GA A*-connector fitness at BASELINE config 3 (512x512, N=4096, W=5, policy main.py:21-24) and one
+    MPA iteration at config 2 (100x100, N=1024, params main.py:44-52)."""
+    import numpy as np
+    import torch
+    from maaco_path_planing_b200 import GridMap, blocks_map
+    from maaco_path_planing_b200.engine import SearchEngine, make_policy
+    from maaco_path_planing_b200.mpa import MPA
+    out = {}
+    # ---- config 3: fitness evaluation of a population of random free-cell waypoint chromosomes ----
+    size, N, W = args.fit_size, args.fit_pop, 5
+    grid = blocks_map(size, 0.20, seed=3000 + size)
+    rng = np.random.default_rng(3)
+    free = np.flatnonzero(grid.ravel() != 1)
+    eng = SearchEngine(GridMap(grid))
+    pol = make_policy(0.3, 0.8, 1.8, 100.0)
+    wps = [torch.as_tensor(free[rng.integers(0, len(free), (N, W))].astype(np.int32), device=dev) for _ in range(3)]
+    eng.waypoint_fitness(wps[0], pol)
+    torch.cuda.synchronize()
+    eng.counters.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for k in range(1, 3):
+        e0.record()
+        cells, ncell, stats = eng.waypoint_fitness(wps[k], pol)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    exp, rel = eng.expansions()
+    t = sum(ms) / 1e3
+    ach = (72.0 * exp + 25.0 * rel) / t / 1e9
+    out["pso_ga_fitness"] = {"workload": f"A*-connector fitness, {N} individuals x {W} waypoints on {size}x{size} blocks map "
+                             "(BASELINE config 3)", "value": 2 * N / t, "unit": "path evals/s", "ms_per_population": 1e3 * t / 2,
+                             "astar_expansions_per_s": exp / t, "expansions_per_eval": exp / (2 * N),
+                             "valid_fraction": float((ncell > 0).float().mean()),
+                             "roofline": {"bound": "hbm", "kernel": "mpp_waypoint_fitness_kernel", "achieved": ach, "peak": peak,
+                                          "unit": "GB/s", "frac": ach / peak,
+                                          "algorithmic_bytes_per_unit": "72 B/expansion + 25 B/relaxation"}}
+    del eng
+    # ---- config 2: MPA iterations ----
+    grid = blocks_map(100, 0.20, seed=2000)
+    mpa = MPA(grid, num_predators=1024, num_iterations=12, FADs_rate=0.2, P_const=0.5, levy_beta=2.0,
+              turn_penalty_factor=0.1, safety_penalty_factor=0.8, min_safe_distance=1.8, diagonal_obstacle_penalty=100.0,
+              rng_seed=2, verbose=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mpa.solve_path_planning()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["mpa"] = {"workload": "MPA 1024 predators x 12 iterations on 100x100 blocks map (BASELINE config 2), "
+                  "sorts + best cascade on the host included", "value": mpa.predator_evaluations / dt,
+                  "unit": "predator-iterations/s", "seconds": dt, "best_fitness": mpa.best_fitness_overall}
+    return out
 
 
 def main():
@@ -299,6 +359,9 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--strong", action="store_true", help="fixed 4096-ant colony sharded over the GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the PSO/GA fitness and MPA side workloads")
+    ap.add_argument("--fit-size", type=int, default=512)
+    ap.add_argument("--fit-pop", type=int, default=4096)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
