@@ -77,11 +77,12 @@ typedef struct {
 
 /* replaces MAACO._initialize_pheromones_maaco (MAACO.py:58-84), _precompute_dist_to_target
  * (:86-91) and the per-candidate heuristic eta'**beta (:197-210, :238) folded into two per-cell
- * tables E[c][cell], c = turn flag.  exp/pow are evaluated on the host with libm (the same
- * functions CPython/NumPy call) so the tables are bit-identical to the reference; outputs are
- * device arrays of rows*cols doubles (dist_t_dev may be NULL).  Synchronous. */
-int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, double *tau0_dev, double *E0_dev,
-                     double *E1_dev, double *dist_t_dev, void *stream);
+ * tables E[cell][c], c = turn flag (interleaved: E01_dev[2*cell + c], 2*rows*cols doubles).  exp/pow
+ * are evaluated on the host with libm (the same functions CPython/NumPy call) so the tables are
+ * bit-identical to the reference; tau0_dev / dist_t_dev are rows*cols doubles (dist_t_dev may be
+ * NULL).  Synchronous. */
+int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, double *tau0_dev, double *E01_dev,
+                     double *dist_t_dev, void *stream);
 
 /* replaces MAACO._calculate_adaptive_q0 (MAACO.py:212-226); pure host function */
 double mpp_maaco_q0(int num_iterations, int iteration, double q0_initial);
@@ -96,16 +97,15 @@ typedef struct {
 /* replaces the ant loop MAACO.py:340-342 -> _construct_ant_solution_maaco (:278-302) with the
  * orientation filter + crossing-prohibition (:100-181) and pseudo-random-proportional selection
  * (:228-262).  Ant i of this call is global ant `ant_offset + i` (its RNG stream id).
- *   tau/E0/E1      rows*cols doubles
+ *   tau / E01      rows*cols / 2*rows*cols doubles (mpp_maaco_tables)
  *   visitT_dev     word-major visited bitmaps: word w of ant i at [w*n_ants + i], ceil(rows*cols/32)
  *                  words per ant; MUST be zero on entry; holds each ant's visited set on return
  *   cells_dev      n_ants x max_cells path cells (cells beyond max_cells are dropped; n_cells still
  *                  counts them)
  *   result_dev     n_ants x mpp_ant_result (:288,:292,:300-302)
  *   steps_dev      optional counter, += number of ant steps taken
- *   lanes_per_ant  8 or 32 (0 = choose)                                                          */
-int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E0_dev, const double *E1_dev,
-                    int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
+ *   lanes_per_ant  8, 16 or 32 lanes cooperate on one ant (0 = choose from n_ants)              */
+int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E01_dev, int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
                     uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, mpp_ant_result *result_dev,
                     unsigned long long *steps_dev, int lanes_per_ant, void *stream);
 

@@ -39,6 +39,7 @@ struct mpp_map {
     int pitch_words;        // padded occupancy row pitch (32-bit words)
     int occ_words;          // (rows+2)*pitch_words, rounded up to a multiple of 4 words (16 B bulk copies)
     uint32_t *occ_dev;      // border-padded bit-packed occupancy; bit (r+1, c+1); border = 1
+    uint8_t *svalid_dev;    // per-cell static move mask, MAACO move order (bounds/obstacle/corner-cut)
     uint8_t *grid_host;     // host copy of the caller's grid (rows*cols) for host-side table builds
     int n_obstacles;
     int sm_count;

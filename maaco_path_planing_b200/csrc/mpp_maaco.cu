@@ -30,9 +30,9 @@ extern "C" double mpp_maaco_q0(int K, int k, double q0_initial) {  // MAACO.py:2
     return q0 < 0.99 ? q0 : 0.99;
 }
 
-extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, double *tau0_dev, double *E0_dev,
-                                double *E1_dev, double *dist_t_dev, void *stream) {
-    MPP_REQUIRE(map && p && tau0_dev && E0_dev && E1_dev, "mpp_maaco_tables: null argument");
+extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, double *tau0_dev, double *E01_dev,
+                                double *dist_t_dev, void *stream) {
+    MPP_REQUIRE(map && p && tau0_dev && E01_dev, "mpp_maaco_tables: null argument");
     MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_tables: map has no start/target");
     const int R = map->rows, C = map->cols;
     const size_t n = (size_t)R * C;
@@ -40,7 +40,7 @@ extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, d
     double dsT = hdist(sr, sc, tr, tc);
     if (dsT < 1e-9) dsT = 1e-9;  // MAACO.py:43-45
     std::vector<double> buf(4 * n);
-    double *tau0 = buf.data(), *E0 = tau0 + n, *E1 = E0 + n, *dt = E1 + n;
+    double *tau0 = buf.data(), *E01 = tau0 + n, *dt = E01 + 2 * n;
     const uint8_t *grid = map->grid_host;
     auto work = [&](int r_lo, int r_hi) {
         for (int r = r_lo; r < r_hi; ++r)
@@ -67,8 +67,8 @@ extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, d
                 double d0 = base + p->a_turn_coef * 0.0, d1 = base + p->a_turn_coef * 1.0;
                 d0 = d0 > 1e-9 ? d0 : 1e-9;
                 d1 = d1 > 1e-9 ? d1 : 1e-9;
-                E0[i] = std::pow(1.0 / d0, p->beta);
-                E1[i] = std::pow(1.0 / d1, p->beta);
+                E01[2 * i] = std::pow(1.0 / d0, p->beta);        // turn flag 0
+                E01[2 * i + 1] = std::pow(1.0 / d1, p->beta);    // turn flag 1
             }
     };
     unsigned nt = std::thread::hardware_concurrency();
@@ -87,8 +87,7 @@ extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, d
     cudaStream_t s = (cudaStream_t)stream;
     MPP_CUDA(cudaSetDevice(map->device));
     MPP_CUDA(cudaMemcpyAsync(tau0_dev, tau0, n * 8, cudaMemcpyHostToDevice, s));
-    MPP_CUDA(cudaMemcpyAsync(E0_dev, E0, n * 8, cudaMemcpyHostToDevice, s));
-    MPP_CUDA(cudaMemcpyAsync(E1_dev, E1, n * 8, cudaMemcpyHostToDevice, s));
+    MPP_CUDA(cudaMemcpyAsync(E01_dev, E01, 2 * n * 8, cudaMemcpyHostToDevice, s));
     if (dist_t_dev) MPP_CUDA(cudaMemcpyAsync(dist_t_dev, dt, n * 8, cudaMemcpyHostToDevice, s));
     MPP_CUDA(cudaStreamSynchronize(s));  // buf is freed on return
     return MPP_OK;
@@ -98,10 +97,9 @@ extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, d
 // K2: tour construction
 // ---------------------------------------------------------------------------------------------
 struct TourArgs {
-    const uint32_t *occ;  // padded occupancy bits (global)
-    int occ_words, pitch;
+    const uint8_t *svalid;  // per-cell static move mask (MAACO move order)
     int R, C, start, target;
-    const double *tau, *E0, *E1;
+    const double *tau, *E01;
     uint32_t it;
     double q0, alpha;
     int n_ants, ant_offset;
@@ -165,39 +163,40 @@ __device__ __noinline__ int roulette_rank(double attr, uint32_t cand, uint32_t g
 
 __device__ __noinline__ double pow_slow(double x, double y) { return pow(x, y); }
 
+// Philox block `blk` of stream (seed, TOUR, it, ant) -> the two uniforms of ant step `blk` (out of line:
+// runs once per LPA steps, keeps the ten rounds out of the step loop's register budget)
+__device__ __noinline__ void tour_uniforms(uint32_t blk, uint32_t ant, uint32_t it, uint32_t k0, uint32_t k1,
+                                           double &u0, double &u1) {
+    const mpp_u4 rb = mpp_philox(blk, ant, it, MPP_CLS_MAACO_TOUR, k0, k1);
+    u0 = mpp_u53(rb.x, rb.y);
+    u1 = mpp_u53(rb.z, rb.w);
+}
+
 template <int LPA>
 __device__ __forceinline__ uint32_t group_ballot(uint32_t gmask, int gshift, bool pred) {
     uint32_t b = __ballot_sync(gmask, pred);
-    return (LPA == 32) ? (b & 0xffu) : ((b >> gshift) & 0xffu);
+    return (LPA == 32) ? (b & 0xffu) : ((b >> gshift) & 0xffu);  // only lanes m < 8 can vote true
 }
 
-// Per step each group (LPA lanes; lane m < 8 owns move m) does: occupancy bits from shared memory,
-// one round of global loads (visited word, tau, E), two ballots, a REDUX max, and the literal
-// selection rules.  Philox blocks are generated LPA steps at a time (lane m computes the block of
-// step base+m) so the per-step cost is two double shuffles instead of ten Philox rounds.
-template <int LPA, bool OCC_SMEM>
-__global__ void __launch_bounds__(MPP_TOUR_THREADS, MPP_TOUR_MIN_BLOCKS) mpp_maaco_tour_kernel(const TourArgs A) {
-    extern __shared__ __align__(16) uint32_t s_occ[];
-    __shared__ __align__(8) uint64_t s_bar;
-    const uint32_t *occ = A.occ;
-    if (OCC_SMEM) {
-        // occupancy grid: HBM -> shared memory as TMA bulk copies (UBLKCP), one per block
-        mpp_stage_bulk(s_occ, A.occ, (uint32_t)A.occ_words * 4u, &s_bar);
-        occ = s_occ;
-    }
+// Per step each group (LPA lanes; lane m < 8 owns move m) does ONE round of loads -- the cell's static
+// move mask (bounds + obstacles + crossing prohibition, precomputed per map), and per move the visited
+// word, tau and E -- then one ballot, a REDUX max and the literal selection rules.  Philox blocks are
+// generated LPA steps at a time (lane m computes the block of step base+m): two double shuffles per step.
+template <int LPA>
+__global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_BLOCKS : 2) mpp_maaco_tour_kernel(const TourArgs A) {
     const int lane = threadIdx.x & 31;
     const int m = lane % LPA;                      // move index handled by this lane (m < 8 active)
     const int gshift = (LPA == 32) ? 0 : (lane / LPA) * LPA;
-    const uint32_t gmask = (LPA == 32) ? 0xffffffffu : (0xffu << gshift);
+    const uint32_t gmask = (LPA == 32) ? 0xffffffffu : (((1u << LPA) - 1u) << gshift);
     const int a = (blockIdx.x * MPP_TOUR_THREADS + threadIdx.x) / LPA;
     if (a >= A.n_ants) return;
-    const bool mv = m < 8;
     // move order MAACO.py:98: (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1); (delta+1) packed 2 bits/move
-    const int mr = mv ? (int)((0xA940u >> (2 * m)) & 3u) - 1 : 0;
-    const int mc = mv ? (int)((0x9224u >> (2 * m)) & 3u) - 1 : 0;
-    const int C = A.C;
-    const int tr = A.target / C, tc = A.target % C;
-    int cr = A.start / C, cc = A.start % C;
+    const int C = A.C, RC = A.R * A.C;
+    const int mm = m & 7;
+    const int delta = ((int)((0xA940u >> (2 * mm)) & 3u) - 1) * C + ((int)((0x9224u >> (2 * mm)) & 3u) - 1);
+    const int target = A.target;
+    const int tr = target / C, tc = target % C;
+    int cur = A.start;
     // orientation masks MAACO.py:146-157
     auto orient_mask = [](int dR, int dC) -> uint32_t {
         uint32_t k = 0xffu;
@@ -207,61 +206,43 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, MPP_TOUR_MIN_BLOCKS) mpp_maa
         if (dR < 0) k &= ~0xE0u;  // dr>0: m5,m6,m7
         return k;
     };
-    const uint32_t P1 = orient_mask(tr - cr, tc - cc);
+    const uint32_t P1 = orient_mask(tr - cur / C, tc - cur % C);
     const uint32_t ant_global = (uint32_t)(A.ant_offset + a);
     const size_t n_ants = (size_t)A.n_ants;
     uint32_t *const visit_a = A.visitT + a;                      // word w of this ant at visit_a[w * n_ants]
     int32_t *const cells_a = A.cells + (size_t)a * A.max_cells;
     const double *const __restrict__ tau = A.tau;
-    const double *const __restrict__ E0 = A.E0;
-    const double *const __restrict__ E1 = A.E1;
+    const double *const __restrict__ E01 = A.E01;                // interleaved: E[2*cell + turn]
+    const uint8_t *const __restrict__ svalid = A.svalid;
     int n_path = 1, prev_m = -1, turns = 0;
     double len = 0.0;
     uint32_t steps = 0;
-    const uint32_t max_steps = 2u * (uint32_t)A.R * (uint32_t)C;  // R*C < 2^30
+    const uint32_t max_steps = 2u * (uint32_t)RC;                 // R*C < 2^30
     bool failed = false;
     double u0_l = 0.0, u1_l = 0.0;
     if (m == 0) {
-        const int s = A.start;
-        visit_a[(size_t)(s >> 5) * n_ants] = 1u << (s & 31);
-        cells_a[0] = s;
+        visit_a[(size_t)(cur >> 5) * n_ants] = 1u << (cur & 31);
+        cells_a[0] = cur;
     }
     __syncwarp(gmask);
-    while (!(cr == tr && cc == tc) && steps < max_steps) {
-        // ---- candidate generation: bounds/obstacle (shared-memory bits), tabu (HBM/L2 bits) ----
-        const int nr = cr + mr, nc = cc + mc;
-        bool blocked = true;
-        if (mv) {
-            const int pb = nc + 1;
-            blocked = (occ[(nr + 1) * A.pitch + (pb >> 5)] >> (pb & 31)) & 1u;
-        }
-        const int j = nr * C + nc;
-        uint32_t tw = 0;
-        double tv = 0.0, ev = 0.0;
-        const bool turn = (n_path >= 2) && (m != prev_m);   // MAACO.py:184-195
-        if (!blocked) {
-            tw = visit_a[(size_t)(j >> 5) * n_ants];
-            tv = tau[j];
-            ev = turn ? E1[j] : E0[j];
-        }
+    while (cur != target && steps < max_steps) {
+        // ---- one round of loads ----
+        const uint32_t sv = svalid[cur];                              // bounds / obstacle / corner-cut (:93-120)
+        int j = cur + delta;
+        j = j < 0 ? 0 : (j >= RC ? RC - 1 : j);                       // clamp: lanes outside the mask are ignored
+        const bool turn = (n_path >= 2) && (m != prev_m);             // MAACO.py:184-195
+        const uint32_t tw = visit_a[(size_t)(j >> 5) * n_ants];
+        const double tv = tau[j];
+        const double ev = E01[2 * (size_t)j + (turn ? 1 : 0)];
         // uniforms: draws 2s (q-test) and 2s+1 (selection) of stream (seed, TOUR, it, ant); block s
         const uint32_t sub = steps & (uint32_t)(LPA - 1);
-        if (sub == 0) {
-            const mpp_u4 rb = mpp_philox(steps + (uint32_t)m, ant_global, A.it, MPP_CLS_MAACO_TOUR, A.k0, A.k1);
-            u0_l = mpp_u53(rb.x, rb.y);
-            u1_l = mpp_u53(rb.z, rb.w);
-        }
+        if (sub == 0) tour_uniforms(steps + (uint32_t)m, ant_global, A.it, A.k0, A.k1, u0_l, u1_l);
         const double u0 = __shfl_sync(gmask, u0_l, gshift + (int)sub);
         const double u1 = __shfl_sync(gmask, u1_l, gshift + (int)sub);
-        const uint32_t o = group_ballot<LPA>(gmask, gshift, blocked);
-        const bool tabu = (tw >> (j & 31)) & 1u;            // tw == 0 for blocked lanes
-        const uint32_t tb = group_ballot<LPA>(gmask, gshift, tabu);
-        // crossing prohibition MAACO.py:100-120: diagonal banned if either orthogonal cell is an obstacle
-        const uint32_t o1 = (o >> 1) & 1u, o3 = (o >> 3) & 1u, o4 = (o >> 4) & 1u, o6 = (o >> 6) & 1u;
-        const uint32_t cut = ((o1 | o3) << 0) | ((o1 | o4) << 2) | ((o6 | o3) << 5) | ((o6 | o4) << 7);
-        const uint32_t valid = ~(o | tb | cut) & 0xffu;
+        const bool free_lane = (m < 8) && ((sv >> m) & 1u) && !((tw >> (j & 31)) & 1u);   // + tabu :93-95
+        const uint32_t valid = group_ballot<LPA>(gmask, gshift, free_lane);
         uint32_t cand = valid & P1;                                   // strategy 1 :165
-        if (!cand) cand = valid & orient_mask(tr - cr, tc - cc);      // strategy 2 :169
+        if (!cand) cand = valid & orient_mask(tr - cur / C, tc - cur % C);   // strategy 2 :169
         if (!cand) cand = valid;                                      // strategy 3 :172-180
         if (!cand) { failed = true; break; }                          // :287-288
         const bool in_c = (cand >> m) & 1u;                           // cand has 8 bits -> false for m >= 8
@@ -303,22 +284,20 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, MPP_TOUR_MIN_BLOCKS) mpp_maa
         const uint32_t sel = group_ballot<LPA>(gmask, gshift, ((pool >> m) & 1u) && __popc(pool & ((1u << m) - 1u)) == k);
         const int pick = __ffs(sel) - 1;
         // ---- advance :293-297 ----
-        const int pr_ = (int)((0xA940u >> (2 * pick)) & 3u) - 1, pc_ = (int)((0x9224u >> (2 * pick)) & 3u) - 1;
-        len += (pr_ != 0 && pc_ != 0) ? MPP_SQRT2 : 1.0;
+        len += ((0xA5u >> pick) & 1u) ? MPP_SQRT2 : 1.0;              // diagonal moves m0,m2,m5,m7
         if (n_path >= 2 && pick != prev_m) ++turns;                   // :264-276 counted on the fly
         prev_m = pick;
         if (m == pick) {
             visit_a[(size_t)(j >> 5) * n_ants] = tw | (1u << (j & 31));
             if (n_path < A.max_cells) cells_a[n_path] = j;
         }
-        cr += pr_;
-        cc += pc_;
+        cur = __shfl_sync(gmask, j, gshift + pick);
         ++n_path;
         ++steps;
         __syncwarp(gmask);
     }
     if (m == 0) {
-        const bool ok = !failed && cr == tr && cc == tc;
+        const bool ok = !failed && cur == target;
         mpp_ant_result res;
         res.length = ok ? len : __longlong_as_double(0x7ff0000000000000ll);
         res.n_cells = ok ? n_path : 0;
@@ -328,40 +307,32 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, MPP_TOUR_MIN_BLOCKS) mpp_maa
     }
 }
 
-extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E0_dev, const double *E1_dev,
+extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E01_dev,
                                int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
                                uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, mpp_ant_result *result_dev,
                                unsigned long long *steps_dev, int lanes_per_ant, void *stream) {
-    MPP_REQUIRE(map && tau_dev && E0_dev && E1_dev && visitT_dev && cells_dev && result_dev,
-                "mpp_maaco_tours: null argument");
+    MPP_REQUIRE(map && tau_dev && E01_dev && visitT_dev && cells_dev && result_dev, "mpp_maaco_tours: null argument");
     MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_tours: map has no start/target");
     MPP_REQUIRE(n_ants > 0 && max_cells > 0, "mpp_maaco_tours: n_ants=%d max_cells=%d", n_ants, max_cells);
-    if (lanes_per_ant == 0) lanes_per_ant = (n_ants <= 64 * map->sm_count) ? 32 : 8;
-    MPP_REQUIRE(lanes_per_ant == 8 || lanes_per_ant == 32, "mpp_maaco_tours: lanes_per_ant must be 8 or 32");
+    if (lanes_per_ant == 0) lanes_per_ant = (n_ants <= 16 * map->sm_count) ? 32 : ((n_ants <= 96 * map->sm_count) ? 16 : 8);
+    MPP_REQUIRE(lanes_per_ant == 8 || lanes_per_ant == 16 || lanes_per_ant == 32,
+                "mpp_maaco_tours: lanes_per_ant must be 8, 16 or 32");
     MPP_CUDA(cudaSetDevice(map->device));
     TourArgs A;
-    A.occ = map->occ_dev; A.occ_words = map->occ_words; A.pitch = map->pitch_words;
+    A.svalid = map->svalid_dev;
     A.R = map->rows; A.C = map->cols; A.start = map->start; A.target = map->target;
-    A.tau = tau_dev; A.E0 = E0_dev; A.E1 = E1_dev;
+    A.tau = tau_dev; A.E01 = E01_dev;
     A.it = (uint32_t)iteration; A.q0 = q0; A.alpha = alpha;
     A.n_ants = n_ants; A.ant_offset = ant_offset;
     A.k0 = (uint32_t)seed; A.k1 = (uint32_t)(seed >> 32);
     A.visitT = visitT_dev; A.cells = cells_dev; A.max_cells = max_cells;
     A.result = result_dev; A.steps = steps_dev;
-    const size_t smem = (size_t)map->occ_words * 4;
-    const bool in_smem = smem <= 200 * 1024;
     const int ants_per_block = MPP_TOUR_THREADS / lanes_per_ant;
     const int blocks = (n_ants + ants_per_block - 1) / ants_per_block;
     cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH(LPA, SM)                                                                                         \
-    do {                                                                                                        \
-        if (SM) MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour_kernel<LPA, SM>,                                   \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-        mpp_maaco_tour_kernel<LPA, SM><<<blocks, MPP_TOUR_THREADS, SM ? smem : 0, s>>>(A);                      \
-    } while (0)
-    if (lanes_per_ant == 32) { if (in_smem) LAUNCH(32, true); else LAUNCH(32, false); }
-    else { if (in_smem) LAUNCH(8, true); else LAUNCH(8, false); }
-#undef LAUNCH
+    if (lanes_per_ant == 32) mpp_maaco_tour_kernel<32><<<blocks, MPP_TOUR_THREADS, 0, s>>>(A);
+    else if (lanes_per_ant == 16) mpp_maaco_tour_kernel<16><<<blocks, MPP_TOUR_THREADS, 0, s>>>(A);
+    else mpp_maaco_tour_kernel<8><<<blocks, MPP_TOUR_THREADS, 0, s>>>(A);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }

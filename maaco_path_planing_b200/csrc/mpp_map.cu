@@ -67,6 +67,29 @@ __global__ void mpp_pack_occ_kernel(const uint8_t *__restrict__ grid, int rows, 
     occ[w] = bits;
 }
 
+// Static per-cell move mask in MAACO's move order (MAACO.py:98): bit m set iff the move stays in bounds,
+// lands on a non-obstacle cell (MAACO.py:93-95 without the tabu test) and, for diagonals, does not cut an
+// obstacle corner (MAACO.py:100-120).  0 for obstacle cells.
+__global__ void mpp_svalid_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, uint8_t *__restrict__ sv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * C) return;
+    const int r = i / C, c = i % C;
+    auto blocked = [&](int rr, int cc) -> bool {
+        const int pb = cc + 1;
+        return (occ[(rr + 1) * pitch + (pb >> 5)] >> (pb & 31)) & 1u;
+    };
+    uint32_t mask = 0;
+    if (!blocked(r, c)) {
+        for (int m = 0; m < 8; ++m) {
+            const int dr = (int)((0xA940u >> (2 * m)) & 3u) - 1, dc = (int)((0x9224u >> (2 * m)) & 3u) - 1;
+            bool ok = !blocked(r + dr, c + dc);
+            if (ok && dr != 0 && dc != 0) ok = !blocked(r + dr, c) && !blocked(r, c + dc);
+            mask |= (ok ? 1u : 0u) << m;
+        }
+    }
+    sv[i] = (uint8_t)mask;
+}
+
 extern "C" int mpp_map_create(const uint8_t *grid_host, int rows, int cols, int device, mpp_map **out) {
     MPP_REQUIRE(grid_host && out, "mpp_map_create: null argument");
     MPP_REQUIRE(rows > 0 && cols > 0 && (long long)rows * cols < (1ll << 30), "mpp_map_create: bad shape %dx%d", rows, cols);
@@ -97,6 +120,9 @@ extern "C" int mpp_map_create(const uint8_t *grid_host, int rows, int cols, int 
     MPP_CUDA(cudaMemcpy(gdev, grid_host, n, cudaMemcpyHostToDevice));
     mpp_pack_occ_kernel<<<(m->occ_words + 255) / 256, 256>>>(gdev, rows, cols, m->pitch_words, m->occ_words, m->occ_dev);
     MPP_CUDA(cudaGetLastError());
+    MPP_CUDA(cudaMalloc(&m->svalid_dev, n));
+    mpp_svalid_kernel<<<((int)n + 255) / 256, 256>>>(m->occ_dev, m->pitch_words, rows, cols, m->svalid_dev);
+    MPP_CUDA(cudaGetLastError());
     MPP_CUDA(cudaDeviceSynchronize());
     MPP_CUDA(cudaFree(gdev));
     *out = m;
@@ -107,6 +133,7 @@ extern "C" void mpp_map_destroy(mpp_map *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->occ_dev) cudaFree(m->occ_dev);
+    if (m->svalid_dev) cudaFree(m->svalid_dev);
     if (m->safety_d2_dev) cudaFree(m->safety_d2_dev);
     if (m->safety_lut_dev) cudaFree(m->safety_lut_dev);
     free(m->grid_host);

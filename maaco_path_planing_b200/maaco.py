@@ -82,14 +82,13 @@ class MAACO:
         f64, i32, i64 = torch.float64, torch.int32, torch.int64
         npad = self.n_words * 32
         self._tau = torch.zeros(npad, dtype=f64, device=dev)        # padded so tau slices all-gather evenly
-        self._E0 = torch.empty(n, dtype=f64, device=dev)
-        self._E1 = torch.empty(n, dtype=f64, device=dev)
+        self._E01 = torch.empty(2 * n, dtype=f64, device=dev)       # eta'**beta, interleaved by turn flag
         self._dist_t = torch.empty(n, dtype=f64, device=dev)
         self._params = _lib.MaacoParams(alpha, beta, rho, Q, a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
                                         C0_initial_pheromone, num_iterations)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(L.mpp_maaco_tables(self.map.handle, C.byref(self._params), _lib.ptr(self._tau), _lib.ptr(self._E0),
-                                      _lib.ptr(self._E1), _lib.ptr(self._dist_t), C.c_void_p(stream)),
+        _lib.check(L.mpp_maaco_tables(self.map.handle, C.byref(self._params), _lib.ptr(self._tau), _lib.ptr(self._E01),
+                                      _lib.ptr(self._dist_t), C.c_void_p(stream)),
                    "mpp_maaco_tables")
         # word-major visited bitmaps of the local ants: [n_words][n_local]
         self._visit_local = torch.zeros(self.n_words * self.n_local, dtype=i32, device=dev)
@@ -129,7 +128,7 @@ class MAACO:
     def _enqueue_tours(self, it, stream):
         nl, off = self.n_local, self.ant_offset
         _lib.check(_lib.lib().mpp_maaco_tours(
-            self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E0), _lib.ptr(self._E1), it,
+            self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E01), it,
             self._calculate_adaptive_q0(it), self.alpha, nl, off, C.c_uint64(self.rng_seed),
             _lib.ptr(self._visit_local), _lib.ptr(self._cells), self.max_cells,
             C.c_void_p(self._result.data_ptr() + 16 * off), _lib.ptr(self._steps), self.lanes_per_ant, stream),
