@@ -314,7 +314,7 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
     MPP_REQUIRE(map && tau_dev && E01_dev && visitT_dev && cells_dev && result_dev, "mpp_maaco_tours: null argument");
     MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_tours: map has no start/target");
     MPP_REQUIRE(n_ants > 0 && max_cells > 0, "mpp_maaco_tours: n_ants=%d max_cells=%d", n_ants, max_cells);
-    if (lanes_per_ant == 0) lanes_per_ant = (n_ants <= 16 * map->sm_count) ? 32 : ((n_ants <= 96 * map->sm_count) ? 16 : 8);
+    if (lanes_per_ant == 0) lanes_per_ant = 32;  // measured on B200: one warp per ant is fastest at every colony size tried (4k..32k ants)
     MPP_REQUIRE(lanes_per_ant == 8 || lanes_per_ant == 16 || lanes_per_ant == 32,
                 "mpp_maaco_tours: lanes_per_ant must be 8, 16 or 32");
     MPP_CUDA(cudaSetDevice(map->device));
@@ -469,6 +469,8 @@ extern "C" int mpp_maaco_best(const mpp_ant_result *result_dev, const int32_t *c
 // (word-major layout => 128-B coalesced loads of 32 ants) and adds deposits in ant order.
 // ---------------------------------------------------------------------------------------------
 #define MPP_PHER_THREADS 256
+struct __align__(16) PherEntry { double d; uint32_t w; uint32_t pad; };
+
 __global__ void __launch_bounds__(MPP_PHER_THREADS)
 mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
                            uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg, int seg_ants,
@@ -476,9 +478,11 @@ mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, i
                            int clear_visit) {
     // visitT is [n_seg][n_words][seg_ants]; global ant = seg*seg_ants + a; this launch owns the
     // cells of words [word0, word0 + n_words)
+    __shared__ PherEntry s_buf[MPP_PHER_THREADS / 32][32];
     const int lane = threadIdx.x & 31;
     const int wl = (blockIdx.x * MPP_PHER_THREADS + threadIdx.x) >> 5;
     if (wl >= n_words) return;
+    PherEntry *sb = s_buf[threadIdx.x >> 5];
     const int RC = R * C;
     const int cell = (word0 + wl) * 32 + lane;
     const bool live = cell < RC;
@@ -486,43 +490,59 @@ mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, i
     double t = 0.0;
     if (live) t = tau[cell] * (1.0 - rho);                                   // :305
     for (int seg = 0; seg < n_seg; ++seg) {
-    uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
-    const double *dep = deposit + (size_t)seg * seg_ants;
-    for (int a0 = 0; a0 < n_ants; a0 += 128) {
-        uint32_t wd[4];
+        uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
+        const double *dep = deposit + (size_t)seg * seg_ants;
+        // software pipeline: the next 128 ants' words are in flight while the current ones are folded
+        uint32_t nx[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int a = a0 + u * 32 + lane;
-            wd[u] = (a < n_ants) ? row[a] : 0u;
-        }
+        for (int u = 0; u < 4; ++u) { const int a = u * 32 + lane; nx[u] = (a < n_ants) ? row[a] : 0u; }
+        for (int a0 = 0; a0 < n_ants; a0 += 128) {
+            uint32_t wd[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            uint32_t nz = __ballot_sync(0xffffffffu, wd[u] != 0u);
-            if (nz) {
+            for (int u = 0; u < 4; ++u) wd[u] = nx[u];
+            if (a0 + 128 < n_ants) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int a = a0 + 128 + u * 32 + lane; nx[u] = (a < n_ants) ? row[a] : 0u; }
+            }
+            uint32_t nz[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nz[u] = __ballot_sync(0xffffffffu, wd[u] != 0u);
+            if ((nz[0] | nz[1] | nz[2] | nz[3]) == 0u) continue;             // ~92 % of the words
+            double d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                                    // deposits of the chunks that need them
                 const int a = a0 + u * 32 + lane;
-                const double d = (a < n_ants) ? dep[a] : 0.0;
+                d[u] = (nz[u] && a < n_ants) ? dep[a] : 0.0;
                 if (clear_visit && wd[u] != 0u) row[a] = 0u;
-                if (__popc(nz) >= 6) {
-                    // dense word (cells near S/T are visited by most ants): branch-free walk over the
-                    // 32 ants in index order; only the dependent DADD chain remains.  t + 0.0 == t exactly.
+            }
 #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t m = nz[u];
+                if (!m) continue;
+                if (__popc(m) >= 6) {
+                    // dense word (cells near S/T are visited by most ants): stage (deposit, word) of the 32
+                    // ants in shared memory and walk them in index order with broadcast reads; what remains
+                    // is the dependent DADD chain.  t + 0.0 == t exactly, so non-depositing ants are harmless.
+                    __syncwarp();
+                    PherEntry e; e.d = d[u]; e.w = wd[u]; e.pad = 0u;
+                    sb[lane] = e;
+                    __syncwarp();
+#pragma unroll 8
                     for (int l = 0; l < 32; ++l) {
-                        const uint32_t wv = __shfl_sync(0xffffffffu, wd[u], l);
-                        const double dv = __shfl_sync(0xffffffffu, d, l);
-                        if ((wv >> lane) & 1u) t += dv;                       // :311
+                        const PherEntry x = sb[l];
+                        if ((x.w >> lane) & 1u) t += x.d;                    // :311
                     }
                 } else {
-                    while (nz) {                                              // ants in index order :306
-                        const int l = __ffs(nz) - 1;
-                        nz &= nz - 1;
+                    while (m) {                                              // ants in index order :306
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
                         const uint32_t wv = __shfl_sync(0xffffffffu, wd[u], l);
-                        const double dv = __shfl_sync(0xffffffffu, d, l);
-                        if ((wv >> lane) & 1u) t += dv;                       // :311
+                        const double dv = __shfl_sync(0xffffffffu, d[u], l);
+                        if ((wv >> lane) & 1u) t += dv;                      // :311
                     }
                 }
             }
         }
-    }
     }
     if (!live) return;
     double b = state->best_len;                                               // :312-316
