@@ -173,7 +173,8 @@ int mpp_astar_max_slots(const mpp_map *map);
  * helper.py:18-53) or MPA._a_star (variant 1, MPA.py:106-151).  avoid_bits_dev: optional n x ceil(rows*cols/32)
  * bitmaps (nodes_to_avoid).  cells_dev: n x max_cells; n_cells_dev[i] = path length (0 = no path / invalid
  * endpoint, -1 = heap_cap overflow, > max_cells = truncated); g_dev[i] = g of the popped target (nullable).
- * counters_dev: optional [2] = (node expansions, successful relaxations), accumulated. */
+ * counters_dev: optional [4] = (node expansions, successful relaxations, ring-bucket pushes, overflow-heap
+ * pushes), accumulated. */
 int mpp_astar_batch(mpp_map *map, int variant, const int32_t *src_dev, const int32_t *dst_dev,
                     const uint32_t *avoid_bits_dev, int n, int allow_diagonal, int restrict_corner,
                     int32_t *cells_dev, int max_cells, int32_t *n_cells_dev, double *g_dev, void *scratch_dev,

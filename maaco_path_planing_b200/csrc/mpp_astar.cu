@@ -102,19 +102,9 @@ extern "C" int mpp_path_stats(mpp_map *map, const int32_t *cells_dev, int max_ce
 // ---------------------------------------------------------------------------------------------
 // scratch layout: [0,256) work counter + error flag; then n_slots search slots
 // ---------------------------------------------------------------------------------------------
-static size_t slot_bytes_host(int rc, int heap_cap) {
-    size_t b = 256;
-    b += ((size_t)rc * 8 + 255) & ~(size_t)255;
-    b += ((size_t)rc * 4 + 255) & ~(size_t)255;
-    size_t hs = (size_t)heap_cap + 64;
-    b += 2 * ((hs * 8 + 255) & ~(size_t)255);
-    b += (hs * 4 + 255) & ~(size_t)255;
-    return b;
-}
-
 extern "C" size_t mpp_astar_scratch_bytes(const mpp_map *map, int n_slots, int heap_cap) {
     if (!map || n_slots <= 0 || heap_cap <= 0) return 0;
-    return 256 + (size_t)n_slots * slot_bytes_host(map->rows * map->cols, heap_cap);
+    return 256 + (size_t)n_slots * astar_slot_bytes(map->rows * map->cols, heap_cap);
 }
 
 extern "C" int mpp_astar_max_slots(const mpp_map *map) { return map ? map->sm_count * 4 * MPP_AS_WARPS : 0; }
@@ -139,6 +129,7 @@ template <bool OCC_SMEM>
 __global__ void __launch_bounds__(MPP_AS_THREADS, 4) mpp_astar_batch_kernel(BatchArgs A) {
     extern __shared__ __align__(16) uint32_t s_occ[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(16) uint8_t s_cnt[MPP_AS_WARPS][MPP_PQ_NB];
     AStarGrid G = A.G;
     if (OCC_SMEM) {
         mpp_stage_bulk(s_occ, A.G.occ, (uint32_t)A.occ_words * 4u, &s_bar);
@@ -148,7 +139,8 @@ __global__ void __launch_bounds__(MPP_AS_THREADS, 4) mpp_astar_batch_kernel(Batc
     const int slot = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) >> 5;
     if (slot >= A.n_slots) return;
     const int rc = G.R * G.C;
-    AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap);
+    AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap,
+                                s_cnt[threadIdx.x >> 5]);
     unsigned int *next = (unsigned int *)A.scratch;
     for (;;) {
         int i = 0;
@@ -157,8 +149,7 @@ __global__ void __launch_bounds__(MPP_AS_THREADS, 4) mpp_astar_batch_kernel(Batc
         if (i >= A.n) break;
         double g;
         const int len = astar_search(G, S, A.variant, A.src[i], A.dst[i], A.avoid ? A.avoid + (size_t)i * A.words : nullptr,
-                                     A.cells + (size_t)i * A.max_cells, A.max_cells, &g,
-                                     A.counters ? A.counters : nullptr, A.counters ? A.counters + 1 : nullptr);
+                                     A.cells + (size_t)i * A.max_cells, A.max_cells, &g, A.counters);
         if (lane == 0) { A.n_cells[i] = len; if (A.g) A.g[i] = g; }
     }
 }
@@ -192,9 +183,9 @@ extern "C" int mpp_astar_batch(mpp_map *map, int variant, const int32_t *src_dev
     A.counters = counters_dev;
     const size_t smem = (size_t)map->occ_words * 4;
     const int blocks = (n_slots + MPP_AS_WARPS - 1) / MPP_AS_WARPS;
-    if (smem <= 48 * 1024) {
+    if (smem <= 32 * 1024) {
         mpp_astar_batch_kernel<true><<<blocks, MPP_AS_THREADS, smem, s>>>(A);
-    } else if (smem <= 56 * 1024) {
+    } else if (smem <= 40 * 1024) {
         MPP_CUDA(cudaFuncSetAttribute(mpp_astar_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mpp_astar_batch_kernel<true><<<blocks, MPP_AS_THREADS, smem, s>>>(A);
     } else {
@@ -231,6 +222,7 @@ template <bool OCC_SMEM>
 __global__ void __launch_bounds__(MPP_AS_THREADS, 4) mpp_waypoint_fitness_kernel(ChainArgs A) {
     extern __shared__ __align__(16) uint32_t s_occ[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(16) uint8_t s_cnt[MPP_AS_WARPS][MPP_PQ_NB];
     AStarGrid G = A.G;
     StatsCtx X = A.X;
     if (OCC_SMEM) {
@@ -242,7 +234,8 @@ __global__ void __launch_bounds__(MPP_AS_THREADS, 4) mpp_waypoint_fitness_kernel
     const int slot = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) >> 5;
     if (slot >= A.n_slots) return;
     const int rc = G.R * G.C;
-    AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap);
+    AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap,
+                                s_cnt[threadIdx.x >> 5]);
     unsigned int *next = (unsigned int *)A.scratch;
     for (;;) {
         int i = 0;
@@ -260,8 +253,7 @@ __global__ void __launch_bounds__(MPP_AS_THREADS, 4) mpp_waypoint_fitness_kernel
             const int goal = (k < A.W) ? A.wps[(size_t)i * A.W + k] : A.target;
             // the segment is written over the tail cell of the path (segment[0] == current_start)
             const int cap = A.max_cells - (n - 1);
-            const int sl = astar_search(G, S, 0, cur, goal, vis, path + (n - 1), cap, nullptr,
-                                        A.counters ? A.counters : nullptr, A.counters ? A.counters + 1 : nullptr);
+            const int sl = astar_search(G, S, 0, cur, goal, vis, path + (n - 1), cap, nullptr, A.counters);
             if (sl < 0) { status = -1; break; }
             if (sl == 0 || (sl == 1 && cur != goal)) { status = 0; break; }          // pso.py:77,87 -> []
             if (sl > cap) { status = 2; n += sl - 1; break; }                        // truncated
@@ -305,9 +297,9 @@ extern "C" int mpp_waypoint_fitness(mpp_map *map, const int32_t *waypoints_dev, 
     A.scratch = (char *)scratch_dev; A.n_slots = n_slots; A.heap_cap = heap_cap; A.counters = counters_dev;
     const size_t smem = (size_t)map->occ_words * 4;
     const int blocks = (n_slots + MPP_AS_WARPS - 1) / MPP_AS_WARPS;
-    if (smem <= 48 * 1024) {
+    if (smem <= 32 * 1024) {
         mpp_waypoint_fitness_kernel<true><<<blocks, MPP_AS_THREADS, smem, s>>>(A);
-    } else if (smem <= 56 * 1024) {
+    } else if (smem <= 40 * 1024) {
         MPP_CUDA(cudaFuncSetAttribute(mpp_waypoint_fitness_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mpp_waypoint_fitness_kernel<true><<<blocks, MPP_AS_THREADS, smem, s>>>(A);
     } else {

@@ -29,34 +29,55 @@ struct AStarGrid {
     int allow_diag, restrict_corner;
 };
 
-// per-warp scratch slot (HBM).  meta word: [31:8] stamp, bit4 closed, bit3 in_open, [2:0] parent move.
+// ---------------------------------------------------------------------------------------------
+// Priority queue = exact extract-min over (f, g, cell), built for one warp:
+//   * a ring of MPP_PQ_NB buckets keyed by floor((f - f0) * MPP_PQ_SCALE), MPP_PQ_CAP (= 32, one per lane)
+//     entries each, bucket fill counts in shared memory.  push = one fire-and-forget store; pop = one
+//     coalesced load of the lowest non-empty bucket + a warp arg-min (bucket index is monotone in f, so the
+//     global minimum lives in the lowest non-empty bucket);
+//   * an overflow 32-ary min-heap in HBM for entries outside the ring window or landing in a full bucket;
+//     its root key is cached in registers and compared with the ring minimum on every pop.
+// Either structure alone is exact; together they keep the common case at one memory round trip per pop.
+// ---------------------------------------------------------------------------------------------
+#define MPP_PQ_NB 2048
+#define MPP_PQ_CAP 32
+#define MPP_PQ_SCALE 256.0
+
+struct __align__(16) AStarRec { double g; uint32_t meta; uint32_t pad; };  // meta: [31:8] stamp, bit4 closed, bit3 in_open, [2:0] parent move
+
+// per-warp scratch slot (HBM)
 struct AStarSlot {
-    double *g;
-    uint32_t *meta;
-    double *hf, *hg;
+    AStarRec *rec;
+    double *bf, *bg;   // ring buckets
+    int32_t *bc;
+    double *hf, *hg;   // overflow heap
     int32_t *hc;
-    uint32_t *hdr;  // hdr[0] = stamp counter
+    uint32_t *hdr;     // hdr[0] = stamp counter
+    uint8_t *cnt;      // shared memory: MPP_PQ_NB bucket fill counts of this warp
     int heap_cap;
 };
 
+__host__ __device__ __forceinline__ size_t astar_align256(size_t b) { return (b + 255) & ~(size_t)255; }
 __host__ __device__ __forceinline__ size_t astar_slot_bytes(int rc, int heap_cap) {
-    size_t b = 256;                                  // header
-    b += ((size_t)rc * 8 + 255) & ~(size_t)255;      // g
-    b += ((size_t)rc * 4 + 255) & ~(size_t)255;      // meta
-    size_t hs = (size_t)heap_cap + 64;               // storage index = node + 31, padded
-    b += 2 * ((hs * 8 + 255) & ~(size_t)255);        // hf, hg
-    b += (hs * 4 + 255) & ~(size_t)255;              // hc
+    size_t b = 256;                                                    // header
+    b += astar_align256((size_t)rc * sizeof(AStarRec));
+    b += 2 * astar_align256((size_t)MPP_PQ_NB * MPP_PQ_CAP * 8) + astar_align256((size_t)MPP_PQ_NB * MPP_PQ_CAP * 4);
+    const size_t hs = (size_t)heap_cap + 64;                           // heap storage index = node + 31, padded
+    b += 2 * astar_align256(hs * 8) + astar_align256(hs * 4);
     return b;
 }
-__device__ __forceinline__ AStarSlot astar_slot_at(char *base, int rc, int heap_cap) {
+__device__ __forceinline__ AStarSlot astar_slot_at(char *base, int rc, int heap_cap, uint8_t *cnt_smem) {
     AStarSlot s;
     s.hdr = (uint32_t *)base; base += 256;
-    s.g = (double *)base; base += ((size_t)rc * 8 + 255) & ~(size_t)255;
-    s.meta = (uint32_t *)base; base += ((size_t)rc * 4 + 255) & ~(size_t)255;
-    size_t hs = (size_t)heap_cap + 64;
-    s.hf = (double *)base; base += (hs * 8 + 255) & ~(size_t)255;
-    s.hg = (double *)base; base += (hs * 8 + 255) & ~(size_t)255;
+    s.rec = (AStarRec *)base; base += astar_align256((size_t)rc * sizeof(AStarRec));
+    s.bf = (double *)base; base += astar_align256((size_t)MPP_PQ_NB * MPP_PQ_CAP * 8);
+    s.bg = (double *)base; base += astar_align256((size_t)MPP_PQ_NB * MPP_PQ_CAP * 8);
+    s.bc = (int32_t *)base; base += astar_align256((size_t)MPP_PQ_NB * MPP_PQ_CAP * 4);
+    const size_t hs = (size_t)heap_cap + 64;
+    s.hf = (double *)base; base += astar_align256(hs * 8);
+    s.hg = (double *)base; base += astar_align256(hs * 8);
     s.hc = (int32_t *)base;
+    s.cnt = cnt_smem;
     s.heap_cap = heap_cap;
     return s;
 }
@@ -104,7 +125,7 @@ __device__ __forceinline__ int warp_argmin_key(double f, double g, int cell) {
 
 #define HIDX(k) ((k) + 31)  // node k -> storage index; children of k = nodes 32k+1..32k+32 (storage aligned to 32)
 
-// Push (f,g,cell) -- warp-uniform arguments.  Returns false on overflow.
+// Overflow heap push (f,g,cell) -- warp-uniform arguments.  Returns false on overflow.
 __device__ __forceinline__ bool heap_push(AStarSlot &S, int &n, double f, double g, int cell) {
     if (n >= S.heap_cap) return false;
     int k = n++;
@@ -122,7 +143,7 @@ __device__ __forceinline__ bool heap_push(AStarSlot &S, int &n, double f, double
     return true;
 }
 
-// Pop the minimum -- returns it in (f,g,cell) (warp-uniform).  n > 0 required.
+// Overflow heap pop -- returns the minimum in (f,g,cell) (warp-uniform).  n > 0 required.
 __device__ __forceinline__ void heap_pop(AStarSlot &S, int &n, double &f, double &g, int &cell) {
     const int lane = threadIdx.x & 31;
     f = S.hf[HIDX(0)]; g = S.hg[HIDX(0)]; cell = S.hc[HIDX(0)];
@@ -150,12 +171,83 @@ __device__ __forceinline__ void heap_pop(AStarSlot &S, int &n, double &f, double
     __syncwarp();
 }
 
+struct AStarPQ {
+    int qlo;         // every ring entry has bucket index >= qlo
+    int n_ring, hn;  // entries in the ring / in the overflow heap
+    double f0;       // bucket origin (f of the start node; f never drops below it except by rounding)
+    double rf, rg;   // cached overflow-heap root key (valid when hn > 0)
+    int rc;
+    unsigned long long ring_pushes, heap_pushes;
+};
+
+__device__ __forceinline__ bool pq_push(AStarSlot &S, AStarPQ &Q, double f, double g, int cell) {
+    const int lane = threadIdx.x & 31;
+    const double x = (f - Q.f0) * MPP_PQ_SCALE;
+    const int q = (x >= 0.0) ? (x < 2.0e9 ? (int)x : 0x7ffffff0) : -1;
+    if (Q.n_ring == 0 && q >= 0) Q.qlo = q;                      // empty ring: re-centre the window
+    int c = MPP_PQ_CAP;
+    const int b = q & (MPP_PQ_NB - 1);
+    if (q >= Q.qlo && q - Q.qlo < MPP_PQ_NB) c = S.cnt[b];
+    if (c < MPP_PQ_CAP) {
+        if (lane == 0) {
+            const int i = b * MPP_PQ_CAP + c;
+            S.bf[i] = f; S.bg[i] = g; S.bc[i] = cell;
+            S.cnt[b] = (uint8_t)(c + 1);
+        }
+        __syncwarp();
+        ++Q.n_ring;
+        ++Q.ring_pushes;
+        return true;
+    }
+    const bool was_empty = Q.hn == 0;
+    if (!heap_push(S, Q.hn, f, g, cell)) return false;
+    if (was_empty || key_less(f, g, cell, Q.rf, Q.rg, Q.rc)) { Q.rf = f; Q.rg = g; Q.rc = cell; }
+    ++Q.heap_pushes;
+    return true;
+}
+
+// extract-min (requires n_ring + hn > 0)
+__device__ __forceinline__ void pq_pop(AStarSlot &S, AStarPQ &Q, double &f, double &g, int &cell) {
+    const int lane = threadIdx.x & 31;
+    double cf = __longlong_as_double(MPP_INF_BITS), cg = 0.0, mf = cf, mg = 0.0;
+    int cc = 0x7fffffff, mc = 0x7fffffff, w = 0, b = 0, c = 0;
+    if (Q.n_ring > 0) {
+        int base = Q.qlo;
+        for (;;) {                                              // lowest non-empty bucket (counts in shared memory)
+            const uint32_t m = __ballot_sync(0xffffffffu, S.cnt[(base + lane) & (MPP_PQ_NB - 1)] != 0);
+            if (m) { Q.qlo = base + __ffs(m) - 1; break; }
+            base += 32;
+        }
+        b = Q.qlo & (MPP_PQ_NB - 1);
+        c = S.cnt[b];
+        if (lane < c) { const int i = b * MPP_PQ_CAP + lane; cf = S.bf[i]; cg = S.bg[i]; cc = S.bc[i]; }
+        w = warp_argmin_key(cf, cg, cc);
+        mf = __shfl_sync(0xffffffffu, cf, w); mg = __shfl_sync(0xffffffffu, cg, w); mc = __shfl_sync(0xffffffffu, cc, w);
+    }
+    if (Q.hn > 0 && (Q.n_ring == 0 || key_less(Q.rf, Q.rg, Q.rc, mf, mg, mc))) {
+        heap_pop(S, Q.hn, f, g, cell);
+        if (Q.hn > 0) { Q.rf = S.hf[HIDX(0)]; Q.rg = S.hg[HIDX(0)]; Q.rc = S.hc[HIDX(0)]; }
+        return;
+    }
+    f = mf; g = mg; cell = mc;
+    const int last = c - 1;
+    if (w != last) {                                            // fill the hole with the bucket's last entry
+        const double lf = __shfl_sync(0xffffffffu, cf, last), lg = __shfl_sync(0xffffffffu, cg, last);
+        const int lc = __shfl_sync(0xffffffffu, cc, last);
+        if (lane == 0) { const int i = b * MPP_PQ_CAP + w; S.bf[i] = lf; S.bg[i] = lg; S.bc[i] = lc; }
+    }
+    if (lane == 0) S.cnt[b] = (uint8_t)last;
+    __syncwarp();
+    --Q.n_ring;
+}
+
 // One search by one warp.  Returns number of path cells written to out[0..) in forward order
 // (0 = no path / invalid endpoints, -1 = heap overflow).  avoid: bitmap over cells or nullptr.
-// *g_out = g of the popped target entry (+inf when no path).
+// *g_out = g of the popped target entry (+inf when no path).  counters: [0] expansions, [1] relaxations,
+// [2] ring pushes, [3] overflow-heap pushes (nullable).
 static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant, int src, int dst,
                             const uint32_t *avoid, int32_t *out, int out_cap, double *g_out,
-                            unsigned long long *n_exp, unsigned long long *n_rel) {
+                            unsigned long long *counters) {
     const int lane = threadIdx.x & 31;
     const int C = G.C;
     const int sr = src / C, sc = src % C, tr = dst / C, tc = dst % C;
@@ -164,19 +256,22 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
     if (variant == 1 && src == dst) { if (lane == 0 && out_cap > 0) out[0] = src; if (g_out) *g_out = 0.0; __syncwarp(); return 1; }  // MPA.py:107-108
     if (occ_bit(G, sr, sc) || occ_bit(G, tr, tc)) return 0;        // astar.py:37-39 / MPA.py:109-111
     if (variant == 0 && src == dst) { if (lane == 0 && out_cap > 0) out[0] = src; if (g_out) *g_out = 0.0; __syncwarp(); return 1; }  // astar.py:41-42
-    // new stamp for this search (meta words of older searches become invalid without clearing)
+    // new stamp for this search (records of older searches become invalid without clearing)
     uint32_t stamp = S.hdr[0] + 1;
-    if (stamp >= (1u << 24)) {  // wrap: clear the meta array once every 16M searches
-        for (int i = lane; i < G.R * C; i += 32) S.meta[i] = 0;
+    if (stamp >= (1u << 24)) {  // wrap: clear the records once every 16M searches
+        for (int i = lane; i < G.R * C; i += 32) S.rec[i].meta = 0;
         stamp = 1;
     }
     __syncwarp();
     if (lane == 0) S.hdr[0] = stamp;
     const uint32_t stamp_hi = stamp << 8;
-    int n = 0;
-    if (lane == 0) { S.g[src] = 0.0; S.meta[src] = stamp_hi | 8u; }
+    for (int i = lane; i < MPP_PQ_NB / 4; i += 32) ((uint32_t *)S.cnt)[i] = 0u;
+    if (lane == 0) { AStarRec r0; r0.g = 0.0; r0.meta = stamp_hi | 8u; r0.pad = 0u; S.rec[src] = r0; }
     __syncwarp();
-    heap_push(S, n, hdist_dev(sr, sc, tr, tc), 0.0, src);          // astar.py:45 / MPA.py:113
+    AStarPQ Q;
+    Q.qlo = 0; Q.n_ring = 0; Q.hn = 0; Q.rf = 0.0; Q.rg = 0.0; Q.rc = 0; Q.ring_pushes = 0; Q.heap_pushes = 0;
+    Q.f0 = hdist_dev(sr, sc, tr, tc);
+    pq_push(S, Q, Q.f0, 0.0, src);                                 // astar.py:45 / MPA.py:113
     const long long max_steps = (long long)G.R * C * (variant == 0 ? 3 : 2);   // astar.py:58 / MPA.py:118
     long long steps = 0;
     unsigned long long exps = 0, rels = 0;
@@ -186,56 +281,66 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
     const double step_cost = (lane & 7) >= 4 ? MPP_ASTAR_SQRT2 : 1.0;  // distance_euclidean: sqrt(1)=1, sqrt(2)
     int found = 0;
     double cur_g = 0.0;
-    while (n > 0 && steps < max_steps) {
+    while (Q.n_ring + Q.hn > 0 && steps < max_steps) {
         double cf;
         int cur;
-        heap_pop(S, n, cf, cur_g, cur);
-        uint32_t mcur = S.meta[cur];
-        if (variant == 0) {
-            if (cur == dst) { found = 1; ++steps; break; }                     // astar.py:64
-            if (mcur & 16u) continue;                                         // stale (lazily deleted) entry
-            ++steps;
-            if (lane == 0) S.meta[cur] = mcur | 16u;                           // closed_set.add astar.py:74
-        } else {
-            ++steps;
-            if (cur == dst) { found = 1; break; }                              // MPA.py:123
-            if (lane == 0) S.meta[cur] = mcur & ~8u;                           // left the open set
-        }
-        ++exps;
+        pq_pop(S, Q, cf, cur_g, cur);
+        if (cur == dst) { found = 1; ++steps; break; }                        // astar.py:64 / MPA.py:123
+        // ---- one round of loads: the popped node's record and, per lane, a neighbour's record + avoid word ----
         const int cr = cur / C, cc = cur % C;
-        const double gbase = (variant == 0) ? cur_g : S.g[cur];                // astar.py:85 vs MPA.py:135
-        __syncwarp();
-        // ---- relax the neighbours, one per lane ----
-        bool push = false;
+        const uint4 vcur = *reinterpret_cast<const uint4 *>(&S.rec[cur]);
+        bool open_nb = false;
         int j = 0;
-        double tg = 0.0;
+        uint4 vj = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t aw = 0u;
         if (nb_lane) {
             const int nr = cr + dr, nc = cc + dc;
             bool blocked = occ_bit(G, nr, nc);
             if (!blocked && (lane >= 4) && G.restrict_corner)                  // helper.py:45-49 / MPA.py:86-96
                 blocked = occ_bit(G, cr + dr, cc) || occ_bit(G, cr, cc + dc);
             if (!blocked) {
+                open_nb = true;
                 j = nr * C + nc;
-                const bool av = avoid ? ((avoid[j >> 5] >> (j & 31)) & 1u) : false;
-                uint32_t mj = S.meta[j];
-                const bool seen = (mj & 0xffffff00u) == stamp_hi;
-                if (!seen) mj = 0;
-                bool excluded;
-                if (variant == 0) excluded = (av && j != src && j != dst) || (mj & 16u);   // closed set astar.py:51-56,80
-                else excluded = av;                                                       // MPA.py:132
-                if (!excluded) {
-                    tg = gbase + step_cost;
-                    const double gj = seen ? S.g[j] : INF;
-                    if (tg < gj) {                                             // astar.py:87 / MPA.py:137
-                        S.g[j] = tg;
-                        // parent = the move taken cur -> j; variant 1 keeps a stale key if already in open
-                        push = (variant == 0) ? true : !(mj & 8u);
-                        S.meta[j] = stamp_hi | (mj & 16u) | 8u | (uint32_t)(lane & 7);
-                        ++rels;
-                    }
+                vj = *reinterpret_cast<const uint4 *>(&S.rec[j]);
+                if (avoid) aw = avoid[j >> 5];
+            }
+        }
+        const uint32_t mcur = vcur.z;
+        if (variant == 0) {
+            if (mcur & 16u) continue;                                         // stale (lazily deleted) entry
+            ++steps;
+            if (lane == 0) S.rec[cur].meta = mcur | 16u;                       // closed_set.add astar.py:74
+        } else {
+            ++steps;
+            if (lane == 0) S.rec[cur].meta = mcur & ~8u;                       // left the open set
+        }
+        ++exps;
+        const double gcur = __longlong_as_double((long long)(((unsigned long long)vcur.y << 32) | vcur.x));
+        const double gbase = (variant == 0) ? cur_g : gcur;                    // astar.py:85 vs MPA.py:135
+        // ---- relax the neighbours, one per lane ----
+        bool push = false;
+        double tg = 0.0;
+        if (open_nb) {
+            const bool av = (aw >> (j & 31)) & 1u;
+            uint32_t mj = vj.z;
+            const bool seen = (mj & 0xffffff00u) == stamp_hi;
+            if (!seen) mj = 0;
+            bool excluded;
+            if (variant == 0) excluded = (av && j != src && j != dst) || (mj & 16u);   // closed set astar.py:51-56,80
+            else excluded = av;                                                       // MPA.py:132
+            if (!excluded) {
+                tg = gbase + step_cost;
+                const double gj = seen ? __longlong_as_double((long long)(((unsigned long long)vj.y << 32) | vj.x)) : INF;
+                if (tg < gj) {                                                 // astar.py:87 / MPA.py:137
+                    // parent = the move taken cur -> j; variant 1 keeps a stale key if already in open
+                    push = (variant == 0) ? true : !(mj & 8u);
+                    AStarRec nrc; nrc.g = tg; nrc.meta = stamp_hi | (mj & 16u) | 8u | (uint32_t)(lane & 7); nrc.pad = 0u;
+                    S.rec[j] = nrc;
+                    ++rels;
                 }
             }
         }
+        __syncwarp();
         uint32_t pm = __ballot_sync(0xffffffffu, push);
         while (pm) {
             const int l = __ffs(pm) - 1;
@@ -243,13 +348,15 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
             const int pj = __shfl_sync(0xffffffffu, j, l);
             const double ptg = __shfl_sync(0xffffffffu, tg, l);
             const double pf = ptg + hdist_dev(pj / C, pj % C, tr, tc);         // astar.py:90 / MPA.py:140
-            if (!heap_push(S, n, pf, ptg, pj)) return -1;
+            if (!pq_push(S, Q, pf, ptg, pj)) return -1;
         }
     }
     rels = __reduce_add_sync(0xffffffffu, (uint32_t)rels);
-    if (lane == 0) {
-        if (n_exp) atomicAdd(n_exp, exps);
-        if (n_rel) atomicAdd(n_rel, rels);
+    if (lane == 0 && counters) {
+        atomicAdd(counters, exps);
+        atomicAdd(counters + 1, rels);
+        atomicAdd(counters + 2, Q.ring_pushes);
+        atomicAdd(counters + 3, Q.heap_pushes);
     }
     if (!found) return 0;
     if (g_out) *g_out = cur_g;
@@ -261,7 +368,7 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
             if (len < out_cap) out[len] = t;
             ++len;
             if (t == src) break;
-            const uint32_t mv = S.meta[t] & 7u;
+            const uint32_t mv = S.rec[t].meta & 7u;
             const int pdr = (int)((MPP_NB_R >> (2 * mv)) & 3u) - 1, pdc = (int)((MPP_NB_C >> (2 * mv)) & 3u) - 1;
             t -= pdr * C + pdc;
         }

@@ -112,6 +112,7 @@ template <bool OCC_SMEM>
 __global__ void __launch_bounds__(MPP_MPA_THREADS, 4) mpp_mpa_iteration_kernel(MpaArgs A) {
     extern __shared__ __align__(16) uint32_t s_occ[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(16) uint8_t s_cnt[MPP_MPA_WARPS][MPP_PQ_NB];
     AStarGrid G = A.G;
     StatsCtx X = A.X;
     if (OCC_SMEM) {
@@ -123,11 +124,11 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 4) mpp_mpa_iteration_kernel(M
     const int slot = (blockIdx.x * MPP_MPA_THREADS + threadIdx.x) >> 5;
     if (slot >= A.n_slots) return;
     const int rc = G.R * G.C, C = G.C;
-    AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap);
+    AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap,
+                                s_cnt[threadIdx.x >> 5]);
     unsigned int *next = (unsigned int *)A.scratch;
     uint32_t *avoid = A.avoid + (size_t)slot * A.words;
     int32_t *tmp = A.tmp_cells + (size_t)slot * A.max_cells;
-    unsigned long long *ce = A.counters ? A.counters : nullptr, *cr_ = A.counters ? A.counters + 1 : nullptr;
     for (;;) {
         int i = 0;
         if (lane == 0) i = (int)atomicAdd(next, 1u);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 4) mpp_mpa_iteration_kernel(M
                 int a_start = cur;
                 if (!occ_bit(G, inter / C, inter % C) && inter != a_start) {       // :298
                     const int cap = A.max_cells - (n - 1);
-                    const int sl = astar_search(G, S, 1, a_start, inter, avoid, out + (n - 1), cap, nullptr, ce, cr_);
+                    const int sl = astar_search(G, S, 1, a_start, inter, avoid, out + (n - 1), cap, nullptr, A.counters);
                     if (sl < 0) st_flag = 1;
                     else if (sl > cap) st_flag = 2;
                     else if (sl > 1) {                                             // :300-305
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 4) mpp_mpa_iteration_kernel(M
                 }
                 if (a_start != A.target && st_flag == 0) {                         // :306-309
                     const int cap = A.max_cells - (n - 1);
-                    const int sl = astar_search(G, S, 1, a_start, A.target, avoid, out + (n - 1), cap, nullptr, ce, cr_);
+                    const int sl = astar_search(G, S, 1, a_start, A.target, avoid, out + (n - 1), cap, nullptr, A.counters);
                     if (sl < 0) st_flag = 1;
                     else if (sl > cap) st_flag = 2;
                     else if (sl > 1) n += sl - 1;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 4) mpp_mpa_iteration_kernel(M
                 const int r = fr.below(G.R), c = fr.below(G.C);                    // :391
                 const int node = r * C + c;
                 if (!occ_bit(G, r, c)) {
-                    const int sl1 = astar_search(G, S, 1, A.start, node, nullptr, tmp, A.max_cells, nullptr, ce, cr_);
+                    const int sl1 = astar_search(G, S, 1, A.start, node, nullptr, tmp, A.max_cells, nullptr, A.counters);
                     if (sl1 < 0) st_flag = 1;
                     else if (sl1 > A.max_cells) st_flag = 2;
                     else if (sl1 > 0) {
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 4) mpp_mpa_iteration_kernel(M
                         __syncwarp();
                         warp_mark(avoid, tmp, sl1 - 1);                            // set(p1[:-1]) :396
                         const int cap = A.max_cells - (sl1 - 1);
-                        const int sl2 = astar_search(G, S, 1, node, A.target, avoid, tmp + (sl1 - 1), cap, nullptr, ce, cr_);
+                        const int sl2 = astar_search(G, S, 1, node, A.target, avoid, tmp + (sl1 - 1), cap, nullptr, A.counters);
                         if (sl2 < 0) st_flag = 1;
                         else if (sl2 > cap) st_flag = 2;
                         else if (sl2 > 0) {
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 4) mpp_mpa_iteration_kernel(M
                     }
                 }
             } else {
-                const int sl = astar_search(G, S, 1, A.start, A.target, nullptr, tmp, A.max_cells, nullptr, ce, cr_);  // :405
+                const int sl = astar_search(G, S, 1, A.start, A.target, nullptr, tmp, A.max_cells, nullptr, A.counters);  // :405
                 if (sl < 0) st_flag = 1;
                 else if (sl > A.max_cells) st_flag = 2;
                 else if (sl > 0) n2 = sl;
@@ -306,9 +307,9 @@ extern "C" int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_p
     A.counters = counters_dev;
     const size_t smem = (size_t)map->occ_words * 4;
     const int blocks = (n_slots + MPP_MPA_WARPS - 1) / MPP_MPA_WARPS;
-    if (smem <= 48 * 1024) {
+    if (smem <= 32 * 1024) {
         mpp_mpa_iteration_kernel<true><<<blocks, MPP_MPA_THREADS, smem, s>>>(A);
-    } else if (smem <= 56 * 1024) {
+    } else if (smem <= 40 * 1024) {
         MPP_CUDA(cudaFuncSetAttribute(mpp_mpa_iteration_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mpp_mpa_iteration_kernel<true><<<blocks, MPP_MPA_THREADS, smem, s>>>(A);
     } else {

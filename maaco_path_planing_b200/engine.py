@@ -38,7 +38,7 @@ class SearchEngine:
         self.max_cells = int(max_cells or min(self.n, max(4096, 16 * (self.rows + self.cols))))
         self._scratch = None
         self._scratch_key = None
-        self.counters = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.counters = torch.zeros(4, dtype=torch.int64, device=self.device)  # expansions, relaxations, ring / heap pushes
         self.launches = 0
 
     # -- buffers ---------------------------------------------------------------------------------
@@ -63,6 +63,11 @@ class SearchEngine:
     def expansions(self):
         c = self.counters.cpu().numpy()
         return int(c[0]), int(c[1])
+
+    def queue_stats(self):
+        """(ring pushes, overflow-heap pushes) of the searches so far."""
+        c = self.counters.cpu().numpy()
+        return int(c[2]), int(c[3])
 
     # -- K5 ---------------------------------------------------------------------------------------
     def astar_batch(self, variant, src, dst, avoid_bits=None, allow_diagonal=True, restrict_corner=True):

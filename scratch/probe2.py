@@ -16,3 +16,4 @@ for size, N in ((100, 1024), (256, 1024), (512, 1024), (512, 4096)):
     e, r = eng.expansions()
     nc = ncell.cpu().numpy()
     print(f'size={size} N={N} time={dt*1e3:.1f} ms evals/s={N/dt:.0f} valid={(nc>0).sum()} meanlen={nc[nc>0].mean():.0f} expansions={e} ({e/N:.0f}/eval) exp/s={e/dt/1e6:.1f}M relax={r} heap_cap={eng.heap_cap} slots={eng._scratch_key}', flush=True)
+    print('   queue: ring pushes, heap pushes =', eng.queue_stats())
