@@ -107,7 +107,7 @@ extern "C" size_t mpp_astar_scratch_bytes(const mpp_map *map, int n_slots, int h
     return 256 + (size_t)n_slots * astar_slot_bytes(map->rows * map->cols, heap_cap);
 }
 
-extern "C" int mpp_astar_max_slots(const mpp_map *map) { return map ? map->sm_count * 4 * MPP_AS_WARPS : 0; }
+extern "C" int mpp_astar_max_slots(const mpp_map *map) { return map ? map->sm_count * 3 * MPP_AS_WARPS : 0; }
 
 struct BatchArgs {
     AStarGrid G;
@@ -126,7 +126,7 @@ struct BatchArgs {
 };
 
 template <bool OCC_SMEM>
-__global__ void __launch_bounds__(MPP_AS_THREADS, 4) mpp_astar_batch_kernel(BatchArgs A) {
+__global__ void __launch_bounds__(MPP_AS_THREADS, 3) mpp_astar_batch_kernel(BatchArgs A) {
     extern __shared__ __align__(16) uint32_t s_occ[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) uint8_t s_cnt[MPP_AS_WARPS][MPP_PQ_NB];
@@ -219,7 +219,7 @@ struct ChainArgs {
 };
 
 template <bool OCC_SMEM>
-__global__ void __launch_bounds__(MPP_AS_THREADS, 4) mpp_waypoint_fitness_kernel(ChainArgs A) {
+__global__ void __launch_bounds__(MPP_AS_THREADS, 3) mpp_waypoint_fitness_kernel(ChainArgs A) {
     extern __shared__ __align__(16) uint32_t s_occ[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) uint8_t s_cnt[MPP_AS_WARPS][MPP_PQ_NB];

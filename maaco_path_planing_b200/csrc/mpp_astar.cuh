@@ -177,13 +177,19 @@ struct AStarPQ {
     double f0;       // bucket origin (f of the start node; f never drops below it except by rounding)
     double rf, rg;   // cached overflow-heap root key (valid when hn > 0)
     int rc;
-    unsigned long long ring_pushes, heap_pushes;
+    uint32_t ring_pushes, heap_pushes;
 };
 
-__device__ __forceinline__ bool pq_push(AStarSlot &S, AStarPQ &Q, double f, double g, int cell) {
-    const int lane = threadIdx.x & 31;
+// bucket index of a key (monotone in f)
+__device__ __forceinline__ int pq_bucket(const AStarPQ &Q, double f) {
     const double x = (f - Q.f0) * MPP_PQ_SCALE;
-    const int q = (x >= 0.0) ? (x < 2.0e9 ? (int)x : 0x7ffffff0) : -1;
+    return (x >= 0.0) ? (x < 2.0e9 ? (int)x : 0x7ffffff0) : -1;
+}
+
+// push with a precomputed bucket index q = pq_bucket(f); all arguments warp-uniform.
+// `cell` is the packed node id (row << 16 | col): same (r, c) lexicographic order as the reference's tuples.
+__device__ __forceinline__ bool pq_push(AStarSlot &S, AStarPQ &Q, double f, double g, int cell, int q) {
+    const int lane = threadIdx.x & 31;
     if (Q.n_ring == 0 && q >= 0) Q.qlo = q;                      // empty ring: re-centre the window
     int c = MPP_PQ_CAP;
     const int b = q & (MPP_PQ_NB - 1);
@@ -221,7 +227,7 @@ __device__ __forceinline__ void pq_pop(AStarSlot &S, AStarPQ &Q, double &f, doub
         b = Q.qlo & (MPP_PQ_NB - 1);
         c = S.cnt[b];
         if (lane < c) { const int i = b * MPP_PQ_CAP + lane; cf = S.bf[i]; cg = S.bg[i]; cc = S.bc[i]; }
-        w = warp_argmin_key(cf, cg, cc);
+        w = (c == 1) ? 0 : warp_argmin_key(cf, cg, cc);
         mf = __shfl_sync(0xffffffffu, cf, w); mg = __shfl_sync(0xffffffffu, cg, w); mc = __shfl_sync(0xffffffffu, cc, w);
     }
     if (Q.hn > 0 && (Q.n_ring == 0 || key_less(Q.rf, Q.rg, Q.rc, mf, mg, mc))) {
@@ -271,10 +277,10 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
     AStarPQ Q;
     Q.qlo = 0; Q.n_ring = 0; Q.hn = 0; Q.rf = 0.0; Q.rg = 0.0; Q.rc = 0; Q.ring_pushes = 0; Q.heap_pushes = 0;
     Q.f0 = hdist_dev(sr, sc, tr, tc);
-    pq_push(S, Q, Q.f0, 0.0, src);                                 // astar.py:45 / MPA.py:113
-    const long long max_steps = (long long)G.R * C * (variant == 0 ? 3 : 2);   // astar.py:58 / MPA.py:118
-    long long steps = 0;
-    unsigned long long exps = 0, rels = 0;
+    const int dst_rc = (tr << 16) | tc;
+    pq_push(S, Q, Q.f0, 0.0, (sr << 16) | sc, 0);                  // astar.py:45 / MPA.py:113
+    const uint32_t max_steps = (uint32_t)G.R * (uint32_t)C * (variant == 0 ? 3u : 2u);   // astar.py:58 / MPA.py:118 (R*C < 2^30)
+    uint32_t steps = 0, exps = 0, rels = 0;
     // per-lane neighbour deltas
     const bool nb_lane = lane < (G.allow_diag ? 8 : 4);
     const int dr = (int)((MPP_NB_R >> (2 * (lane & 7))) & 3u) - 1, dc = (int)((MPP_NB_C >> (2 * (lane & 7))) & 3u) - 1;
@@ -283,18 +289,19 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
     double cur_g = 0.0;
     while (Q.n_ring + Q.hn > 0 && steps < max_steps) {
         double cf;
-        int cur;
-        pq_pop(S, Q, cf, cur_g, cur);
-        if (cur == dst) { found = 1; ++steps; break; }                        // astar.py:64 / MPA.py:123
+        int cur_rc;
+        pq_pop(S, Q, cf, cur_g, cur_rc);
+        if (cur_rc == dst_rc) { found = 1; ++steps; break; }                  // astar.py:64 / MPA.py:123
         // ---- one round of loads: the popped node's record and, per lane, a neighbour's record + avoid word ----
-        const int cr = cur / C, cc = cur % C;
+        const int cr = cur_rc >> 16, cc = cur_rc & 0xffff;
+        const int cur = cr * C + cc;
         const uint4 vcur = *reinterpret_cast<const uint4 *>(&S.rec[cur]);
         bool open_nb = false;
-        int j = 0;
+        int j = 0, nr = 0, nc = 0;
         uint4 vj = make_uint4(0u, 0u, 0u, 0u);
         uint32_t aw = 0u;
         if (nb_lane) {
-            const int nr = cr + dr, nc = cc + dc;
+            nr = cr + dr; nc = cc + dc;
             bool blocked = occ_bit(G, nr, nc);
             if (!blocked && (lane >= 4) && G.restrict_corner)                  // helper.py:45-49 / MPA.py:86-96
                 blocked = occ_bit(G, cr + dr, cc) || occ_bit(G, cr, cc + dc);
@@ -305,6 +312,18 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
                 if (avoid) aw = avoid[j >> 5];
             }
         }
+        if (lane >= 8 && lane < 12) {
+            // warm L2 for the records two rows away (the neighbours of this node's neighbours): a search mostly
+            // continues next to where it just was, and first touches of a record are otherwise DRAM-latency misses
+            const int pr = cr + ((lane & 1) ? 2 : -2);
+            const int pc = cc + ((lane & 2) ? 2 : -2);
+            if (pr >= 0 && pr < G.R) {
+                const int pcc = pc < 0 ? 0 : (pc >= C ? C - 1 : pc);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&S.rec[pr * C + pcc]));
+            }
+        }
+        // heuristic of the neighbour, in parallel across lanes while the loads are in flight (astar.py:90)
+        const double hj = open_nb ? hdist_dev(nr, nc, tr, tc) : 0.0;
         const uint32_t mcur = vcur.z;
         if (variant == 0) {
             if (mcur & 16u) continue;                                         // stale (lazily deleted) entry
@@ -319,7 +338,8 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
         const double gbase = (variant == 0) ? cur_g : gcur;                    // astar.py:85 vs MPA.py:135
         // ---- relax the neighbours, one per lane ----
         bool push = false;
-        double tg = 0.0;
+        double tg = 0.0, pf = 0.0;
+        int pq = 0;
         if (open_nb) {
             const bool av = (aw >> (j & 31)) & 1u;
             uint32_t mj = vj.z;
@@ -336,27 +356,31 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
                     push = (variant == 0) ? true : !(mj & 8u);
                     AStarRec nrc; nrc.g = tg; nrc.meta = stamp_hi | (mj & 16u) | 8u | (uint32_t)(lane & 7); nrc.pad = 0u;
                     S.rec[j] = nrc;
+                    pf = tg + hj;                                              // astar.py:90 / MPA.py:140
+                    pq = pq_bucket(Q, pf);
                     ++rels;
                 }
             }
         }
         __syncwarp();
         uint32_t pm = __ballot_sync(0xffffffffu, push);
+        const int nrc_packed = (nr << 16) | nc;
         while (pm) {
             const int l = __ffs(pm) - 1;
             pm &= pm - 1;
-            const int pj = __shfl_sync(0xffffffffu, j, l);
+            const int prc = __shfl_sync(0xffffffffu, nrc_packed, l);
             const double ptg = __shfl_sync(0xffffffffu, tg, l);
-            const double pf = ptg + hdist_dev(pj / C, pj % C, tr, tc);         // astar.py:90 / MPA.py:140
-            if (!pq_push(S, Q, pf, ptg, pj)) return -1;
+            const double ppf = __shfl_sync(0xffffffffu, pf, l);
+            const int ppq = __shfl_sync(0xffffffffu, pq, l);
+            if (!pq_push(S, Q, ppf, ptg, prc, ppq)) return -1;
         }
     }
-    rels = __reduce_add_sync(0xffffffffu, (uint32_t)rels);
+    rels = __reduce_add_sync(0xffffffffu, rels);
     if (lane == 0 && counters) {
-        atomicAdd(counters, exps);
-        atomicAdd(counters + 1, rels);
-        atomicAdd(counters + 2, Q.ring_pushes);
-        atomicAdd(counters + 3, Q.heap_pushes);
+        atomicAdd(counters, (unsigned long long)exps);
+        atomicAdd(counters + 1, (unsigned long long)rels);
+        atomicAdd(counters + 2, (unsigned long long)Q.ring_pushes);
+        atomicAdd(counters + 3, (unsigned long long)Q.heap_pushes);
     }
     if (!found) return 0;
     if (g_out) *g_out = cur_g;

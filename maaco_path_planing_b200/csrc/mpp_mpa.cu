@@ -109,7 +109,7 @@ __device__ __forceinline__ void copy_stats(double *dst, const double *src) {
 }
 
 template <bool OCC_SMEM>
-__global__ void __launch_bounds__(MPP_MPA_THREADS, 4) mpp_mpa_iteration_kernel(MpaArgs A) {
+__global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(MpaArgs A) {
     extern __shared__ __align__(16) uint32_t s_occ[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) uint8_t s_cnt[MPP_MPA_WARPS][MPP_PQ_NB];
