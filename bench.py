@@ -345,6 +345,21 @@ def side_workloads(args, dev, peak):
     out["mpa"] = {"workload": "MPA 1024 predators x 12 iterations on 100x100 blocks map (BASELINE config 2), "
                   "sorts + best cascade on the host included", "value": mpa.predator_evaluations / dt,
                   "unit": "predator-iterations/s", "seconds": dt, "best_fitness": mpa.best_fitness_overall}
+    # ---- config 5 (one GPU's share): independent 256x256 maps x 1024 ants, colonies overlapped on streams ----
+    from maaco_path_planing_b200.batch import solve_maaco_batch
+    n_maps, ants, iters = args.batch_maps, 1024, 5
+    grids = [blocks_map(256, 0.20, seed=5000 + i) for i in range(n_maps)]
+    solve_maaco_batch(grids[:4], ants, 2, MAACO_PARAMS, seeds=list(range(4)), concurrent=4)      # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = solve_maaco_batch(grids, ants, iters, MAACO_PARAMS, seeds=list(range(n_maps)), concurrent=args.batch_concurrent)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["batched_maps"] = {"workload": f"{n_maps} independent 256x256 maps x {ants} ants x {iters} MAACO iterations, "
+                           f"{args.batch_concurrent} colonies overlapped on CUDA streams (BASELINE config 5, one GPU's share; "
+                           "includes per-map table build + H2D)", "value": n_maps * ants * iters / dt, "unit": "path evals/s",
+                           "maps_per_s": n_maps / dt, "seconds": dt,
+                           "solved_maps": sum(1 for r in res if r[1])}
     return out
 
 
@@ -362,6 +377,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the PSO/GA fitness and MPA side workloads")
     ap.add_argument("--fit-size", type=int, default=512)
     ap.add_argument("--fit-pop", type=int, default=4096)
+    ap.add_argument("--batch-maps", type=int, default=48)
+    ap.add_argument("--batch-concurrent", type=int, default=12)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

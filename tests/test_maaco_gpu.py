@@ -165,3 +165,18 @@ def test_sharded_colony_two_gpus():
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multigpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "multigpu_check ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_batched_maps_equal_individual_solves():
+    """Config-5 style sweep: several independent maps solved concurrently (one stream per colony) give exactly
+    the per-map results."""
+    from maaco_path_planing_b200 import MAACO, blocks_map
+    from maaco_path_planing_b200.batch import solve_maaco_batch
+    grids = [blocks_map(64, 0.2, seed=500 + i) for i in range(5)]
+    seeds = [900 + i for i in range(5)]
+    res = solve_maaco_batch(grids, 128, 4, MAACO_DEFAULT, seeds=seeds, concurrent=3)
+    assert [r[0] for r in res] == list(range(5))
+    for i, path, length, turns, curve in res:
+        solo = MAACO(grids[i], 128, 4, rng_seed=seeds[i], verbose=False, **MAACO_DEFAULT)
+        p2, l2, t2 = solo.solve_path_planning()
+        assert path == p2 and length == l2 and turns == t2 and curve == solo.convergence_curve_data
