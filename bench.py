@@ -182,31 +182,12 @@ def run_gpu(args):
         sampler.start()
         time.sleep(0.25)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
-    import ctypes as C
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     t_wall0 = time.time()
     sync_all()
     for k in range(K):
         flush.fill_(k & 0xff)                                   # evict L2 between timed steps (untimed)
         it += 1
-        ev[k][0].record()
-        solver._enqueue_tours(it, stream)
-        ev[k][1].record()
-        if world > 1:
-            from maaco_path_planing_b200 import dist as dm
-            nl, off = solver.n_local, solver.ant_offset
-            dm.exchange_results(solver._result, solver._result[off:off + nl].clone(), group)
-            dm.exchange_visit_slices(solver._visit_recv, solver._visit_local, group)
-            solver._visit_local.zero_()
-        solver._enqueue_best(it, stream)
-        ev[k][2].record()
-        solver._enqueue_pheromone(stream)
-        if world > 1:
-            wn32 = solver.words_per_rank * 32
-            solver._tau_slice.copy_(solver._tau[solver.rank * wn32:(solver.rank + 1) * wn32])
-            dm.gather_tau(solver._tau, solver._tau_slice, group)
-        ev[k][3].record()
-        solver.kernel_launches += 3
+        solver._enqueue_iteration(it, events=ev[k])             # events: start / after tours / before pheromone / end
     sync_all()
     t_wall1 = time.time()
     step_ms = [e[0].elapsed_time(e[3]) for e in ev]

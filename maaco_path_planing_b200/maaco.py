@@ -94,7 +94,7 @@ class MAACO:
         self._visit_local = torch.zeros(self.n_words * self.n_local, dtype=i32, device=dev)
         if self.world > 1:
             self._visit_recv = torch.empty(self.n_words * self.n_local, dtype=i32, device=dev)  # [G][Wn][n_local]
-            self._tau_slice = torch.empty(self.words_per_rank * 32, dtype=f64, device=dev)
+            self._side = torch.cuda.Stream(device=dev)
         self._cells = torch.zeros(self.n_local * self.max_cells, dtype=i32, device=dev)
         self._result = torch.zeros((num_ants, 2), dtype=i64, device=dev)   # mpp_ant_result per global ant
         self._deposit = torch.zeros(num_ants, dtype=f64, device=dev)
@@ -152,21 +152,36 @@ class MAACO:
                                              _lib.ptr(self._deposit), self.world, self.n_local, self.rank * wn, wn,
                                              self.rho, _lib.ptr(self._state), 0, stream), "mpp_maaco_pheromone")
 
-    def _enqueue_iteration(self, it):
+    def _enqueue_iteration(self, it, events=None):
+        """One colony pass.  `events`: optional 4 CUDA events recorded at (start, after tours, before the
+        pheromone update, end) on the launching stream -- used by bench.py for per-kernel timing."""
         import torch
-        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        cur = torch.cuda.current_stream(self.device)
+        stream = C.c_void_p(cur.cuda_stream)
+        if events:
+            events[0].record(cur)
         self._enqueue_tours(it, stream)
+        if events:
+            events[1].record(cur)
         if self.world > 1:
             nl, off = self.n_local, self.ant_offset
-            dist_mod.exchange_results(self._result, self._result[off:off + nl].clone(), self.group)
+            # in-place all-gather: this rank's slice of the result table is already in position
+            dist_mod.exchange_results(self._result, self._result[off:off + nl], self.group)
             dist_mod.exchange_visit_slices(self._visit_recv, self._visit_local, self.group)
-            self._visit_local.zero_()
+            # the local bitmaps are free again once the all-to-all has read them: clear them off the critical path
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._visit_local.zero_()
         self._enqueue_best(it, stream)
+        if events:
+            events[2].record(cur)
         self._enqueue_pheromone(stream)
         if self.world > 1:
             wn32 = self.words_per_rank * 32
-            self._tau_slice.copy_(self._tau[self.rank * wn32:(self.rank + 1) * wn32])
-            dist_mod.gather_tau(self._tau, self._tau_slice, self.group)
+            dist_mod.gather_tau(self._tau, self._tau[self.rank * wn32:(self.rank + 1) * wn32], self.group)
+            cur.wait_stream(self._side)                                # next pass's tours need the cleared bitmaps
+        if events:
+            events[3].record(cur)
         self.kernel_launches += 3
 
     def _read_state(self):

@@ -20,13 +20,11 @@ import ref_harness as H  # noqa: E402
 def rand_grid(rng, n, dens):
     g = (rng.random((n, n)) < dens).astype(int)
     free = np.argwhere(g == 0)
-    s, t = free[rng.integers(len(free))], free[rng.integers(len(free))]
+    s = free[rng.integers(len(free))]
     g[s[0], s[1]] = 2
-    if tuple(s) != tuple(t):
-        g[t[0], t[1]] = 3
-    else:
-        t = free[(rng.integers(len(free)))]
-        g[t[0], t[1]] = 3
+    free = np.argwhere(g == 0)
+    t = free[rng.integers(len(free))]
+    g[t[0], t[1]] = 3
     return g
 
 
