@@ -143,6 +143,26 @@ int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t *visitT_de
                         int n_seg, int seg_ants, int word0, int n_words, double rho,
                         const mpp_maaco_state *state_dev, int clear_visit, void *stream);
 
+/* ---- sharded-colony exchange (no reference counterpart: the reference is single-process; these implement the
+ * per-iteration exchange BASELINE's north star asks for, bit-exactly) ----------------------------------------
+ * Tours travel between GPUs as 1-byte move codes (MAACO move order, MAACO.py:98).
+ * mpp_maaco_move_offsets: from the all-gathered results ([n_seg*seg_ants], segment = source rank) compute each
+ *   ant's byte offset inside its segment's packed buffer and the per-segment totals (n_cells-1 bytes per
+ *   successful ant, 0 for failed ants).
+ * mpp_maaco_pack_moves: encode this rank's paths (cells_dev, n_local x max_cells) at offsets_local_dev.
+ *   status_dev[0] = 2 if a path was truncated at max_cells or does not fit `capacity`.
+ * mpp_maaco_rebuild_visits: replay the codes of every ant (packed_all_dev = n_seg buffers of `capacity` bytes)
+ *   and set the visited bits falling into words [word0, word0+n_words) of visit_seg_dev
+ *   ([n_seg][n_words][seg_ants], zero on entry) -- the input layout of mpp_maaco_pheromone. */
+int mpp_maaco_move_offsets(const mpp_ant_result *result_dev, int n_seg, int seg_ants, int32_t *offsets_dev,
+                           int32_t *totals_dev, void *stream);
+int mpp_maaco_pack_moves(const mpp_map *map, const int32_t *cells_dev, int max_cells,
+                         const mpp_ant_result *result_local_dev, const int32_t *offsets_local_dev, int n_local,
+                         uint8_t *packed_dev, int capacity, int32_t *status_dev, void *stream);
+int mpp_maaco_rebuild_visits(const mpp_map *map, const uint8_t *packed_all_dev, int capacity,
+                             const int32_t *offsets_dev, const mpp_ant_result *result_dev, int n_seg, int seg_ants,
+                             int word0, int n_words, uint32_t *visit_seg_dev, void *stream);
+
 /* ---- A* connectors, waypoint-chain fitness, path statistics (astar.py, MPA.py, helper.py, pso.py, ga_solver.py) ---- */
 typedef struct {
     double turn_penalty_factor, safety_penalty_factor, min_safe_distance, diagonal_obstacle_penalty_value;

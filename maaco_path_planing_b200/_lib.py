@@ -75,6 +75,11 @@ _SIGS = {
                                   c_double, c_double, c_u64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, C.c_size_t, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p]),
+    "mpp_maaco_move_offsets": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mpp_maaco_pack_moves": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                     c_void_p]),
+    "mpp_maaco_rebuild_visits": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_void_p]),
 }
 
 _lib = None

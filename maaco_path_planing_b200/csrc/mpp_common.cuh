@@ -47,6 +47,11 @@ struct mpp_map {
     double safety_msd;      // msd the table was built for (<0 = none)
     uint8_t *safety_d2_dev; // rows*cols
     double *safety_lut_dev; // 256 doubles: penalty contribution for class d^2
+    // hand-over scratch of the chained (sharded-colony) pheromone update
+    double *chain_tbuf;
+    uint32_t *chain_flags;
+    size_t chain_cap;
+    uint32_t chain_epoch;
 };
 
 int mpp_check_device(int device);

@@ -471,6 +471,81 @@ extern "C" int mpp_maaco_best(const mpp_ant_result *result_dev, const int32_t *c
 #define MPP_PHER_THREADS 256
 struct __align__(16) PherEntry { double d; uint32_t w; uint32_t pad; };
 
+// Fold the deposits of one segment's ants (index order) into this lane's cell.  row = that segment's words of
+// this warp's bitmap word ([seg_ants] uint32), dep = its deposits.
+__device__ __forceinline__ double pher_fold_segment(uint32_t *__restrict__ row, const double *__restrict__ dep,
+                                                    int n_ants, int lane, PherEntry *sb, double t, int clear_visit) {
+    // software pipeline: the next 128 ants' words are in flight while the current ones are folded
+    uint32_t nx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int a = u * 32 + lane; nx[u] = (a < n_ants) ? row[a] : 0u; }
+    for (int a0 = 0; a0 < n_ants; a0 += 128) {
+        uint32_t wd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wd[u] = nx[u];
+        if (a0 + 128 < n_ants) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int a = a0 + 128 + u * 32 + lane; nx[u] = (a < n_ants) ? row[a] : 0u; }
+        }
+        uint32_t nz[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nz[u] = __ballot_sync(0xffffffffu, wd[u] != 0u);
+        if ((nz[0] | nz[1] | nz[2] | nz[3]) == 0u) continue;             // ~92 % of the words
+        double d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                                    // deposits of the chunks that need them
+            const int a = a0 + u * 32 + lane;
+            d[u] = (nz[u] && a < n_ants) ? dep[a] : 0.0;
+            if (clear_visit && wd[u] != 0u) row[a] = 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint32_t m = nz[u];
+            if (!m) continue;
+            if (__popc(m) >= 6) {
+                // dense word (cells near S/T are visited by most ants): stage (deposit, word) of the 32
+                // ants in shared memory and walk them in index order with broadcast reads; what remains
+                // is the dependent DADD chain.  t + 0.0 == t exactly, so non-depositing ants are harmless.
+                __syncwarp();
+                PherEntry e; e.d = d[u]; e.w = wd[u]; e.pad = 0u;
+                sb[lane] = e;
+                __syncwarp();
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) {
+                    const PherEntry x = sb[l];
+                    if ((x.w >> lane) & 1u) t += x.d;                    // :311
+                }
+            } else {
+                while (m) {                                              // ants in index order :306
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t wv = __shfl_sync(0xffffffffu, wd[u], l);
+                    const double dv = __shfl_sync(0xffffffffu, d[u], l);
+                    if ((wv >> lane) & 1u) t += dv;                      // :311
+                }
+            }
+        }
+    }
+    return t;
+}
+
+// MMAS clip + obstacle reset (MAACO.py:312-332) for one cell
+__device__ __forceinline__ double pher_finalize(double t, int cell, const uint32_t *occ, int pitch, int R, int C,
+                                                double rho, const mpp_maaco_state *state) {
+    double b = state->best_len;                                               // :312-316
+    if (b == __longlong_as_double(0x7ff0000000000000ll)) b = (double)(R + C);
+    if (b < 1e-6) b = 1e-6;
+    const double tmax = (1.0 / (1.0 - rho)) * (1.0 / b);                      // :317
+    int mx = C > R ? C : R;
+    if (mx < 1) mx = 1;
+    const double tmin = tmax / (2.0 * (double)mx);                            // :323
+    const int r = cell / C, c = cell % C, pb = c + 1;
+    const bool obst = (occ[(r + 1) * pitch + (pb >> 5)] >> (pb & 31)) & 1u;
+    if (obst) return 1e-9;                                                    // :332
+    t = t > tmin ? t : tmin;                                                  // :327-331 np.clip
+    return t < tmax ? t : tmax;
+}
+
 __global__ void __launch_bounds__(MPP_PHER_THREADS)
 mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
                            uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg, int seg_ants,
@@ -483,80 +558,70 @@ mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, i
     const int wl = (blockIdx.x * MPP_PHER_THREADS + threadIdx.x) >> 5;
     if (wl >= n_words) return;
     PherEntry *sb = s_buf[threadIdx.x >> 5];
-    const int RC = R * C;
     const int cell = (word0 + wl) * 32 + lane;
-    const bool live = cell < RC;
-    const int n_ants = seg_ants;
+    const bool live = cell < R * C;
     double t = 0.0;
     if (live) t = tau[cell] * (1.0 - rho);                                   // :305
-    for (int seg = 0; seg < n_seg; ++seg) {
-        uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
-        const double *dep = deposit + (size_t)seg * seg_ants;
-        // software pipeline: the next 128 ants' words are in flight while the current ones are folded
-        uint32_t nx[4];
+    for (int seg = 0; seg < n_seg; ++seg)
+        t = pher_fold_segment(visitT + ((size_t)seg * n_words + wl) * seg_ants, deposit + (size_t)seg * seg_ants,
+                              seg_ants, lane, sb, t, clear_visit);
+    if (live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
+}
+
+// Sharded colony: one warp per (bitmap word, segment).  Every warp first streams its segment's words (no
+// dependency: this is the HBM-bound part and runs fully in parallel over words x segments), then receives
+// the 32 running cell values from the previous segment's warp through global memory (flag = launch epoch),
+// folds its own ants in order and hands over.  Blocks are ordered segment-major, so a warp only ever waits
+// for a block with a lower index (already dispatched).  The fold order per cell is the global ant order.
+__global__ void __launch_bounds__(MPP_PHER_THREADS)
+mpp_maaco_pheromone_chain_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
+                                 uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg,
+                                 int seg_ants, int word0, int n_words, double rho,
+                                 const mpp_maaco_state *__restrict__ state, int clear_visit, double *tbuf,
+                                 volatile uint32_t *flags, uint32_t epoch) {
+    __shared__ PherEntry s_buf[MPP_PHER_THREADS / 32][32];
+    const int lane = threadIdx.x & 31;
+    const int wpb = MPP_PHER_THREADS / 32;
+    const int wb_count = (n_words + wpb - 1) / wpb;
+    const int seg = blockIdx.x / wb_count;
+    const int wl = (blockIdx.x % wb_count) * wpb + (threadIdx.x >> 5);
+    if (wl >= n_words) return;
+    PherEntry *sb = s_buf[threadIdx.x >> 5];
+    const int cell = (word0 + wl) * 32 + lane;
+    const bool live = cell < R * C;
+    uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
+    // phase 1: does this segment touch the word at all?  (also pulls the row into L2 for the fold)
+    uint32_t any = 0u;
+    for (int a0 = 0; a0 < seg_ants; a0 += 256) {
+        uint32_t v = 0u;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int a = u * 32 + lane; nx[u] = (a < n_ants) ? row[a] : 0u; }
-        for (int a0 = 0; a0 < n_ants; a0 += 128) {
-            uint32_t wd[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) wd[u] = nx[u];
-            if (a0 + 128 < n_ants) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const int a = a0 + 128 + u * 32 + lane; nx[u] = (a < n_ants) ? row[a] : 0u; }
-            }
-            uint32_t nz[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) nz[u] = __ballot_sync(0xffffffffu, wd[u] != 0u);
-            if ((nz[0] | nz[1] | nz[2] | nz[3]) == 0u) continue;             // ~92 % of the words
-            double d[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {                                    // deposits of the chunks that need them
-                const int a = a0 + u * 32 + lane;
-                d[u] = (nz[u] && a < n_ants) ? dep[a] : 0.0;
-                if (clear_visit && wd[u] != 0u) row[a] = 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                uint32_t m = nz[u];
-                if (!m) continue;
-                if (__popc(m) >= 6) {
-                    // dense word (cells near S/T are visited by most ants): stage (deposit, word) of the 32
-                    // ants in shared memory and walk them in index order with broadcast reads; what remains
-                    // is the dependent DADD chain.  t + 0.0 == t exactly, so non-depositing ants are harmless.
-                    __syncwarp();
-                    PherEntry e; e.d = d[u]; e.w = wd[u]; e.pad = 0u;
-                    sb[lane] = e;
-                    __syncwarp();
-#pragma unroll 8
-                    for (int l = 0; l < 32; ++l) {
-                        const PherEntry x = sb[l];
-                        if ((x.w >> lane) & 1u) t += x.d;                    // :311
-                    }
-                } else {
-                    while (m) {                                              // ants in index order :306
-                        const int l = __ffs(m) - 1;
-                        m &= m - 1;
-                        const uint32_t wv = __shfl_sync(0xffffffffu, wd[u], l);
-                        const double dv = __shfl_sync(0xffffffffu, d[u], l);
-                        if ((wv >> lane) & 1u) t += dv;                      // :311
-                    }
-                }
-            }
-        }
+        for (int u = 0; u < 8; ++u) { const int a = a0 + u * 32 + lane; if (a < seg_ants) v |= row[a]; }
+        any |= v;
     }
-    if (!live) return;
-    double b = state->best_len;                                               // :312-316
-    if (b == __longlong_as_double(0x7ff0000000000000ll)) b = (double)(R + C);
-    if (b < 1e-6) b = 1e-6;
-    const double tmax = (1.0 / (1.0 - rho)) * (1.0 / b);                      // :317
-    int mx = C > R ? C : R;
-    if (mx < 1) mx = 1;
-    const double tmin = tmax / (2.0 * (double)mx);                            // :323
-    const int r = cell / C, c = cell % C, pb = c + 1;
-    const bool obst = (occ[(r + 1) * pitch + (pb >> 5)] >> (pb & 31)) & 1u;
-    if (obst) t = 1e-9;                                                       // :332
-    else { t = t > tmin ? t : tmin; t = t < tmax ? t : tmax; }                // :327-331 np.clip
-    tau[cell] = t;
+    any = __ballot_sync(0xffffffffu, any != 0u);
+    // phase 2: running values from the previous segment
+    double t = 0.0;
+    if (seg == 0) {
+        if (live) t = tau[cell] * (1.0 - rho);                               // :305
+    } else {
+        const size_t prev = (size_t)(seg - 1) * n_words + wl;
+        if (lane == 0) while (flags[prev] != epoch) __nanosleep(64);
+        __syncwarp();
+        __threadfence();
+        t = __ldcg(tbuf + prev * 32 + lane);
+    }
+    // phase 3: this segment's ants in index order
+    if (any) t = pher_fold_segment(row, deposit + (size_t)seg * seg_ants, seg_ants, lane, sb, t, clear_visit);
+    // phase 4: hand over / finish
+    if (seg == n_seg - 1) {
+        if (live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
+    } else {
+        const size_t me = (size_t)seg * n_words + wl;
+        __stcg(tbuf + me * 32 + lane, t);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) flags[me] = epoch;
+    }
 }
 
 extern "C" int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t *visitT_dev,
@@ -567,9 +632,161 @@ extern "C" int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t
     MPP_CUDA(cudaSetDevice(map->device));
     const int warps_per_block = MPP_PHER_THREADS / 32;
     const int blocks = (n_words + warps_per_block - 1) / warps_per_block;
-    mpp_maaco_pheromone_kernel<<<blocks, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
-        map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants, word0,
-        n_words, rho, state_dev, clear_visit);
+    if (n_seg == 1) {
+        mpp_maaco_pheromone_kernel<<<blocks, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
+            map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
+            word0, n_words, rho, state_dev, clear_visit);
+    } else {
+        // chained (word, segment) warps: scratch for the hand-over values + epoch flags lives in the map handle
+        mpp_map *m = const_cast<mpp_map *>(map);
+        const size_t need = (size_t)(n_seg - 1) * n_words;
+        if (m->chain_cap < need) {
+            if (m->chain_tbuf) { MPP_CUDA(cudaFree(m->chain_tbuf)); MPP_CUDA(cudaFree(m->chain_flags)); }
+            MPP_CUDA(cudaMalloc(&m->chain_tbuf, need * 32 * sizeof(double)));
+            MPP_CUDA(cudaMalloc(&m->chain_flags, need * sizeof(uint32_t)));
+            MPP_CUDA(cudaMemset(m->chain_flags, 0, need * sizeof(uint32_t)));
+            m->chain_cap = need;
+            m->chain_epoch = 0;
+        }
+        m->chain_epoch += 1;
+        mpp_maaco_pheromone_chain_kernel<<<blocks * n_seg, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
+            map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
+            word0, n_words, rho, state_dev, clear_visit, m->chain_tbuf, m->chain_flags, m->chain_epoch);
+    }
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded-colony exchange: tours travel between GPUs as 1-byte move codes (MAACO move order), ~10x
+// smaller than dense visited bitmaps and 4x smaller than int32 cell lists; every rank replays the codes of
+// all ants into the visited words of ITS slice of the map.
+// ---------------------------------------------------------------------------------------------
+// offsets[i] = byte offset of ant i's codes inside its segment's packed buffer; totals[seg] = bytes of
+// segment seg.  One block per segment (exclusive scan over the segment's ants of n_cells-1, 0 for failed ants).
+__global__ void __launch_bounds__(1024) mpp_maaco_move_offsets_kernel(const mpp_ant_result *__restrict__ res,
+                                                                      int seg_ants, int32_t *__restrict__ offsets,
+                                                                      int32_t *__restrict__ totals) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < seg_ants; base += 1024) {
+        const int a = base + tid;
+        int len = 0;
+        if (a < seg_ants) { const int n = res[(size_t)seg * seg_ants + a].n_cells; len = n > 0 ? n - 1 : 0; }
+        int x = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int excl = s_carry + (wid ? s_warp[wid - 1] : 0) + x - len;
+        if (a < seg_ants) offsets[(size_t)seg * seg_ants + a] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry += s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) totals[seg] = s_carry;
+}
+
+// one warp per local ant: cells -> move codes at packed[offsets[a] ...]
+__global__ void __launch_bounds__(256) mpp_maaco_pack_moves_kernel(const int32_t *__restrict__ cells, int max_cells,
+                                                                   const mpp_ant_result *__restrict__ res_local,
+                                                                   const int32_t *__restrict__ offsets_local, int n_local,
+                                                                   int C, uint8_t *__restrict__ packed, int cap,
+                                                                   int32_t *__restrict__ status) {
+    const int a = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (a >= n_local) return;
+    const int n = res_local[a].n_cells;
+    if (n <= 1) return;
+    if (n > max_cells || offsets_local[a] + (n - 1) > cap) { if (lane == 0) atomicMax(status, 2); return; }
+    const int32_t *p = cells + (size_t)a * max_cells;
+    uint8_t *out = packed + offsets_local[a];
+    for (int i = lane; i + 1 < n; i += 32) {
+        const int d = p[i + 1] - p[i];                     // -C-1,-C,-C+1,-1,+1,C-1,C,C+1 -> move 0..7
+        const int dr = (d + C + 1) / C - 1 + ((d + C + 1) < 0 ? -1 : 0);  // rows: d in [-C-1,-C+1] -> -1, [-1,1] -> 0, [C-1,C+1] -> 1
+        const int dc = d - dr * C;
+        const int i9 = (dr + 1) * 3 + (dc + 1);
+        out[i] = (uint8_t)(i9 - (i9 > 4));
+    }
+}
+
+// one warp per global ant: replay its moves 32 at a time (warp prefix sum of the cell deltas) and set the
+// visited bits that fall into words [word0, word0 + n_words); visit_seg is [n_seg][n_words][seg_ants] and
+// must be zero on entry.  Bits are set with fire-and-forget RED.OR (a column belongs to one ant).
+__global__ void __launch_bounds__(256) mpp_maaco_rebuild_visits_kernel(const uint8_t *__restrict__ packed_all, int cap,
+                                                                       const int32_t *__restrict__ offsets,
+                                                                       const mpp_ant_result *__restrict__ res, int n_seg,
+                                                                       int seg_ants, int start, int C, int word0,
+                                                                       int n_words, uint32_t *__restrict__ visit_seg) {
+    const int g = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n_seg * seg_ants) return;
+    const int n = res[g].n_cells;
+    if (n <= 0) return;                                      // failed ants deposit nothing (MAACO.py:307)
+    const int seg = g / seg_ants, a = g - seg * seg_ants;
+    const uint8_t *codes = packed_all + (size_t)seg * cap + offsets[g];
+    uint32_t *col = visit_seg + (size_t)seg * n_words * seg_ants + a;     // word w of this ant at col[w * seg_ants]
+    int base_cell = start;                                   // cell before the first move of the current chunk
+    if (lane == 0) {
+        const int w = (start >> 5) - word0;
+        if (w >= 0 && w < n_words) atomicOr(&col[(size_t)w * seg_ants], 1u << (start & 31));
+    }
+    for (int i0 = 0; i0 < n - 1; i0 += 32) {
+        const int i = i0 + lane;
+        int d = 0;
+        if (i < n - 1) {
+            const int m = codes[i];
+            d = ((int)((0xA940u >> (2 * m)) & 3u) - 1) * C + ((int)((0x9224u >> (2 * m)) & 3u) - 1);
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, d, o); if (lane >= o) d += y; }
+        const int cell = base_cell + d;                      // cell reached after move i
+        if (i < n - 1) {
+            const int w = (cell >> 5) - word0;
+            if (w >= 0 && w < n_words) atomicOr(&col[(size_t)w * seg_ants], 1u << (cell & 31));
+        }
+        base_cell = __shfl_sync(0xffffffffu, cell, 31);
+    }
+}
+
+extern "C" int mpp_maaco_move_offsets(const mpp_ant_result *result_dev, int n_seg, int seg_ants, int32_t *offsets_dev,
+                                      int32_t *totals_dev, void *stream) {
+    MPP_REQUIRE(result_dev && offsets_dev && totals_dev && n_seg > 0 && seg_ants > 0, "mpp_maaco_move_offsets: bad argument");
+    mpp_maaco_move_offsets_kernel<<<n_seg, 1024, 0, (cudaStream_t)stream>>>(result_dev, seg_ants, offsets_dev, totals_dev);
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}
+
+extern "C" int mpp_maaco_pack_moves(const mpp_map *map, const int32_t *cells_dev, int max_cells,
+                                    const mpp_ant_result *result_local_dev, const int32_t *offsets_local_dev, int n_local,
+                                    uint8_t *packed_dev, int capacity, int32_t *status_dev, void *stream) {
+    MPP_REQUIRE(map && cells_dev && result_local_dev && offsets_local_dev && packed_dev && status_dev && n_local > 0,
+                "mpp_maaco_pack_moves: bad argument");
+    MPP_CUDA(cudaSetDevice(map->device));
+    mpp_maaco_pack_moves_kernel<<<(n_local + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        cells_dev, max_cells, result_local_dev, offsets_local_dev, n_local, map->cols, packed_dev, capacity, status_dev);
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}
+
+extern "C" int mpp_maaco_rebuild_visits(const mpp_map *map, const uint8_t *packed_all_dev, int capacity,
+                                        const int32_t *offsets_dev, const mpp_ant_result *result_dev, int n_seg,
+                                        int seg_ants, int word0, int n_words, uint32_t *visit_seg_dev, void *stream) {
+    MPP_REQUIRE(map && packed_all_dev && offsets_dev && result_dev && visit_seg_dev && n_seg > 0 && seg_ants > 0,
+                "mpp_maaco_rebuild_visits: bad argument");
+    MPP_CUDA(cudaSetDevice(map->device));
+    const int total = n_seg * seg_ants;
+    mpp_maaco_rebuild_visits_kernel<<<(total + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        packed_all_dev, capacity, offsets_dev, result_dev, n_seg, seg_ants, map->start, map->cols, word0, n_words,
+        visit_seg_dev);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }

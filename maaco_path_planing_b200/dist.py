@@ -5,9 +5,13 @@ Ants are independent given tau (MAACO.py:340-342), so rank g constructs ants
 *global ant order* to stay bit-exact.  The exchange is therefore:
 
   1. all-gather of the 16-byte per-ant results (length, n_cells, turns) -> replicated best scan;
-  2. all-to-all of visited-bitmap *word slices*: rank g receives, from every source rank s, the
-     words [g*Wn, (g+1)*Wn) of s's ants ([Wn][N_local], contiguous in the word-major layout), and
-     updates only the cells of its slice with all N ants in order (segments = source ranks);
+  2. the visited sets, one of two ways:
+     "moves" (default): all-gather of the tours as 1-byte move codes (~0.8 KB/ant); every rank replays
+        all ants and sets the visited bits that fall into ITS slice of bitmap words;
+     "dense": all-to-all of visited-bitmap word slices -- rank g receives, from every source rank s, the
+        words [g*Wn, (g+1)*Wn) of s's ants ([Wn][N_local], contiguous in the word-major layout);
+     either way rank g updates only the cells of its slice, with all N ants in global order
+     (segments = source ranks), so tau is bit-identical to the single-GPU run;
   3. all-gather of the updated tau slices (replicated tau for the next colony pass).
 
 Everything here is plain torch / torch.distributed on whatever device the tensors live on, so the
@@ -59,3 +63,8 @@ def exchange_visit_slices(visit_recv, visit_local, group):
 def gather_tau(tau_full, tau_slice, group):
     """tau_slice: this rank's [Wn*32] cells -> tau_full [W_pad*32] (replicated)."""
     dist.all_gather_into_tensor(tau_full, tau_slice, group=group)
+
+
+def exchange_moves(packed_all, packed_local, group):
+    """packed_local: this rank's move-code buffer [cap] uint8 -> packed_all [G*cap] in rank order."""
+    dist.all_gather_into_tensor(packed_all, packed_local, group=group)

@@ -30,7 +30,8 @@ class MAACO:
                  alpha, beta, rho, Q,
                  a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
                  C0_initial_pheromone=0.1, *,
-                 rng_seed=None, device=None, max_cells=None, lanes_per_ant=0, group=None, verbose=True):
+                 rng_seed=None, device=None, max_cells=None, lanes_per_ant=0, group=None, exchange="moves",
+                 verbose=True):
         import torch
         self.grid = np.array(grid, dtype=int)                       # MAACO.py:15
         self.rows, self.cols = self.grid.shape
@@ -54,6 +55,9 @@ class MAACO:
         self.rng_seed = _fresh_seed() if rng_seed is None else int(rng_seed)
         self.verbose = verbose
         self.lanes_per_ant = lanes_per_ant
+        if exchange not in ("moves", "dense"):
+            raise ValueError("exchange must be 'moves' or 'dense'")
+        self.exchange = exchange
 
         # ---- sharding of the colony over the process group (ants are independent given tau) ----
         self.group = group
@@ -95,6 +99,15 @@ class MAACO:
         if self.world > 1:
             self._visit_recv = torch.empty(self.n_words * self.n_local, dtype=i32, device=dev)  # [G][Wn][n_local]
             self._side = torch.cuda.Stream(device=dev)
+            if self.exchange == "moves":
+                if self.cols < 3:
+                    raise ValueError("the move-code exchange needs at least 3 columns")
+                self._visit_recv.zero_()                              # rebuilt per pass, cleared by the update
+                self._offsets = torch.zeros(num_ants, dtype=i32, device=dev)
+                self._totals = torch.zeros(self.world, dtype=i32, device=dev)
+                self._totals_host = torch.zeros(self.world, dtype=i32).pin_memory()
+                self._xstatus = torch.zeros(1, dtype=i32, device=dev)
+                self._packed_cap = 0
         self._cells = torch.zeros(self.n_local * self.max_cells, dtype=i32, device=dev)
         self._result = torch.zeros((num_ants, 2), dtype=i64, device=dev)   # mpp_ant_result per global ant
         self._deposit = torch.zeros(num_ants, dtype=f64, device=dev)
@@ -150,7 +163,8 @@ class MAACO:
             wn = self.words_per_rank
             _lib.check(L.mpp_maaco_pheromone(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._visit_recv),
                                              _lib.ptr(self._deposit), self.world, self.n_local, self.rank * wn, wn,
-                                             self.rho, _lib.ptr(self._state), 0, stream), "mpp_maaco_pheromone")
+                                             self.rho, _lib.ptr(self._state), 1 if self.exchange == "moves" else 0,
+                                             stream), "mpp_maaco_pheromone")
 
     def _enqueue_iteration(self, it, events=None):
         """One colony pass.  `events`: optional 4 CUDA events recorded at (start, after tours, before the
@@ -165,10 +179,35 @@ class MAACO:
             events[1].record(cur)
         if self.world > 1:
             nl, off = self.n_local, self.ant_offset
+            L = _lib.lib()
             # in-place all-gather: this rank's slice of the result table is already in position
             dist_mod.exchange_results(self._result, self._result[off:off + nl], self.group)
-            dist_mod.exchange_visit_slices(self._visit_recv, self._visit_local, self.group)
-            # the local bitmaps are free again once the all-to-all has read them: clear them off the critical path
+            if self.exchange == "dense":
+                dist_mod.exchange_visit_slices(self._visit_recv, self._visit_local, self.group)
+            else:
+                _lib.check(L.mpp_maaco_move_offsets(_lib.ptr(self._result), self.world, nl, _lib.ptr(self._offsets),
+                                                    _lib.ptr(self._totals), stream), "mpp_maaco_move_offsets")
+                self._totals_host.copy_(self._totals, non_blocking=True)
+                cur.synchronize()                                      # the all-gather below is sized on the host
+                cap = ((int(self._totals_host.max()) + 65535) // 65536) * 65536
+                if cap > self._packed_cap:
+                    self._packed_cap = cap
+                    self._packed_local = torch.empty(cap, dtype=torch.uint8, device=self.device)
+                    self._packed_all = torch.empty(cap * self.world, dtype=torch.uint8, device=self.device)
+                cap = self._packed_cap
+                _lib.check(L.mpp_maaco_pack_moves(self.map.handle, _lib.ptr(self._cells), self.max_cells,
+                                                  C.c_void_p(self._result.data_ptr() + 16 * off),
+                                                  C.c_void_p(self._offsets.data_ptr() + 4 * off), nl,
+                                                  _lib.ptr(self._packed_local), cap, _lib.ptr(self._xstatus), stream),
+                           "mpp_maaco_pack_moves")
+                dist_mod.exchange_moves(self._packed_all, self._packed_local, self.group)
+                wn = self.words_per_rank
+                _lib.check(L.mpp_maaco_rebuild_visits(self.map.handle, _lib.ptr(self._packed_all), cap,
+                                                      _lib.ptr(self._offsets), _lib.ptr(self._result), self.world, nl,
+                                                      self.rank * wn, wn, _lib.ptr(self._visit_recv), stream),
+                           "mpp_maaco_rebuild_visits")
+                self.kernel_launches += 3
+            # the local bitmaps are free again: clear them off the critical path
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
                 self._visit_local.zero_()
@@ -196,6 +235,8 @@ class MAACO:
         torch.cuda.synchronize(self.device)
         self._iter_done = K
         st = self._read_state()
+        if self.world > 1 and self.exchange == "moves" and int(self._xstatus.item()) != 0:
+            raise _lib.MppError("a tour exceeded max_cells and could not be exchanged; re-run with a larger max_cells")
         log = self._log.cpu().numpy().reshape(-1, 4)[:K]
         if st.best_n_cells > self.max_cells:
             raise _lib.MppError(f"best path has {st.best_n_cells} cells but max_cells={self.max_cells}; "

@@ -25,7 +25,7 @@ def main():
                   q0_initial=0.5, C0_initial_pheromone=0.1)
     g = blocks_map(96, 0.2, seed=11)
     N, K, seed = 64 * world, 6, 9
-    dev = MAACO(g, N, K, rng_seed=seed, device=local, group=dist.group.WORLD, verbose=False, **params)
+    dev = MAACO(g, N, K, rng_seed=seed, device=local, group=dist.group.WORLD, verbose=False, exchange=os.environ.get("MPP_EXCHANGE", "moves"), **params)
     orc = O.MaacoOracle(g, N, K, seed=seed, **params)
     for it in range(1, K + 1):
         dev.run_iteration(it)

@@ -180,3 +180,56 @@ def test_batched_maps_equal_individual_solves():
         solo = MAACO(grids[i], 128, 4, rng_seed=seeds[i], verbose=False, **MAACO_DEFAULT)
         p2, l2, t2 = solo.solve_path_planning()
         assert path == p2 and length == l2 and turns == t2 and curve == solo.convergence_curve_data
+
+
+def test_chained_segment_pheromone_equals_single_segment():
+    """The (word, segment)-chained update used by the sharded colony folds ants in the same global order as the
+    single-segment kernel: identical tau for identical (re-laid-out) visited bitmaps and deposits."""
+    import ctypes as C
+    import torch
+    from maaco_path_planing_b200 import _lib, GridMap, blocks_map
+    g = blocks_map(96, 0.2, seed=77)
+    gm = GridMap(g)
+    dev = torch.device("cuda", gm.device)
+    n = g.size
+    words = (n + 31) // 32
+    n_seg, seg_ants = 4, 96
+    N = n_seg * seg_ants
+    rng = np.random.default_rng(5)
+    vis = np.zeros((words, N), np.uint32)                                  # [word][global ant]
+    hits = rng.random((words, N)) < 0.05
+    vis[hits] = rng.integers(1, 2**32, hits.sum(), dtype=np.uint64).astype(np.uint32)
+    vis[:3, :] = rng.integers(1, 2**32, (3, N), dtype=np.uint64).astype(np.uint32)   # dense words (start region)
+    dep = rng.random(N) * 0.01
+    dep[rng.random(N) < 0.3] = 0.0                                         # failed ants deposit nothing
+    tau0 = rng.random(words * 32) + 0.01
+    st = _lib.MaacoState(123.5, 7, 0, 0, -1, 0.0, -1, -1)
+    state = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(dev)
+    L = _lib.lib()
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    outs = []
+    for layout in ("single", "chained"):
+        tau = torch.as_tensor(tau0.copy(), device=dev)
+        if layout == "single":
+            v = torch.as_tensor(vis.view(np.int32).copy(), device=dev)
+            args = (1, N)
+        else:
+            seg = vis.reshape(words, n_seg, seg_ants).transpose(1, 0, 2).copy()   # [seg][word][ant in seg]
+            v = torch.as_tensor(seg.view(np.int32), device=dev)
+            args = (n_seg, seg_ants)
+        d = torch.as_tensor(dep, device=dev)
+        _lib.check(L.mpp_maaco_pheromone(gm.handle, _lib.ptr(tau), _lib.ptr(v), _lib.ptr(d), args[0], args[1], 0, words,
+                                         0.1, _lib.ptr(state), 0, stream), "mpp_maaco_pheromone")
+        torch.cuda.synchronize()
+        outs.append(tau.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    # and against a plain numpy fold for a few cells
+    for cell in (0, 5, 33, 700, n - 1):
+        t = tau0[cell] * (1.0 - 0.1)
+        for a in range(N):
+            if (vis[cell >> 5, a] >> (cell & 31)) & 1:
+                t += dep[a]
+        tmax = (1.0 / (1.0 - 0.1)) * (1.0 / 123.5)
+        tmin = tmax / (2.0 * 96)
+        want = 1e-9 if g.ravel()[cell] == 1 else min(max(t, tmin), tmax)
+        assert outs[0][cell] == want
