@@ -3,6 +3,7 @@
 // Reference semantics: MAACO.py:58-91 (tables), :100-181 (filter), :197-262 (selection),
 // :278-302 (tour), :304-332 (pheromone), :343-358 (best tracking).
 #include <cmath>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -632,7 +633,8 @@ extern "C" int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t
     MPP_CUDA(cudaSetDevice(map->device));
     const int warps_per_block = MPP_PHER_THREADS / 32;
     const int blocks = (n_words + warps_per_block - 1) / warps_per_block;
-    if (n_seg == 1) {
+    static const bool use_chain = getenv("MPP_PHER_CHAIN") != nullptr;  // experimental: measured no gain on 8xB200
+    if (n_seg == 1 || !use_chain) {
         mpp_maaco_pheromone_kernel<<<blocks, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
             map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
             word0, n_words, rho, state_dev, clear_visit);

@@ -182,9 +182,10 @@ def test_batched_maps_equal_individual_solves():
         assert path == p2 and length == l2 and turns == t2 and curve == solo.convergence_curve_data
 
 
-def test_chained_segment_pheromone_equals_single_segment():
-    """The (word, segment)-chained update used by the sharded colony folds ants in the same global order as the
-    single-segment kernel: identical tau for identical (re-laid-out) visited bitmaps and deposits."""
+def test_segmented_pheromone_equals_single_segment():
+    """The segmented update used by the sharded colony ([segment][word][ant] bitmaps, one segment per source
+    rank) folds ants in the same global order as the single-segment kernel: identical tau for identical
+    (re-laid-out) visited bitmaps and deposits."""
     import ctypes as C
     import torch
     from maaco_path_planing_b200 import _lib, GridMap, blocks_map
