@@ -569,6 +569,89 @@ mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, i
     if (live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
 }
 
+// Block-per-word variant (default): 8 warps scan 1024 ants per round for nonzero words and compact the hits
+// -- (deposit, word) in ant order -- into shared memory, double buffered; warp 0 then folds only the hits.
+// The streaming / zero-skipping (HBM-bound) is spread over 8 warps per word and overlapped with the fold, and
+// the sequential part is proportional to the number of ants that actually visited the word.
+#define MPP_PHER_ROUND 1024
+__global__ void __launch_bounds__(MPP_PHER_THREADS)
+mpp_maaco_pheromone_block_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
+                                 uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg,
+                                 int seg_ants, int word0, int n_words, double rho,
+                                 const mpp_maaco_state *__restrict__ state, int clear_visit) {
+    __shared__ PherEntry s_list[2][MPP_PHER_ROUND];          // per round: warp k owns entries [128k, 128k+128)
+    __shared__ int s_cnt[2][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int wl = blockIdx.x;                               // one bitmap word (32 cells) per block
+    const int cell = (word0 + wl) * 32 + lane;
+    const bool live = cell < R * C;
+    double t = 0.0;
+    if (wid == 0 && live) t = tau[cell] * (1.0 - rho);       // :305
+    const int rounds_per_seg = (seg_ants + MPP_PHER_ROUND - 1) / MPP_PHER_ROUND;
+    const int n_rounds = n_seg * rounds_per_seg;
+    // the words of round r+1 are loaded while round r is compacted (one DRAM latency per round otherwise)
+    auto load_round = [&](int r, uint32_t (&v)[4]) {
+        const int seg = r / rounds_per_seg, a_base = (r % rounds_per_seg) * MPP_PHER_ROUND + wid * 128;
+        const uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int a = a_base + u * 32 + lane; v[u] = (a < seg_ants) ? row[a] : 0u; }
+    };
+    uint32_t nx[4] = {0u, 0u, 0u, 0u};
+    if (n_rounds > 0) load_round(0, nx);
+    for (int r = 0; r <= n_rounds; ++r) {
+        const int buf = r & 1;
+        if (r < n_rounds) {
+            // ---- produce round r: this warp's 128 ants ----
+            const int seg = r / rounds_per_seg, a_base = (r % rounds_per_seg) * MPP_PHER_ROUND + wid * 128;
+            uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
+            const double *dep = deposit + (size_t)seg * seg_ants;
+            uint32_t wd[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wd[u] = nx[u];
+            if (r + 1 < n_rounds) load_round(r + 1, nx);
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t nz = __ballot_sync(0xffffffffu, wd[u] != 0u);
+                if (wd[u] != 0u) {
+                    const int a = a_base + u * 32 + lane;
+                    PherEntry e; e.d = dep[a]; e.w = wd[u]; e.pad = 0u;
+                    s_list[buf][wid * 128 + cnt + __popc(nz & ((1u << lane) - 1u))] = e;
+                    if (clear_visit) row[a] = 0u;
+                }
+                cnt += __popc(nz);
+            }
+            if (lane == 0) s_cnt[buf][wid] = cnt;
+        }
+        if (r > 0 && wid == 0) {
+            // ---- consume round r-1 (filled before the previous barrier): ants in index order :306 ----
+            const int pb = buf ^ 1;
+#pragma unroll 1
+            for (int k = 0; k < 8; ++k) {
+                const int n = s_cnt[pb][k];
+                const PherEntry *lst = &s_list[pb][k * 128];
+                int i = 0;
+                for (; i + 4 <= n; i += 4) {
+                    // select the operand, not the sum: the loop-carried chain is a bare DADD (t + 0.0 == t exactly)
+                    const PherEntry x0 = lst[i], x1 = lst[i + 1], x2 = lst[i + 2], x3 = lst[i + 3];
+                    const double a0 = ((x0.w >> lane) & 1u) ? x0.d : 0.0, a1 = ((x1.w >> lane) & 1u) ? x1.d : 0.0;
+                    const double a2 = ((x2.w >> lane) & 1u) ? x2.d : 0.0, a3 = ((x3.w >> lane) & 1u) ? x3.d : 0.0;
+                    t += a0;                                                 // :311
+                    t += a1;
+                    t += a2;
+                    t += a3;
+                }
+                for (; i < n; ++i) {
+                    const PherEntry x = lst[i];
+                    t += ((x.w >> lane) & 1u) ? x.d : 0.0;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (wid == 0 && live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
+}
+
 // Sharded colony: one warp per (bitmap word, segment).  Every warp first streams its segment's words (no
 // dependency: this is the HBM-bound part and runs fully in parallel over words x segments), then receives
 // the 32 running cell values from the previous segment's warp through global memory (flag = launch epoch),
@@ -634,7 +717,12 @@ extern "C" int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t
     const int warps_per_block = MPP_PHER_THREADS / 32;
     const int blocks = (n_words + warps_per_block - 1) / warps_per_block;
     static const bool use_chain = getenv("MPP_PHER_CHAIN") != nullptr;  // experimental: measured no gain on 8xB200
-    if (n_seg == 1 || !use_chain) {
+    static const bool use_warp = getenv("MPP_PHER_WARP") != nullptr;    // previous warp-per-word kernel
+    if (!use_chain && !use_warp) {
+        mpp_maaco_pheromone_block_kernel<<<n_words, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
+            map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
+            word0, n_words, rho, state_dev, clear_visit);
+    } else if (n_seg == 1 || !use_chain) {
         mpp_maaco_pheromone_kernel<<<blocks, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
             map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
             word0, n_words, rho, state_dev, clear_visit);
