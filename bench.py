@@ -233,6 +233,10 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if world == 1 and args.ants == 4096 and args.size == 512 and os.path.exists(tp):
+        traffic = json.load(open(tp))["mpp_maaco_tour_kernel"]["dram_bytes_per_launch"]   # from the committed ncu capture
     value = total_ants * K / (total_ms / 1e3)
     tour_avg_ms = sum(tour_ms) / K
     achieved = BYTES_PER_ANT_STEP * (ant_steps_local / K) / (tour_avg_ms / 1e3) / 1e9
@@ -246,7 +250,7 @@ def run_gpu(args):
         "gpu_launches": solver.kernel_launches - launches_before - 3 * K2,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "mpp_maaco_tour_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_unit": BYTES_PER_ANT_STEP, "units_per_launch": ant_steps_local / K,
                      "kernel_ms": tour_avg_ms,
                      "pheromone_kernel": {"ms": sum(pher_ms) / K,
