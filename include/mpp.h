@@ -190,7 +190,8 @@ size_t mpp_astar_scratch_bytes(const mpp_map *map, int n_slots, int heap_cap);
 int mpp_astar_max_slots(const mpp_map *map);
 
 /* replaces n independent calls of AStarSolver.solve (variant 0, astar.py:33-101, with get_valid_neighbors
- * helper.py:18-53) or MPA._a_star (variant 1, MPA.py:106-151).  avoid_bits_dev: optional n x ceil(rows*cols/32)
+ * helper.py:18-53), MPA._a_star (variant 1, MPA.py:106-151) or DijkstraSolver.solve (variant 2,
+ * dijkstra.py:32-97 = variant 0 with a zero heuristic).  avoid_bits_dev: optional n x ceil(rows*cols/32)
  * bitmaps (nodes_to_avoid).  cells_dev: n x max_cells; n_cells_dev[i] = path length (0 = no path / invalid
  * endpoint, -1 = heap_cap overflow, > max_cells = truncated); g_dev[i] = g of the popped target (nullable).
  * counters_dev: optional [4] = (node expansions, successful relaxations, ring-bucket pushes, overflow-heap

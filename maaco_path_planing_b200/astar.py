@@ -10,6 +10,7 @@ from .helper import BasePathfinder
 
 
 class AStarSolver(BasePathfinder):
+    _variant = 0                                                            # connector semantics (0 = astar.py)
     def __init__(self, grid, turn_penalty_factor=0.1, safety_penalty_factor=0.05, min_safe_distance=1.5,
                  allow_diagonal_moves=True, restrict_diagonal_near_obstacle_policy=True,
                  diagonal_obstacle_penalty_value=1000.0, *, device=None, gridmap=None, engine=None):
@@ -39,7 +40,7 @@ class AStarSolver(BasePathfinder):
         bits = None
         if avoid_sets is not None:
             bits = np.stack([self._avoid_bits(a or ()) for a in avoid_sets])
-        cells, ncell, g = self.engine.astar_batch(0, src, dst, bits, self.allow_diagonal_moves,
+        cells, ncell, g = self.engine.astar_batch(self._variant, src, dst, bits, self.allow_diagonal_moves,
                                                   self.astar_strictly_restricts_corners)
         cells, ncell, g = cells.cpu().numpy(), ncell.cpu().numpy(), g.cpu().numpy()
         return [(self._nodes(cells[i, :ncell[i]]), float(g[i])) for i in range(len(src))]

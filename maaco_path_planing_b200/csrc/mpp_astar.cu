@@ -167,7 +167,7 @@ extern "C" int mpp_astar_batch(mpp_map *map, int variant, const int32_t *src_dev
                                void *scratch_dev, size_t scratch_bytes, int n_slots, int heap_cap,
                                unsigned long long *counters_dev, void *stream) {
     MPP_REQUIRE(map && src_dev && dst_dev && cells_dev && n_cells_dev && scratch_dev, "mpp_astar_batch: null argument");
-    MPP_REQUIRE(variant == 0 || variant == 1, "mpp_astar_batch: variant must be 0 (astar.py) or 1 (MPA.py)");
+    MPP_REQUIRE(variant >= 0 && variant <= 2, "mpp_astar_batch: variant must be 0 (astar.py), 1 (MPA.py) or 2 (dijkstra.py)");
     MPP_REQUIRE(n > 0 && max_cells > 0, "mpp_astar_batch: bad sizes");
     int rc = check_scratch(map, scratch_bytes, n_slots, heap_cap);
     if (rc) return rc;

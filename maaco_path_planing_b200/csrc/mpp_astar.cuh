@@ -2,6 +2,7 @@
 //
 //   variant 0: AStarSolver.solve  (astar.py:33-101)  -- closed set seeded from nodes_to_avoid minus
 //              {start,target}, relax from the popped g, in-place decrease-key.
+//   variant 2: DijkstraSolver.solve (dijkstra.py:32-97) -- variant 0 with a zero heuristic (key (g, r, c)).
 //   variant 1: MPA._a_star        (MPA.py:106-151)   -- no closed set, avoid-set filters neighbours only,
 //              relax from g_score[current], keys of nodes already in the open set are left stale,
 //              nodes not in the open set (incl. already expanded ones) are re-pushed.
@@ -261,7 +262,9 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
     if (g_out) *g_out = INF;
     if (variant == 1 && src == dst) { if (lane == 0 && out_cap > 0) out[0] = src; if (g_out) *g_out = 0.0; __syncwarp(); return 1; }  // MPA.py:107-108
     if (occ_bit(G, sr, sc) || occ_bit(G, tr, tc)) return 0;        // astar.py:37-39 / MPA.py:109-111
-    if (variant == 0 && src == dst) { if (lane == 0 && out_cap > 0) out[0] = src; if (g_out) *g_out = 0.0; __syncwarp(); return 1; }  // astar.py:41-42
+    if (variant != 1 && src == dst) { if (lane == 0 && out_cap > 0) out[0] = src; if (g_out) *g_out = 0.0; __syncwarp(); return 1; }  // astar.py:41-42
+    const bool dijkstra = (variant == 2);                          // dijkstra.py:44,59,88: the key is (g, node)
+    if (dijkstra) variant = 0;
     // new stamp for this search (records of older searches become invalid without clearing)
     uint32_t stamp = S.hdr[0] + 1;
     if (stamp >= (1u << 24)) {  // wrap: clear the records once every 16M searches
@@ -276,7 +279,7 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
     __syncwarp();
     AStarPQ Q;
     Q.qlo = 0; Q.n_ring = 0; Q.hn = 0; Q.rf = 0.0; Q.rg = 0.0; Q.rc = 0; Q.ring_pushes = 0; Q.heap_pushes = 0;
-    Q.f0 = hdist_dev(sr, sc, tr, tc);
+    Q.f0 = dijkstra ? 0.0 : hdist_dev(sr, sc, tr, tc);
     const int dst_rc = (tr << 16) | tc;
     pq_push(S, Q, Q.f0, 0.0, (sr << 16) | sc, 0);                  // astar.py:45 / MPA.py:113
     const uint32_t max_steps = (uint32_t)G.R * (uint32_t)C * (variant == 0 ? 3u : 2u);   // astar.py:58 / MPA.py:118 (R*C < 2^30)
@@ -323,7 +326,7 @@ static __device__ int astar_search(const AStarGrid &G, AStarSlot &S, int variant
             }
         }
         // heuristic of the neighbour, in parallel across lanes while the loads are in flight (astar.py:90)
-        const double hj = open_nb ? hdist_dev(nr, nc, tr, tc) : 0.0;
+        const double hj = (open_nb && !dijkstra) ? hdist_dev(nr, nc, tr, tc) : 0.0;
         const uint32_t mcur = vcur.z;
         if (variant == 0) {
             if (mcur & 16u) continue;                                         // stale (lazily deleted) entry

@@ -240,7 +240,52 @@ def solver_cases():
     np.savez_compressed(os.path.join(HERE, "solver_cases.npz"), **out)
 
 
+def dijkstra_cases(n_cases=120):
+    """Reference outputs of DijkstraSolver.solve (dijkstra.py:32-97) on random (grid, src, dst, avoid) tuples."""
+    ref = H.load_reference()
+    rng = np.random.default_rng(5)
+    rec = dict(grid=[], shape=[], src=[], dst=[], avoid=[], avoid_off=[0], flags=[], path=[], off=[0])
+    for case in range(n_cases):
+        n, m = int(rng.integers(5, 30)), int(rng.integers(5, 30))
+        g = rand_grid(rng, n, m, rng.uniform(0.05, 0.35))
+        ad, rs = bool(rng.random() < 0.9), bool(rng.random() < 0.8)
+        cells = [(r, c) for r in range(n) for c in range(m)]
+
+        def pick():
+            if rng.random() < 0.08:
+                return cells[rng.integers(len(cells))]
+            fr = np.argwhere(g != 1)
+            q = fr[rng.integers(len(fr))]
+            return (int(q[0]), int(q[1]))
+        src, dst = pick(), pick()
+        avoid = {cells[rng.integers(len(cells))] for _ in range(int(rng.integers(0, n + m)))}
+        with H.quiet():
+            sol = ref.dijkstra.DijkstraSolver(grid=g, turn_penalty_factor=0, safety_penalty_factor=0, min_safe_distance=0,
+                                              allow_diagonal_moves=ad, restrict_diagonal_near_obstacle_policy=rs,
+                                              diagonal_obstacle_penalty_value=0)
+            rp = sol.solve(start_node_override=src, target_node_override=dst, nodes_to_avoid=set(avoid))[0]
+        rec["grid"].append(g.astype(np.uint8).ravel())
+        rec["shape"].append((n, m))
+        rec["src"].append(src[0] * m + src[1])
+        rec["dst"].append(dst[0] * m + dst[1])
+        rec["avoid"].extend(sorted(r * m + c for r, c in avoid))
+        rec["avoid_off"].append(len(rec["avoid"]))
+        rec["flags"].append((int(ad), int(rs)))
+        rec["path"].extend(int(r) * m + int(c) for r, c in rp)
+        rec["off"].append(len(rec["path"]))
+    np.savez_compressed(os.path.join(HERE, "dijkstra_cases.npz"), grid=np.concatenate(rec["grid"]),
+                        shape=np.array(rec["shape"], np.int32), src=np.array(rec["src"], np.int32),
+                        dst=np.array(rec["dst"], np.int32), avoid=np.array(rec["avoid"], np.int32),
+                        avoid_off=np.array(rec["avoid_off"], np.int64), flags=np.array(rec["flags"], np.int32),
+                        path=np.array(rec["path"], np.int32), off=np.array(rec["off"], np.int64))
+    print("dijkstra cases", n_cases)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "dijkstra":
+        dijkstra_cases()
+        return
+    dijkstra_cases()
     solver_cases()
     astar_cases()
     fitness_cases()

@@ -126,3 +126,22 @@ def test_path_stats_edge_cases():
             for i, p in enumerate(paths):
                 want = O.path_stats(grid, p, tpf, 0.8, msd, 100.0, True, mode=mode)
                 assert np.array_equal(st[i], want), (mode, msd, i, st[i], want)
+
+
+def test_dijkstra_matches_reference_goldens_and_anchor():
+    """dijkstra.py:32-97 = connector variant 2 (zero heuristic).  Anchor (main.py policy):
+    T=12, SP=0.3274397055203064, fitness=35.41830095052029."""
+    import pyoracle as O
+    from test_oracle_golden import _dijkstra_golden
+    from maaco_path_planing_b200.dijkstra import DijkstraSolver
+    for i, grid, src, dst, avoid, ad, rs, want in _dijkstra_golden():
+        eng = _engine(grid)
+        bits = O.cells_to_bits(avoid, grid.size).view(np.int32)[None, :]
+        cells, ncell, g = eng.astar_batch(2, [src], [dst], bits, ad, rs)
+        n = int(ncell[0])
+        assert n == len(want) and np.array_equal(cells[0, :n].cpu().numpy(), want), f"case {i}"
+    grid = load_golden("env_grids")["fig7"].astype(int)
+    d = DijkstraSolver(grid, turn_penalty_factor=0.3, safety_penalty_factor=0.8, min_safe_distance=1.8,
+                       diagonal_obstacle_penalty_value=100.0)
+    path, L, T, SP, DP, F = d.solve()
+    assert T == 12 and SP == 0.3274397055203064 and F == 35.41830095052029 and len(path) == 28

@@ -88,3 +88,22 @@ def test_fitness_oracle_reproduces_reference(key):
         assert np.array_equal(stats[i], g[key + "_stats"][i])              # bit-exact incl. inf
         ms = O.path_stats(grid, want, 0.1, 0.8, msd, 100.0, True, mode=1)
         assert np.array_equal(ms, g[key + "_mpastats"][i])
+
+
+def _dijkstra_golden():
+    g = load_golden("dijkstra_cases")
+    pos = 0
+    for i in range(len(g["src"])):
+        n, m = g["shape"][i]
+        grid = g["grid"][pos:pos + n * m].reshape(n, m).astype(int)
+        pos += n * m
+        avoid = g["avoid"][g["avoid_off"][i]:g["avoid_off"][i + 1]]
+        yield (i, grid, int(g["src"][i]), int(g["dst"][i]), avoid, bool(g["flags"][i][0]), bool(g["flags"][i][1]),
+               g["path"][g["off"][i]:g["off"][i + 1]])
+
+
+def test_dijkstra_oracle_reproduces_reference():
+    for i, grid, src, dst, avoid, ad, rs, want in _dijkstra_golden():
+        orc = O.AStarOracle(grid, ad, rs)
+        got, _, _, _ = orc.solve(2, src, dst, O.cells_to_bits(avoid, grid.size))
+        assert np.array_equal(got, want), f"case {i}"
