@@ -132,3 +132,19 @@ def test_mpa_anchor_and_errors():
     assert ind["fitness"] == ind["length"] + 0.1 * ind["turns"]
     with pytest.raises(ValueError, match="MPA: Start node not found in grid."):
         MPA(np.zeros((5, 5), int), 4, 2)
+
+
+def test_demo_driver_runs_all_planners(tmp_path):
+    """The main.py-equivalent driver: all six planners on one map, results exported to .npz."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = tmp_path / "demo.npz"
+    r = subprocess.run([sys.executable, "-m", "maaco_path_planing_b200.demo", "--map", "blocks:40:1", "--scale", "0.1",
+                        "--out", str(out)], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    z = np.load(out)
+    for name in ("MAACO", "MPA", "A*", "Dijkstra", "GA", "PSO"):
+        p = z[name + "_path"]
+        assert len(p) > 0 and tuple(p[0]) == (0, 0) and tuple(p[-1]) == (39, 39), name
+    assert z["A*_stats"][0] <= z["GA_stats"][0] + 1e-9                     # A* length is optimal
