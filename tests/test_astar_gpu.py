@@ -82,7 +82,7 @@ def test_waypoint_fitness_matches_reference_goldens(key):
     assert np.array_equal(ms, g[key + "_mpastats"])
 
 
-@pytest.mark.parametrize("size,N,W", [(100, 256, 5), (256, 128, 5), (64, 200, 3)])
+@pytest.mark.parametrize("size,N,W", [(100, 256, 5), (256, 128, 5), (64, 200, 3), (512, 192, 5)])
 def test_waypoint_fitness_vs_oracle(size, N, W):
     """Population-sized batches incl. obstacle / duplicate waypoints (invalid individuals)."""
     import pyoracle as O
