@@ -262,7 +262,13 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
             // greedy :241-250.  Sequential rule == {first arg-max r} U {i>r : |attr_i - max| < 1e-9}
             const uint32_t eq = group_ballot<LPA>(gmask, gshift, in_c && attr == mx);
             const int r = __ffs(eq) - 1;
-            pool = group_ballot<LPA>(gmask, gshift, in_c && (m == r || (m > r && fabs(attr - mx) < 1e-9)));
+            if (mx < 1e-9) {
+                // every candidate lies in [0, max] with max < 1e-9, so |attr_i - max| < 1e-9 holds for all of
+                // them: the pool is the first arg-max and every later candidate (the common case on large maps)
+                pool = cand & ~((1u << r) - 1u);
+            } else {
+                pool = group_ballot<LPA>(gmask, gshift, in_c && (m == r || (m > r && fabs(attr - mx) < 1e-9)));
+            }
         } else {
             pool = cand;
             // :251-262.  sum() over np.float64 items == plain left-to-right.  n <= 8 terms <= mx, so
