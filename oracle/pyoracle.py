@@ -55,6 +55,8 @@ def lib():
         _lib.orc_astar.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_maaco_best_scan.restype = C.c_int
+        _lib.orc_ga_select.restype = C.c_int
+        _lib.orc_ga_select.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32]
     return _lib
 
 

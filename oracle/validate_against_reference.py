@@ -139,7 +139,8 @@ def main(n_cases=1500):
                 bad_stats += 1
     out["waypoint_chain"] = {"cases": n_chain, "path_mismatches": bad_path, "stats_mismatches": bad_stats, "invalid_paths": invalid}
     print(out["waypoint_chain"], flush=True)
-    json.dump(out, open(os.path.join(HERE, "VALIDATION.json"), "w"), indent=1)
+    if "--no-write" not in sys.argv:
+        json.dump(out, open(os.path.join(HERE, "VALIDATION.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

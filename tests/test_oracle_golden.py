@@ -107,3 +107,35 @@ def test_dijkstra_oracle_reproduces_reference():
         orc = O.AStarOracle(grid, ad, rs)
         got, _, _, _ = orc.solve(2, src, dst, O.cells_to_bits(avoid, grid.size))
         assert np.array_equal(got, want), f"case {i}"
+
+
+SOLVER_CASES = [(m, n) for m in ("fig7", "blocks40") for n in (20, 33)]
+
+
+@pytest.mark.parametrize("name,N", SOLVER_CASES)
+def test_pso_oracle_reproduces_reference(name, N):
+    """Oracle mirror of the PSO solve loop (sequential, asynchronous gbest) vs the reference trajectory."""
+    from py_solvers import PsoOracle
+    g = load_golden("solver_cases")
+    k = f"pso_{name}_{N}"
+    _, K, seed = (int(x) for x in g[k + "_meta"])
+    o = PsoOracle(g[k + "_grid"].astype(int), K, N, 5, 0.7, 1.5, 1.5, 0.3, 0.8, 1.8, 100.0, seed)
+    path, fit = o.solve()
+    assert np.array_equal(np.array(o.curve), g[k + "_curve"])
+    assert np.array_equal(path, g[k + "_best"]) and fit == g[k + "_stats"][4]
+    assert np.array_equal(o.pos, g[k + "_pos"]) and np.array_equal(o.vel, g[k + "_vel"])
+    assert np.array_equal(o.pbest_fit, g[k + "_pbest_fit"]) and np.array_equal(o.cur_fit, g[k + "_cur_fit"])
+
+
+@pytest.mark.parametrize("name,N", SOLVER_CASES)
+def test_ga_oracle_reproduces_reference(name, N):
+    from py_solvers import GaOracle
+    g = load_golden("solver_cases")
+    k = f"ga_{name}_{N}"
+    _, K, seed = (int(x) for x in g[k + "_meta"])
+    o = GaOracle(g[k + "_grid"].astype(int), K, N, 5, 0.1, 0.8, 3, 0.3, 0.8, 1.8, 100.0, seed)
+    path, st = o.solve()
+    assert np.array_equal(np.array(o.curve), g[k + "_curve"])
+    assert np.array_equal(path, g[k + "_best"]) and np.array_equal(st, g[k + "_stats"])
+    assert np.array_equal(np.array([ind[0] for ind in o.pop], np.int32), g[k + "_chrom"])
+    assert np.array_equal(np.array([ind[1][4] for ind in o.pop]), g[k + "_fit"])

@@ -148,3 +148,89 @@ def test_demo_driver_runs_all_planners(tmp_path):
         p = z[name + "_path"]
         assert len(p) > 0 and tuple(p[0]) == (0, 0) and tuple(p[-1]) == (39, 39), name
     assert z["A*_stats"][0] <= z["GA_stats"][0] + 1e-9                     # A* length is optimal
+
+
+def test_pso_ga_medium_vs_oracle_mirrors():
+    """Sizes beyond the recorded reference goldens: the CUDA solvers vs the oracle's sequential mirrors of the
+    solve loops (themselves pinned to the reference in tests/test_oracle_golden.py)."""
+    from py_solvers import GaOracle, PsoOracle
+    from maaco_path_planing_b200 import blocks_map
+    from maaco_path_planing_b200.ga_solver import GASolver
+    from maaco_path_planing_b200.pso import PSOSolver
+    g = blocks_map(72, 0.2, seed=61)
+    N, K = 96, 4
+    s = PSOSolver(g, num_iterations=K, num_particles=N, num_waypoints_per_particle=4, w=0.7, c1=1.5, c2=1.5,
+                  rng_seed=31, verbose=False, **POLICY)
+    res = s.solve()
+    o = PsoOracle(g, K, N, 4, 0.7, 1.5, 1.5, 0.3, 0.8, 1.8, 100.0, 31)
+    opath, ofit = o.solve()
+    assert s.convergence_curve == o.curve and res[5] == ofit
+    assert [r * 72 + c for r, c in res[0]] == list(opath)
+    assert np.array_equal(s._state["pos"].cpu().numpy(), o.pos) and np.array_equal(s._state["vel"].cpu().numpy(), o.vel)
+    assert np.array_equal(s._state["pbest_fit"].cpu().numpy(), o.pbest_fit)
+    ga = GASolver(g, num_generations=K, population_size=N, num_waypoints_per_chromosome=4, mutation_rate=0.1,
+                  crossover_rate=0.8, tournament_size=3, rng_seed=32, verbose=False, **POLICY)
+    gres = ga.solve()
+    go = GaOracle(g, K, N, 4, 0.1, 0.8, 3, 0.3, 0.8, 1.8, 100.0, 32)
+    gpath, gst = go.solve()
+    assert ga.convergence_curve == go.curve
+    assert [r * 72 + c for r, c in gres[0]] == list(gpath)
+    assert np.array_equal(ga._pop["chrom"].cpu().numpy(), np.array([ind[0] for ind in go.pop], np.int32))
+
+
+def test_population_kernels_full_size_vs_oracle():
+    """K8 / K9 at BASELINE config-3 population (4096 x 5 waypoints, 512x512): update, selection and breeding
+    kernels vs the C oracle, bit-exact."""
+    import ctypes as C
+    import torch
+    import pyoracle as O
+    from maaco_path_planing_b200 import _lib, GridMap, blocks_map
+    g = blocks_map(512, 0.2, seed=3512)
+    gm = GridMap(g)
+    dev = torch.device("cuda", gm.device)
+    L = _lib.lib()
+    N, W, seed, it = 4096, 5, 77, 3
+    rng = np.random.default_rng(0)
+    pos = rng.random((N, W, 2)) * 511
+    vel = (rng.random((N, W, 2)) - 0.5) * 30
+    pbest = rng.random((N, W, 2)) * 511
+    gbest = rng.random((W, 2)) * 511
+    d_pos, d_vel = torch.as_tensor(pos.copy(), device=dev), torch.as_tensor(vel.copy(), device=dev)
+    d_pb, d_gb = torch.as_tensor(pbest, device=dev), torch.as_tensor(gbest, device=dev)
+    wp = torch.empty((N, W), dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    max_vel = max(1.0, 0.15 * 512)
+    _lib.check(L.mpp_pso_update(gm.handle, _lib.ptr(d_pos), _lib.ptr(d_vel), _lib.ptr(d_pb), _lib.ptr(d_gb), N, 0, W, 0.7,
+                                1.5, 1.5, max_vel, C.c_uint64(seed), it, _lib.ptr(wp), stream), "mpp_pso_update")
+    torch.cuda.synchronize()
+    owp = np.zeros(W, np.int32)
+    gpos, gvel, gwp = d_pos.cpu().numpy(), d_vel.cpu().numpy(), wp.cpu().numpy()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for i in list(range(0, N, 37)) + [N - 1]:
+        a, b = np.ascontiguousarray(pos[i]), np.ascontiguousarray(vel[i])
+        O.lib().orc_pso_update_particle(p(a), p(b), p(np.ascontiguousarray(pbest[i])), p(gbest), W, C.c_double(0.7),
+                                        C.c_double(1.5), C.c_double(1.5), C.c_double(max_vel), 512, 512, C.c_uint64(seed),
+                                        it, i, p(owp))
+        assert np.array_equal(gpos[i], a) and np.array_equal(gvel[i], b) and np.array_equal(gwp[i], owp), i
+    # selection + breeding
+    fit = np.sort(rng.random(N) * 100 + 700)
+    d_fit = torch.as_tensor(fit, device=dev)
+    parents = torch.empty(N, dtype=torch.int32, device=dev)
+    _lib.check(L.mpp_ga_select(_lib.ptr(d_fit), N, 3, C.c_uint64(seed), it, _lib.ptr(parents), stream), "mpp_ga_select")
+    free = np.flatnonzero(g.ravel() != 1)
+    chrom = free[rng.integers(0, len(free), (N, W))].astype(np.int32)
+    d_chrom = torch.as_tensor(chrom, device=dev)
+    children = torch.empty((N, W), dtype=torch.int32, device=dev)
+    _lib.check(L.mpp_ga_breed(gm.handle, _lib.ptr(d_chrom), _lib.ptr(parents), N, W, 0.8, 0.1, C.c_uint64(seed), it,
+                              _lib.ptr(children), stream), "mpp_ga_breed")
+    torch.cuda.synchronize()
+    par, ch = parents.cpu().numpy(), children.cpu().numpy()
+    want = np.array([O.lib().orc_ga_select(p(fit), N, 3, C.c_uint64(seed), it, t) for t in range(N)], np.int32)
+    assert np.array_equal(par, want)
+    g8 = np.ascontiguousarray(g, dtype=np.uint8)
+    c1, c2 = np.zeros(W, np.int32), np.zeros(W, np.int32)
+    for pair in range(N // 2):
+        O.lib().orc_ga_breed_pair(p(g8), 512, 512, p(np.ascontiguousarray(chrom[par[2 * pair]])),
+                                  p(np.ascontiguousarray(chrom[par[2 * pair + 1]])), W, C.c_double(0.8), C.c_double(0.1),
+                                  C.c_uint64(seed), it, pair, p(c1), p(c2))
+        assert np.array_equal(ch[2 * pair], c1) and np.array_equal(ch[2 * pair + 1], c2), pair
