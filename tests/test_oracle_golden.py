@@ -139,3 +139,20 @@ def test_ga_oracle_reproduces_reference(name, N):
     assert np.array_equal(path, g[k + "_best"]) and np.array_equal(st, g[k + "_stats"])
     assert np.array_equal(np.array([ind[0] for ind in o.pop], np.int32), g[k + "_chrom"])
     assert np.array_equal(np.array([ind[1][4] for ind in o.pop]), g[k + "_fit"])
+
+
+@pytest.mark.parametrize("name,N", [(m, n) for m in ("fig7", "blocks40") for n in (20, 24)])
+def test_mpa_oracle_reproduces_reference(name, N):
+    """Oracle mirror of the MPA solve loop (Levy/Brownian targets with libm, private A*, memory, FADs, sorts)."""
+    from py_solvers import MpaOracle
+    g = load_golden("solver_cases")
+    k = f"mpa_{name}_{N}"
+    _, K, seed, beta10 = (int(x) for x in g[k + "_meta"])
+    o = MpaOracle(g[k + "_grid"].astype(int), N, K, 0.2, 0.5, beta10 / 10.0, 0.1, 0.8, 1.8, 100.0, seed)
+    path, st = o.solve()
+    assert np.array_equal(np.array(o.curve), g[k + "_curve"])
+    assert np.array_equal(np.array(path, np.int32), g[k + "_best"]) and np.array_equal(st, g[k + "_stats"])
+    assert np.array_equal(np.array([ind["stats"][4] for ind in o.pop]), g[k + "_pop_fit"])
+    offs = g[k + "_pop_offs"]
+    for i, ind in enumerate(o.pop):
+        assert np.array_equal(np.array(ind["path"], np.int32), g[k + "_pop_cells"][offs[i]:offs[i + 1]])

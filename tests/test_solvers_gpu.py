@@ -234,3 +234,24 @@ def test_population_kernels_full_size_vs_oracle():
                                   p(np.ascontiguousarray(chrom[par[2 * pair + 1]])), W, C.c_double(0.8), C.c_double(0.1),
                                   C.c_uint64(seed), it, pair, p(c1), p(c2))
         assert np.array_equal(ch[2 * pair], c1) and np.array_equal(ch[2 * pair + 1], c2), pair
+
+
+@pytest.mark.parametrize("beta", [2.0, 1.5])
+def test_mpa_medium_vs_oracle_mirror(beta):
+    """MPA beyond the recorded goldens: 128 predators x 9 iterations on a 72x72 map vs the oracle's mirror of the
+    solve loop (libm transcendental functions on the oracle side, device ones in the kernel)."""
+    from py_solvers import MpaOracle
+    from maaco_path_planing_b200 import blocks_map
+    from maaco_path_planing_b200.mpa import MPA
+    g = blocks_map(72, 0.2, seed=62)
+    N, K, seed = 128, 9, 41
+    s = MPA(g, num_predators=N, num_iterations=K, FADs_rate=0.2, P_const=0.5, levy_beta=beta, turn_penalty_factor=0.1,
+            safety_penalty_factor=0.8, min_safe_distance=1.8, diagonal_obstacle_penalty=100.0, rng_seed=seed, verbose=False)
+    res = s.solve_path_planning()
+    o = MpaOracle(g, N, K, 0.2, 0.5, beta, 0.1, 0.8, 1.8, 100.0, seed)
+    opath, ost = o.solve()
+    assert s.convergence_curve_data == o.curve
+    assert [r * 72 + c for r, c in res[0]] == list(opath) and res[5] == ost[4]
+    cells, ncell = s._pop["cells"].cpu().numpy(), s._pop["ncell"].cpu().numpy()
+    for i, ind in enumerate(o.pop):
+        assert np.array_equal(cells[i, :ncell[i]], np.array(ind["path"], np.int32)), f"predator {i}"
