@@ -251,9 +251,11 @@ int mpp_ga_breed(const mpp_map *map, const int32_t *chrom_dev, const int32_t *pa
  * N x max_cells) must be sorted by fitness (row 0 = elite, :333-334); the next population is written
  * unsorted to out_*.  phase = 1/2/3 (:339,:348,:365), CF as computed at :336, levy_sigma as at :251-253.
  * tmp_cells_dev: n_slots x max_cells, avoid_dev: n_slots x ceil(rows*cols/32) words of scratch.
- * status_dev[0] (zero it first): 1 = heap overflow, 2 = a path exceeded max_cells (repeat with larger
+ * Only predators [pred_begin, pred_end) are processed (a rank's shard of the population; their rows of out_* are
+ * written).  status_dev[0] (zero it first): 1 = heap overflow, 2 = a path exceeded max_cells (repeat with larger
  * buffers).  Streams (seed, MPA_PHASE, iteration, i) and (seed, MPA_FADS, iteration, i). */
-int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_predators, int iteration, int phase,
+int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_predators, int pred_begin, int pred_end,
+                      int iteration, int phase,
                       double P_const, double CF, double FADs_rate, double levy_sigma, double levy_beta, uint64_t seed,
                       const int32_t *cells_dev, const int32_t *n_cells_dev, const double *stats_dev, int max_cells,
                       int32_t *out_cells_dev, int32_t *out_n_dev, double *out_stats_dev, int32_t *tmp_cells_dev,

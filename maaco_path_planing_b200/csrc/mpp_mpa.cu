@@ -19,6 +19,7 @@ struct MpaArgs {
     StatsCtx X;
     int start, target;
     int N, iteration, phase;          // phase 1/2/3 (MPA.py:339,348,365)
+    int pred_begin, pred_end;         // predators handled by this launch (a rank's shard)
     double P_const, CF, FADs_rate, levy_sigma, levy_inv_beta;
     uint32_t k0, k1;
     const int32_t *cells;             // old population, sorted: N x max_cells
@@ -131,9 +132,9 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
     int32_t *tmp = A.tmp_cells + (size_t)slot * A.max_cells;
     for (;;) {
         int i = 0;
-        if (lane == 0) i = (int)atomicAdd(next, 1u);
+        if (lane == 0) i = A.pred_begin + (int)atomicAdd(next, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= A.N) break;
+        if (i >= A.pred_end) break;
         int st_flag = 0;
         const int32_t *old_path = A.cells + (size_t)i * A.max_cells;
         const int old_n = A.n_cells[i];
@@ -275,7 +276,8 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
     }
 }
 
-extern "C" int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_predators, int iteration, int phase,
+extern "C" int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_predators, int pred_begin, int pred_end,
+                                 int iteration, int phase,
                                  double P_const, double CF, double FADs_rate, double levy_sigma, double levy_beta,
                                  uint64_t seed, const int32_t *cells_dev, const int32_t *n_cells_dev,
                                  const double *stats_dev, int max_cells, int32_t *out_cells_dev, int32_t *out_n_dev,
@@ -285,6 +287,8 @@ extern "C" int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_p
     MPP_REQUIRE(map && policy && cells_dev && n_cells_dev && stats_dev && out_cells_dev && out_n_dev && out_stats_dev &&
                     tmp_cells_dev && avoid_dev && scratch_dev && status_dev, "mpp_mpa_iteration: null argument");
     MPP_REQUIRE(n_predators > 0 && max_cells > 1 && phase >= 1 && phase <= 3, "mpp_mpa_iteration: bad sizes");
+    MPP_REQUIRE(pred_begin >= 0 && pred_begin <= pred_end && pred_end <= n_predators, "mpp_mpa_iteration: bad predator range");
+    if (pred_begin == pred_end) return MPP_OK;
     MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_mpa_iteration: map has no start/target");
     MPP_REQUIRE(n_slots > 0 && heap_cap >= 64 && scratch_bytes >= mpp_astar_scratch_bytes(map, n_slots, heap_cap),
                 "mpp_mpa_iteration: scratch too small");
@@ -298,6 +302,7 @@ extern "C" int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_p
     A.G.allow_diag = policy->allow_diagonal; A.G.restrict_corner = policy->restrict_policy;
     A.occ_words = map->occ_words; A.start = map->start; A.target = map->target;
     A.N = n_predators; A.iteration = iteration; A.phase = phase;
+    A.pred_begin = pred_begin; A.pred_end = pred_end;
     A.P_const = P_const; A.CF = CF; A.FADs_rate = FADs_rate; A.levy_sigma = levy_sigma; A.levy_inv_beta = 1.0 / levy_beta;
     A.k0 = (uint32_t)seed; A.k1 = (uint32_t)(seed >> 32);
     A.cells = cells_dev; A.n_cells = n_cells_dev; A.stats = stats_dev; A.max_cells = max_cells;

@@ -21,8 +21,9 @@ def make_policy(turn_penalty_factor, safety_penalty_factor, min_safe_distance, d
 
 
 class SearchEngine:
-    def __init__(self, gridmap: GridMap, max_cells=None, heap_cap=None, n_slots=None):
+    def __init__(self, gridmap: GridMap, max_cells=None, heap_cap=None, n_slots=None, group=None):
         import torch
+        self.group = group            # torch.distributed group: population batches are sharded over its ranks
         self.torch = torch
         self.map = gridmap
         self.rows, self.cols = gridmap.rows, gridmap.cols
@@ -94,9 +95,39 @@ class SearchEngine:
 
     # -- K6 + K7 ----------------------------------------------------------------------------------
     def waypoint_fitness(self, waypoints, policy):
-        """waypoints: [N, W] int32 cells.  Returns (cells, n_cells, stats[N,5]) device tensors."""
+        """waypoints: [N, W] int32 cells.  Returns (cells, n_cells, stats[N,5]) device tensors.
+
+        With a process group, individuals are independent units: rank g evaluates rows
+        [g*per, (g+1)*per) and the results are all-gathered (no other data-path collective)."""
         t = self.torch
         wps = self._dev_i32(waypoints)
+        N, W = wps.shape
+        world = 1
+        if self.group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if world == 1 or N < 2 * world:
+            return self._waypoint_fitness_local(wps, policy)
+        per = (N + world - 1) // world
+        if per * world != N:                                           # pad with copies of row 0 (equal shards)
+            wps = t.cat([wps, wps[:1].expand(per * world - N, W)]).contiguous()
+        while True:
+            cells, ncell, stats = self._waypoint_fitness_local(wps[rank * per:(rank + 1) * per].contiguous(), policy,
+                                                               retry=False)
+            flags = t.stack([ncell.min(), -ncell.max()]).to(t.int64)
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=self.group)
+            if self._grow_from(int(flags[0]), int(-flags[1])):
+                continue                                               # every rank grows the same way and repeats
+            a_cells = t.empty((per * world, cells.shape[1]), dtype=t.int32, device=self.device)
+            a_ncell = t.empty(per * world, dtype=t.int32, device=self.device)
+            a_stats = t.empty((per * world, 5), dtype=t.float64, device=self.device)
+            dist.all_gather_into_tensor(a_cells, cells.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(a_ncell, ncell, group=self.group)
+            dist.all_gather_into_tensor(a_stats, stats, group=self.group)
+            return a_cells[:N], a_ncell[:N], a_stats[:N]
+
+    def _waypoint_fitness_local(self, wps, policy, retry=True):
+        t = self.torch
         N, W = wps.shape
         while True:
             scratch, slots = self._scratch_for(N)
@@ -109,12 +140,14 @@ class SearchEngine:
                 _lib.ptr(ncell), _lib.ptr(stats), _lib.ptr(visited), _lib.ptr(scratch), scratch.numel(), slots,
                 self.heap_cap, _lib.ptr(self.counters), self._stream()), "mpp_waypoint_fitness")
             self.launches += 1
-            if not self._grow_if_needed(ncell):
+            if not retry or not self._grow_if_needed(ncell):
                 return cells, ncell, stats
 
     def _grow_if_needed(self, ncell):
         """Heap overflow (-1) or truncated paths (> max_cells) -> enlarge and tell the caller to repeat."""
-        mn, mx = int(ncell.min().item()), int(ncell.max().item())
+        return self._grow_from(int(ncell.min().item()), int(ncell.max().item()))
+
+    def _grow_from(self, mn, mx):
         grew = False
         if mn < 0:
             if self.heap_cap >= 8 * self.n:

@@ -21,7 +21,7 @@ class GASolver(BasePathfinder):
     def __init__(self, grid, num_generations, population_size, num_waypoints_per_chromosome, mutation_rate,
                  crossover_rate, tournament_size=3, turn_penalty_factor=0.1, safety_penalty_factor=0.05,
                  min_safe_distance=1.5, allow_diagonal_moves=True, restrict_diagonal_near_obstacle_policy=True,
-                 diagonal_obstacle_penalty_value=1000.0, *, rng_seed=None, device=None, verbose=True):
+                 diagonal_obstacle_penalty_value=1000.0, *, rng_seed=None, device=None, verbose=True, group=None):
         g = np.asarray(grid)
         s = np.argwhere(g == START_NODE_VAL)
         t = np.argwhere(g == TARGET_NODE_VAL)
@@ -43,6 +43,7 @@ class GASolver(BasePathfinder):
                                           restrict_diagonal_near_obstacle_policy=self.restrict_diagonal_near_obstacle_policy,
                                           diagonal_obstacle_penalty_value=0, gridmap=self.map, engine=self.engine)
         self.rng_seed = _fresh_seed() if rng_seed is None else int(rng_seed)
+        self.engine.group = group   # fitness evaluation is sharded over the group's ranks (individuals are independent)
         self.verbose = verbose
         self.best_solution_overall = {'fitness': INF, 'path': []}
         self.fitness_evaluations = 0

@@ -20,7 +20,7 @@ class MPA:
     def __init__(self, grid, num_predators, num_iterations, FADs_rate=0.2, P_const=0.5, levy_beta=1.5,
                  turn_penalty_factor=0.1, safety_penalty_factor=0.05, min_safe_distance=1.5,
                  allow_diagonal_moves=True, restrict_diagonal_near_obstacle=True, diagonal_obstacle_penalty=1000.0,
-                 *, rng_seed=None, device=None, verbose=True):
+                 *, rng_seed=None, device=None, verbose=True, group=None):
         self.grid = np.array(grid, dtype=int)                           # MPA.py:20
         self.rows, self.cols = self.grid.shape
         self.num_predators = num_predators
@@ -50,6 +50,7 @@ class MPA:
         self.convergence_curve_data = []
         self.rng_seed = _fresh_seed() if rng_seed is None else int(rng_seed)
         self.verbose = verbose
+        self.group = group          # predators are independent given the sorted old population: sharded over ranks
         self.map = GridMap(self.grid, device=device)
         self.engine = SearchEngine(self.map)
         self.policy = make_policy(turn_penalty_factor, safety_penalty_factor, min_safe_distance,
@@ -132,26 +133,39 @@ class MPA:
         t = self.engine.torch
         eng = self.engine
         N = self.num_predators
+        world, rank = 1, 0
+        if self.group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        per = (N + world - 1) // world
+        lo, hi = min(N, rank * per), min(N, (rank + 1) * per)
         while True:
             P = self._pop
             mc = P["cells"].shape[1]
-            scratch, slots = eng._scratch_for(N)
-            out_cells = t.empty((N, mc), dtype=t.int32, device=eng.device)
-            out_n = t.empty(N, dtype=t.int32, device=eng.device)
-            out_stats = t.empty((N, 5), dtype=t.float64, device=eng.device)
+            scratch, slots = eng._scratch_for(max(1, hi - lo))
+            out_cells = t.empty((per * world, mc), dtype=t.int32, device=eng.device)
+            out_n = t.empty(per * world, dtype=t.int32, device=eng.device)
+            out_stats = t.empty((per * world, 5), dtype=t.float64, device=eng.device)
             tmp = t.empty((slots, mc), dtype=t.int32, device=eng.device)
             avoid = t.empty((slots, eng.words), dtype=t.int32, device=eng.device)
             status = t.zeros(1, dtype=t.int32, device=eng.device)
             _lib.check(_lib.lib().mpp_mpa_iteration(
-                self.map.handle, C.byref(self.policy), N, it, phase, self.P_const, CF, self.FADs_rate, self._levy_sigma,
-                self.levy_beta, C.c_uint64(self.rng_seed), _lib.ptr(P["cells"]), _lib.ptr(P["ncell"]), _lib.ptr(P["stats"]),
-                mc, _lib.ptr(out_cells), _lib.ptr(out_n), _lib.ptr(out_stats), _lib.ptr(tmp), _lib.ptr(avoid),
-                _lib.ptr(scratch), scratch.numel(), slots, eng.heap_cap, _lib.ptr(status), _lib.ptr(eng.counters),
-                eng._stream()), "mpp_mpa_iteration")
+                self.map.handle, C.byref(self.policy), N, lo, hi, it, phase, self.P_const, CF, self.FADs_rate,
+                self._levy_sigma, self.levy_beta, C.c_uint64(self.rng_seed), _lib.ptr(P["cells"]), _lib.ptr(P["ncell"]),
+                _lib.ptr(P["stats"]), mc, _lib.ptr(out_cells), _lib.ptr(out_n), _lib.ptr(out_stats), _lib.ptr(tmp),
+                _lib.ptr(avoid), _lib.ptr(scratch), scratch.numel(), slots, eng.heap_cap, _lib.ptr(status),
+                _lib.ptr(eng.counters), eng._stream()), "mpp_mpa_iteration")
             eng.launches += 1
+            if world > 1:
+                dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
             st = int(status.item())
             if st == 0:
-                self._pop = dict(cells=out_cells, ncell=out_n, stats=out_stats)
+                if world > 1:                                          # in-place all-gather of the ranks' row blocks
+                    sl = slice(rank * per, (rank + 1) * per)
+                    dist.all_gather_into_tensor(out_cells, out_cells[sl], group=self.group)
+                    dist.all_gather_into_tensor(out_n, out_n[sl], group=self.group)
+                    dist.all_gather_into_tensor(out_stats, out_stats[sl], group=self.group)
+                self._pop = dict(cells=out_cells[:N], ncell=out_n[:N], stats=out_stats[:N])
                 self.predator_evaluations += N
                 return
             if st == 1:

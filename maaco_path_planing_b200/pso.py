@@ -24,7 +24,7 @@ class PSOSolver(BasePathfinder):
     def __init__(self, grid, num_iterations, num_particles, num_waypoints_per_particle, w, c1, c2,
                  turn_penalty_factor=0.1, safety_penalty_factor=0.05, min_safe_distance=1.5,
                  allow_diagonal_moves=True, restrict_diagonal_near_obstacle_policy=True,
-                 diagonal_obstacle_penalty_value=1000.0, *, rng_seed=None, device=None, verbose=True):
+                 diagonal_obstacle_penalty_value=1000.0, *, rng_seed=None, device=None, verbose=True, group=None):
         g = np.asarray(grid)
         s = np.argwhere(g == START_NODE_VAL)
         t = np.argwhere(g == TARGET_NODE_VAL)
@@ -45,6 +45,7 @@ class PSOSolver(BasePathfinder):
                                           restrict_diagonal_near_obstacle_policy=self.restrict_diagonal_near_obstacle_policy,
                                           diagonal_obstacle_penalty_value=0, gridmap=self.map, engine=self.engine)
         self.rng_seed = _fresh_seed() if rng_seed is None else int(rng_seed)
+        self.engine.group = group   # fitness evaluation is sharded over the group's ranks (individuals are independent)
         self.verbose = verbose
         self.gbest_particle_data = {'fitness': INF, 'path': [], 'position': []}
         self.fitness_evaluations = 0

@@ -255,3 +255,18 @@ def test_mpa_medium_vs_oracle_mirror(beta):
     cells, ncell = s._pop["cells"].cpu().numpy(), s._pop["ncell"].cpu().numpy()
     for i, ind in enumerate(o.pop):
         assert np.array_equal(cells[i, :ncell[i]], np.array(ind["path"], np.int32)), f"predator {i}"
+
+
+def test_sharded_populations_two_gpus():
+    """PSO / GA / MPA with their populations sharded over 2 GPUs == reference goldens (skipped on a 1-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tests", "multigpu_solvers_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "multigpu_solvers_check ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
