@@ -579,13 +579,18 @@ mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, i
 // -- (deposit, word) in ant order -- into shared memory, double buffered; warp 0 then folds only the hits.
 // The streaming / zero-skipping (HBM-bound) is spread over 8 warps per word and overlapped with the fold, and
 // the sequential part is proportional to the number of ants that actually visited the word.
+#ifndef MPP_PHER_ROUND
 #define MPP_PHER_ROUND 1024
+#endif
+#define MPP_PHER_PW (MPP_PHER_ROUND / 8)   // ants per warp per round
+#define MPP_PHER_U (MPP_PHER_PW / 32)     // loads per lane per round
 __global__ void __launch_bounds__(MPP_PHER_THREADS)
 mpp_maaco_pheromone_block_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
                                  uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg,
                                  int seg_ants, int word0, int n_words, double rho,
                                  const mpp_maaco_state *__restrict__ state, int clear_visit) {
-    __shared__ PherEntry s_list[2][MPP_PHER_ROUND];          // per round: warp k owns entries [128k, 128k+128)
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    PherEntry (*s_list)[MPP_PHER_ROUND] = reinterpret_cast<PherEntry (*)[MPP_PHER_ROUND]>(s_dyn);  // [2][ROUND]; warp k owns [PW*k, PW*(k+1))
     __shared__ int s_cnt[2][8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int wl = blockIdx.x;                               // one bitmap word (32 cells) per block
@@ -596,33 +601,33 @@ mpp_maaco_pheromone_block_kernel(const uint32_t *__restrict__ occ, int pitch, in
     const int rounds_per_seg = (seg_ants + MPP_PHER_ROUND - 1) / MPP_PHER_ROUND;
     const int n_rounds = n_seg * rounds_per_seg;
     // the words of round r+1 are loaded while round r is compacted (one DRAM latency per round otherwise)
-    auto load_round = [&](int r, uint32_t (&v)[4]) {
-        const int seg = r / rounds_per_seg, a_base = (r % rounds_per_seg) * MPP_PHER_ROUND + wid * 128;
+    auto load_round = [&](int r, uint32_t (&v)[MPP_PHER_U]) {
+        const int seg = r / rounds_per_seg, a_base = (r % rounds_per_seg) * MPP_PHER_ROUND + wid * MPP_PHER_PW;
         const uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int a = a_base + u * 32 + lane; v[u] = (a < seg_ants) ? row[a] : 0u; }
+        for (int u = 0; u < MPP_PHER_U; ++u) { const int a = a_base + u * 32 + lane; v[u] = (a < seg_ants) ? row[a] : 0u; }
     };
-    uint32_t nx[4] = {0u, 0u, 0u, 0u};
+    uint32_t nx[MPP_PHER_U] = {};
     if (n_rounds > 0) load_round(0, nx);
     for (int r = 0; r <= n_rounds; ++r) {
         const int buf = r & 1;
         if (r < n_rounds) {
-            // ---- produce round r: this warp's 128 ants ----
-            const int seg = r / rounds_per_seg, a_base = (r % rounds_per_seg) * MPP_PHER_ROUND + wid * 128;
+            // ---- produce round r: this warp's MPP_PHER_PW ants ----
+            const int seg = r / rounds_per_seg, a_base = (r % rounds_per_seg) * MPP_PHER_ROUND + wid * MPP_PHER_PW;
             uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
             const double *dep = deposit + (size_t)seg * seg_ants;
-            uint32_t wd[4];
+            uint32_t wd[MPP_PHER_U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) wd[u] = nx[u];
+            for (int u = 0; u < MPP_PHER_U; ++u) wd[u] = nx[u];
             if (r + 1 < n_rounds) load_round(r + 1, nx);
             int cnt = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < MPP_PHER_U; ++u) {
                 const uint32_t nz = __ballot_sync(0xffffffffu, wd[u] != 0u);
                 if (wd[u] != 0u) {
                     const int a = a_base + u * 32 + lane;
                     PherEntry e; e.d = dep[a]; e.w = wd[u]; e.pad = 0u;
-                    s_list[buf][wid * 128 + cnt + __popc(nz & ((1u << lane) - 1u))] = e;
+                    s_list[buf][wid * MPP_PHER_PW + cnt + __popc(nz & ((1u << lane) - 1u))] = e;
                     if (clear_visit) row[a] = 0u;
                 }
                 cnt += __popc(nz);
@@ -635,7 +640,7 @@ mpp_maaco_pheromone_block_kernel(const uint32_t *__restrict__ occ, int pitch, in
 #pragma unroll 1
             for (int k = 0; k < 8; ++k) {
                 const int n = s_cnt[pb][k];
-                const PherEntry *lst = &s_list[pb][k * 128];
+                const PherEntry *lst = &s_list[pb][k * MPP_PHER_PW];
                 int i = 0;
                 for (; i + 4 <= n; i += 4) {
                     // select the operand, not the sum: the loop-carried chain is a bare DADD (t + 0.0 == t exactly)
@@ -725,7 +730,14 @@ extern "C" int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t
     static const bool use_chain = getenv("MPP_PHER_CHAIN") != nullptr;  // experimental: measured no gain on 8xB200
     static const bool use_warp = getenv("MPP_PHER_WARP") != nullptr;    // previous warp-per-word kernel
     if (!use_chain && !use_warp) {
-        mpp_maaco_pheromone_block_kernel<<<n_words, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
+        const size_t list_bytes = 2 * (size_t)MPP_PHER_ROUND * sizeof(PherEntry);
+        static bool attr_set = false;
+        if (!attr_set && list_bytes > 48 * 1024) {
+            MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_pheromone_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)list_bytes));
+            attr_set = true;
+        }
+        mpp_maaco_pheromone_block_kernel<<<n_words, MPP_PHER_THREADS, list_bytes, (cudaStream_t)stream>>>(
             map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
             word0, n_words, rho, state_dev, clear_visit);
     } else if (n_seg == 1 || !use_chain) {
