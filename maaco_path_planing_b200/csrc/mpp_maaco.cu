@@ -215,10 +215,9 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
     const double *const __restrict__ tau = A.tau;
     const double *const __restrict__ E01 = A.E01;                // interleaved: E[2*cell + turn]
     const uint8_t *const __restrict__ svalid = A.svalid;
-    int n_path = 1, prev_m = -1, turns = 0;
+    int n_path = 1, prev_m = -1, turns = 0;                       // steps taken == n_path - 1
     double len = 0.0;
-    uint32_t steps = 0;
-    const uint32_t max_steps = 2u * (uint32_t)RC;                 // R*C < 2^30
+    const int max_path = 2 * RC + 1;                              // step cap 2*R*C (MAACO.py:283); R*C < 2^30
     bool failed = false;
     double u0_l = 0.0, u1_l = 0.0;
     if (m == 0) {
@@ -226,7 +225,8 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
         cells_a[0] = cur;
     }
     __syncwarp(gmask);
-    while (cur != target && steps < max_steps) {
+    int32_t *cell_out = cells_a + 1;                              // next path slot
+    while (cur != target && n_path < max_path) {
         // ---- one round of loads ----
         const uint32_t sv = svalid[cur];                              // bounds / obstacle / corner-cut (:93-120)
         int j = cur + delta;
@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
         const double tv = tau[j];
         const double ev = E01[2 * (size_t)j + (turn ? 1 : 0)];
         // uniforms: draws 2s (q-test) and 2s+1 (selection) of stream (seed, TOUR, it, ant); block s
-        const uint32_t sub = steps & (uint32_t)(LPA - 1);
-        if (sub == 0) tour_uniforms(steps + (uint32_t)m, ant_global, A.it, A.k0, A.k1, u0_l, u1_l);
+        const uint32_t step = (uint32_t)(n_path - 1), sub = step & (uint32_t)(LPA - 1);
+        if (sub == 0) tour_uniforms(step + (uint32_t)m, ant_global, A.it, A.k0, A.k1, u0_l, u1_l);
         const double u0 = __shfl_sync(gmask, u0_l, gshift + (int)sub);
         const double u1 = __shfl_sync(gmask, u1_l, gshift + (int)sub);
         const bool free_lane = (m < 8) && ((sv >> m) & 1u) && !((tw >> (j & 31)) & 1u);   // + tabu :93-95
@@ -296,11 +296,11 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
         prev_m = pick;
         if (m == pick) {
             visit_a[(size_t)(j >> 5) * n_ants] = tw | (1u << (j & 31));
-            if (n_path < A.max_cells) cells_a[n_path] = j;
+            if (n_path < A.max_cells) *cell_out = j;
         }
         cur = __shfl_sync(gmask, j, gshift + pick);
         ++n_path;
-        ++steps;
+        ++cell_out;
         __syncwarp(gmask);
     }
     if (m == 0) {
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
         res.n_cells = ok ? n_path : 0;
         res.turns = ok ? turns : -1;
         A.result[a] = res;
-        if (A.steps) atomicAdd(A.steps, (unsigned long long)steps);
+        if (A.steps) atomicAdd(A.steps, (unsigned long long)(n_path - 1));
     }
 }
 
