@@ -145,3 +145,37 @@ def test_dijkstra_matches_reference_goldens_and_anchor():
                        diagonal_obstacle_penalty_value=100.0)
     path, L, T, SP, DP, F = d.solve()
     assert T == 12 and SP == 0.3274397055203064 and F == 35.41830095052029 and len(path) == 28
+
+
+def test_config3_full_population_properties():
+    """BASELINE config 3 at full size (4096 individuals x 5 waypoints, 512x512): size-independent properties --
+    idempotence (same chromosomes -> identical bytes), every valid path is a start->target chain through its
+    waypoints in order, statistics recomputed by the stand-alone kernel equal the fused ones."""
+    from maaco_path_planing_b200 import blocks_map
+    from maaco_path_planing_b200.engine import make_policy
+    size, N, W = 512, 4096, 5
+    grid = blocks_map(size, 0.2, seed=3000 + size)
+    rng = np.random.default_rng(11)
+    free = np.flatnonzero(grid.ravel() != 1)
+    wps = free[rng.integers(0, len(free), (N, W))].astype(np.int32)
+    eng = _engine(grid)
+    pol = make_policy(0.3, 0.8, 1.8, 100.0)
+    cells, ncell, stats = eng.waypoint_fitness(wps, pol)
+    c2, n2, s2 = eng.waypoint_fitness(wps, pol)
+    assert bool((ncell == n2).all()) and bool((stats == s2).all() | (stats != stats).all())
+    nc = ncell.cpu().numpy()
+    st = stats.cpu().numpy()
+    assert np.array_equal(st, s2.cpu().numpy())
+    assert (nc > 0).mean() > 0.95
+    re = eng.path_stats(cells, ncell, pol).cpu().numpy()
+    ok = nc > 0
+    assert np.array_equal(re[ok], st[ok])                                  # fused stats == stand-alone kernel
+    cc = cells.cpu().numpy()
+    flat = grid.ravel()
+    for i in np.flatnonzero(ok)[:128]:
+        p = cc[i, :nc[i]]
+        assert p[0] == 0 and p[-1] == size * size - 1 and not np.any(flat[p] == 1)
+        pos = {int(c): k for k, c in enumerate(p.tolist())}
+        order = [pos[int(w)] for w in wps[i]]
+        assert order == sorted(order)                                      # waypoints visited in chromosome order
+        assert np.array_equal(c2[i, :nc[i]].cpu().numpy(), p)
