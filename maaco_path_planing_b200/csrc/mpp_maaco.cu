@@ -99,6 +99,7 @@ extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, d
 // ---------------------------------------------------------------------------------------------
 struct TourArgs {
     const uint8_t *svalid;  // per-cell static move mask (MAACO move order)
+    const uint32_t *rank;   // per (cell, turn context) move ranking (mpp_maaco_rank) or null
     int R, C, start, target;
     const double *tau, *E01;
     uint32_t it;
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
     const double *const __restrict__ tau = A.tau;
     const double *const __restrict__ E01 = A.E01;                // interleaved: E[2*cell + turn]
     const uint8_t *const __restrict__ svalid = A.svalid;
+    const uint32_t *const __restrict__ rank = A.rank;
     int n_path = 1, prev_m = -1, turns = 0;                       // steps taken == n_path - 1
     double len = 0.0;
     const int max_path = 2 * RC + 1;                              // step cap 2*R*C (MAACO.py:283); R*C < 2^30
@@ -227,14 +229,15 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
     __syncwarp(gmask);
     int32_t *cell_out = cells_a + 1;                              // next path slot
     while (cur != target && n_path < max_path) {
-        // ---- one round of loads ----
-        const uint32_t sv = svalid[cur];                              // bounds / obstacle / corner-cut (:93-120)
+        // ---- one round of loads: the cell's ranking word (or static mask) and this lane's visited word ----
+        // ranking word (mpp_maaco_rank): [31:24] static move mask, [23:0] rank position of each move by
+        // attractiveness (3 bits/move) for this (cell, previous move); 0xFFFFFF = "not small, use the full rule"
+        const uint32_t ctx = (n_path >= 2) ? (uint32_t)(prev_m + 1) : 0u;
+        const uint32_t rw = rank ? rank[(size_t)cur * 9 + ctx] : (((uint32_t)svalid[cur] << 24) | 0xFFFFFFu);
+        const uint32_t sv = rw >> 24;                                 // bounds / obstacle / corner-cut (:93-120)
         int j = cur + delta;
         j = j < 0 ? 0 : (j >= RC ? RC - 1 : j);                       // clamp: lanes outside the mask are ignored
-        const bool turn = (n_path >= 2) && (m != prev_m);             // MAACO.py:184-195
         const uint32_t tw = visit_a[(size_t)(j >> 5) * n_ants];
-        const double tv = tau[j];
-        const double ev = E01[2 * (size_t)j + (turn ? 1 : 0)];
         // uniforms: draws 2s (q-test) and 2s+1 (selection) of stream (seed, TOUR, it, ant); block s
         const uint32_t step = (uint32_t)(n_path - 1), sub = step & (uint32_t)(LPA - 1);
         if (sub == 0) tour_uniforms(step + (uint32_t)m, ant_global, A.it, A.k0, A.k1, u0_l, u1_l);
@@ -247,6 +250,24 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
         if (!cand) cand = valid;                                      // strategy 3 :172-180
         if (!cand) { failed = true; break; }                          // :287-288
         const bool in_c = (cand >> m) & 1u;                           // cand has 8 bits -> false for m >= 8
+        uint32_t pool;   // the set the final uniform index is taken from
+        int k = -1;      // >= 0: rank already decided by the roulette
+        if ((rw & 0xFFFFFFu) != 0xFFFFFFu) {
+            // every attractiveness around this cell is < 1e-10 (mpp_maaco_rank), hence:
+            //  greedy  :241-250 -> |attr_i - max| < 1e-9 for all i: pool = first arg-max + every later candidate;
+            //  roulette:251-254 -> sum < 1e-9: uniform over all candidates.
+            // Only the ORDER of the attractiveness values matters, and that was ranked once per cell.
+            if (u0 <= A.q0) {
+                const uint32_t key = in_c ? ((((rw >> (3 * m)) & 7u) << 3) | (uint32_t)m) : 0xFFu;
+                const int r = (int)(__reduce_min_sync(gmask, key) & 7u);   // best-ranked candidate == first arg-max
+                pool = cand & ~((1u << r) - 1u);
+            } else {
+                pool = cand;
+            }
+        } else {
+        const bool turn = (n_path >= 2) && (m != prev_m);             // MAACO.py:184-195
+        const double tv = tau[j];
+        const double ev = E01[2 * (size_t)j + (turn ? 1 : 0)];
         const double ta = (A.alpha == 1.0) ? tv : pow_slow(tv, A.alpha);   // tau**alpha (x**1.0 == x exactly)
         const double attr = ta * ev;                                  // :238
         // group max of attr over the candidates (attr >= 0: IEEE order == unsigned bit order)
@@ -256,15 +277,13 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
         const uint32_t lo = (in_c && hi == mhi) ? (uint32_t)key : 0u;
         const uint32_t mlo = __reduce_max_sync(gmask, lo);
         const double mx = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-        uint32_t pool;   // the set the final uniform index is taken from
-        int k = -1;      // >= 0: rank already decided by the roulette
         if (u0 <= A.q0) {
             // greedy :241-250.  Sequential rule == {first arg-max r} U {i>r : |attr_i - max| < 1e-9}
             const uint32_t eq = group_ballot<LPA>(gmask, gshift, in_c && attr == mx);
             const int r = __ffs(eq) - 1;
             if (mx < 1e-9) {
                 // every candidate lies in [0, max] with max < 1e-9, so |attr_i - max| < 1e-9 holds for all of
-                // them: the pool is the first arg-max and every later candidate (the common case on large maps)
+                // them: the pool is the first arg-max and every later candidate
                 pool = cand & ~((1u << r) - 1u);
             } else {
                 pool = group_ballot<LPA>(gmask, gshift, in_c && (m == r || (m > r && fabs(attr - mx) < 1e-9)));
@@ -272,7 +291,7 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
         } else {
             pool = cand;
             // :251-262.  sum() over np.float64 items == plain left-to-right.  n <= 8 terms <= mx, so
-            // 8*mx < 0.9e-9 already implies S < 1e-9 (the common case on large maps: attr ~ 1e-20)
+            // 8*mx < 0.9e-9 already implies S < 1e-9
             if (!(mx * 8.0 < 0.9e-9)) {
                 double S = 0.0;
 #pragma unroll
@@ -282,6 +301,7 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
                 }
                 if (!(S < 1e-9)) k = roulette_rank(attr, cand, gmask, gshift, S, u1);  // rare: near T only
             }
+        }
         }
         if (k < 0) {                                                  // random.choice(pool) -> pool[floor(u*n)]
             const int n = __popc(pool);
@@ -315,7 +335,7 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
 }
 
 extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E01_dev,
-                               int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
+                               const uint32_t *rank_dev, int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
                                uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, mpp_ant_result *result_dev,
                                unsigned long long *steps_dev, int lanes_per_ant, void *stream) {
     MPP_REQUIRE(map && tau_dev && E01_dev && visitT_dev && cells_dev && result_dev, "mpp_maaco_tours: null argument");
@@ -327,6 +347,7 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
     MPP_CUDA(cudaSetDevice(map->device));
     TourArgs A;
     A.svalid = map->svalid_dev;
+    A.rank = rank_dev;
     A.R = map->rows; A.C = map->cols; A.start = map->start; A.target = map->target;
     A.tau = tau_dev; A.E01 = E01_dev;
     A.it = (uint32_t)iteration; A.q0 = q0; A.alpha = alpha;
@@ -340,6 +361,62 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
     if (lanes_per_ant == 32) mpp_maaco_tour_kernel<32><<<blocks, MPP_TOUR_THREADS, 0, s>>>(A);
     else if (lanes_per_ant == 16) mpp_maaco_tour_kernel<16><<<blocks, MPP_TOUR_THREADS, 0, s>>>(A);
     else mpp_maaco_tour_kernel<8><<<blocks, MPP_TOUR_THREADS, 0, s>>>(A);
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2a: per (cell, turn context) ranking of the 8 moves by attractiveness tau**alpha * eta'**beta (MAACO.py:238).
+// With beta = 7 the values are ~1e-8..1e-20, so the selection rules (:241-262) only depend on their ORDER
+// (|attr_i - max| < 1e-9 and sum < 1e-9 always hold); the tour kernel then needs one 4-byte word per step
+// instead of 16 fp64 loads.  Context 0 = no previous move (turn flag 0 for every candidate, :185-186),
+// context p+1 = previous move p (turn flag = (m != p)).  Word: [31:24] static move mask, [23:0] rank position
+// of each move (0 = largest attractiveness, ties -> lower move index, exactly the order the sequential scan
+// sees), or 0xFFFFFF when some attractiveness is >= 1e-10 (the tour kernel then applies the full rule).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mpp_maaco_rank_kernel(const uint8_t *__restrict__ svalid,
+                                                             const double *__restrict__ tau,
+                                                             const double *__restrict__ E01, double alpha, int R, int C,
+                                                             uint32_t *__restrict__ rank) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= R * C * 9) return;
+    const int cell = t / 9, ctx = t - cell * 9;
+    const uint32_t sv = svalid[cell];
+    double a[8];
+    double mx = 0.0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        a[m] = -1.0;
+        if ((sv >> m) & 1u) {
+            const int j = cell + ((int)((0xA940u >> (2 * m)) & 3u) - 1) * C + ((int)((0x9224u >> (2 * m)) & 3u) - 1);
+            const double tv = tau[j];
+            const double ta = (alpha == 1.0) ? tv : pow_slow(tv, alpha);
+            const bool turn = ctx > 0 && m != ctx - 1;
+            a[m] = ta * E01[2 * (size_t)j + (turn ? 1 : 0)];
+            mx = a[m] > mx ? a[m] : mx;
+        }
+    }
+    uint32_t word = 0xFFFFFFu;
+    if (mx < 1e-10) {
+        word = 0u;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            int pos = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pos += (a[q] > a[m]) || (a[q] == a[m] && q < m);
+            word |= (uint32_t)pos << (3 * m);
+        }
+    }
+    rank[t] = word | (sv << 24);
+}
+
+extern "C" int mpp_maaco_rank(const mpp_map *map, const double *tau_dev, const double *E01_dev, double alpha,
+                              uint32_t *rank_dev, void *stream) {
+    MPP_REQUIRE(map && tau_dev && E01_dev && rank_dev, "mpp_maaco_rank: null argument");
+    MPP_CUDA(cudaSetDevice(map->device));
+    const int total = map->rows * map->cols * 9;
+    mpp_maaco_rank_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(map->svalid_dev, tau_dev, E01_dev, alpha,
+                                                                              map->rows, map->cols, rank_dev);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }

@@ -31,7 +31,7 @@ class MAACO:
                  a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
                  C0_initial_pheromone=0.1, *,
                  rng_seed=None, device=None, max_cells=None, lanes_per_ant=0, group=None, exchange="moves",
-                 verbose=True):
+                 use_rank=True, verbose=True):
         import torch
         self.grid = np.array(grid, dtype=int)                       # MAACO.py:15
         self.rows, self.cols = self.grid.shape
@@ -88,6 +88,8 @@ class MAACO:
         self._tau = torch.zeros(npad, dtype=f64, device=dev)        # padded so tau slices all-gather evenly
         self._E01 = torch.empty(2 * n, dtype=f64, device=dev)       # eta'**beta, interleaved by turn flag
         self._dist_t = torch.empty(n, dtype=f64, device=dev)
+        self.use_rank = use_rank
+        self._rank = torch.empty(9 * n, dtype=i32, device=dev) if use_rank else None
         self._params = _lib.MaacoParams(alpha, beta, rho, Q, a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
                                         C0_initial_pheromone, num_iterations)
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -140,8 +142,11 @@ class MAACO:
     # ---- one colony pass (MAACO.py:336-359), fully asynchronous ----------------------------
     def _enqueue_tours(self, it, stream):
         nl, off = self.n_local, self.ant_offset
+        if self.use_rank:                                            # move ranking for the current tau
+            _lib.check(_lib.lib().mpp_maaco_rank(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E01), self.alpha,
+                                                 _lib.ptr(self._rank), stream), "mpp_maaco_rank")
         _lib.check(_lib.lib().mpp_maaco_tours(
-            self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E01), it,
+            self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E01), _lib.ptr(self._rank) if self.use_rank else None, it,
             self._calculate_adaptive_q0(it), self.alpha, nl, off, C.c_uint64(self.rng_seed),
             _lib.ptr(self._visit_local), _lib.ptr(self._cells), self.max_cells,
             C.c_void_p(self._result.data_ptr() + 16 * off), _lib.ptr(self._steps), self.lanes_per_ant, stream),
@@ -206,7 +211,7 @@ class MAACO:
                                                       _lib.ptr(self._offsets), _lib.ptr(self._result), self.world, nl,
                                                       self.rank * wn, wn, _lib.ptr(self._visit_recv), stream),
                            "mpp_maaco_rebuild_visits")
-                self.kernel_launches += 3
+                self.kernel_launches += 4 if self.use_rank else 3
             # the local bitmaps are free again: clear them off the critical path
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
@@ -221,7 +226,7 @@ class MAACO:
             cur.wait_stream(self._side)                                # next pass's tours need the cleared bitmaps
         if events:
             events[3].record(cur)
-        self.kernel_launches += 3
+        self.kernel_launches += 4 if self.use_rank else 3
 
     def _read_state(self):
         st = _lib.MaacoState.from_buffer_copy(self._state.cpu().numpy().tobytes())
