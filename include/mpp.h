@@ -90,7 +90,7 @@ double mpp_maaco_q0(int num_iterations, int iteration, double q0_initial);
 /* ranks, per cell and previous-move context, the 8 moves by attractiveness tau**alpha * eta'**beta
  * (MAACO.py:235-239).  Where every value is < 1e-10 the selection rules (:241-262) depend only on that order
  * and the tour kernel uses the ranking; elsewhere the word says "evaluate".  Must be re-run after every
- * pheromone update.  rank_dev: 9*rows*cols uint32. */
+ * pheromone update.  rank_dev: 9*rows*cols entries of two uint32. */
 int mpp_maaco_rank(const mpp_map *map, const double *tau_dev, const double *E01_dev, double alpha, uint32_t *rank_dev,
                    void *stream);
 
@@ -105,7 +105,7 @@ typedef struct {
  * orientation filter + crossing-prohibition (:100-181) and pseudo-random-proportional selection
  * (:228-262).  Ant i of this call is global ant `ant_offset + i` (its RNG stream id).
  *   tau / E01      rows*cols / 2*rows*cols doubles (mpp_maaco_tables)
- *   rank_dev       optional 9*rows*cols words from mpp_maaco_rank for the CURRENT tau (NULL = evaluate the
+ *   rank_dev       optional 9*rows*cols two-word entries from mpp_maaco_rank for the CURRENT tau (NULL = evaluate the
  *                  attractiveness of every candidate at every step)
  *   visitT_dev     word-major visited bitmaps: word w of ant i at [w*n_ants + i], ceil(rows*cols/32)
  *                  words per ant; MUST be zero on entry; holds each ant's visited set on return
@@ -113,7 +113,7 @@ typedef struct {
  *                  counts them)
  *   result_dev     n_ants x mpp_ant_result (:288,:292,:300-302)
  *   steps_dev      optional counter, += number of ant steps taken
- *   lanes_per_ant  8, 16 or 32 lanes cooperate on one ant (0 = choose from n_ants)              */
+ *   lanes_per_ant  1 = one thread per ant; 8, 16 or 32 lanes cooperate on one ant; 0 = library default              */
 int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E01_dev, const uint32_t *rank_dev,
                     int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
                     uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, mpp_ant_result *result_dev,

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
         // ranking word (mpp_maaco_rank): [31:24] static move mask, [23:0] rank position of each move by
         // attractiveness (3 bits/move) for this (cell, previous move); 0xFFFFFF = "not small, use the full rule"
         const uint32_t ctx = (n_path >= 2) ? (uint32_t)(prev_m + 1) : 0u;
-        const uint32_t rw = rank ? rank[(size_t)cur * 9 + ctx] : (((uint32_t)svalid[cur] << 24) | 0xFFFFFFu);
+        const uint32_t rw = rank ? rank[2 * ((size_t)cur * 9 + ctx) + 1] : (((uint32_t)svalid[cur] << 24) | 0xFFFFFFu);
         const uint32_t sv = rw >> 24;                                 // bounds / obstacle / corner-cut (:93-120)
         int j = cur + delta;
         j = j < 0 ? 0 : (j >= RC ? RC - 1 : j);                       // clamp: lanes outside the mask are ignored
@@ -334,6 +334,405 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2, thread-per-ant form.  One ant step is a serial chain (position -> tabu bits -> candidate set ->
+// selection -> position) and a colony pass lasts as long as its longest tour times the latency of that
+// chain, so the chain stays inside ONE thread (no shuffles / votes / warp reductions on it) and touches
+// only shared memory and one L2-resident ranking word:
+//   * tabu bits (:93-95) come from a 64x64-cell WINDOW of the ant's visited set kept in shared memory
+//     (toroidal: cell (r,c) -> row r&63, bit c&63).  A global store to a line evicts it from L1 (measured:
+//     tools/ubench/l1_store.cu, 123 -> 432 cycles per dependent load), so re-reading a bitmap the ant
+//     itself keeps writing costs an L2 round trip per step; the window never re-reads what it wrote.
+//     Every mark is also RED.OR'ed into the word-major visitT (what the pheromone update streams); when
+//     the ant comes within one cell of the window edge the window slides by one 32-cell tile and the warp
+//     reloads the entering tiles from visitT;
+//   * selection: the ranking word of (cell, previous move) when usable, else the literal rules on
+//     tau**alpha * eta'**beta (tour_select_slow);
+//   * the warp's lanes generate Philox blocks together: lane L makes the block of ant L%apw, step s+L/apw.
+// `apw` lanes of each warp own an ant: fewer ants per warp = more warps to spread over the SMs.
+// ---------------------------------------------------------------------------------------------
+#define MPP_TOUR1_THREADS 128
+
+// literal selection rules MAACO.py:228-262 for one ant; cand = candidate move mask (move order :98).
+__device__ __noinline__ int tour_select_slow(uint32_t cand, int cr, int cc, int C, bool have_prev, int prev_m,
+                                             const double *__restrict__ tau, const double *__restrict__ E01,
+                                             double alpha, double q0, double u0, double u1) {
+    int mv[8], n = 0;
+    double attr[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        if (!((cand >> m) & 1u)) continue;
+        const int dr = (int)((0xA940u >> (2 * m)) & 3u) - 1, dc = (int)((0x9224u >> (2 * m)) & 3u) - 1;
+        const int j = (cr + dr) * C + (cc + dc);
+        const bool turn = have_prev && (m != prev_m);                 // :184-195
+        const double tv = tau[j];
+        const double ta = (alpha == 1.0) ? tv : pow_slow(tv, alpha);
+        attr[n] = ta * E01[2 * (size_t)j + (turn ? 1 : 0)];           // :238
+        mv[n] = m;
+        ++n;
+    }
+    int k;
+    if (u0 <= q0) {                                                   // greedy :241-250
+        double mx = -1.0;
+        int best[8], nb = 0;
+        for (int i = 0; i < n; ++i) {
+            if (attr[i] > mx) { mx = attr[i]; nb = 0; best[nb++] = i; }
+            else if (fabs(attr[i] - mx) < 1e-9) best[nb++] = i;
+        }
+        int q = (int)(u1 * (double)nb);
+        q = q < nb ? q : nb - 1;
+        k = best[q];
+    } else {
+        double S = 0.0;                                               // :252 plain left-to-right
+        for (int i = 0; i < n; ++i) S += attr[i];
+        bool uniform = S < 1e-9;                                      // :253-254
+        double pr[8];
+        double ps = 0.0;
+        if (!uniform) {
+            for (int i = 0; i < n; ++i) { pr[i] = attr[i] / S; ps += pr[i]; }   // :255
+            if (fabs(ps - 1.0) > 1e-6) {                              // :257-258
+                const double ps0 = ps;
+                ps = 0.0;
+                for (int i = 0; i < n; ++i) { pr[i] = pr[i] / ps0; ps += pr[i]; }
+            }
+            if (!(fabs(ps - 1.0) <= 1.4901161193847656e-08)) uniform = true;    // choice() ValueError -> :262
+        }
+        if (uniform) {
+            k = (int)(u1 * (double)n);
+        } else {
+            // RandomState.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, side='right')
+            double cdf[8], acc = 0.0;
+            for (int i = 0; i < n; ++i) { acc += pr[i]; cdf[i] = acc; }
+            k = 0;
+            for (int i = 0; i < n; ++i)
+                if (cdf[i] / acc <= u1) ++k;
+        }
+        k = k < n ? k : n - 1;
+    }
+    return mv[k];
+}
+
+// visited bits of cells (r, 32*tcx .. 32*tcx+31) from the word-major bitmap (flat cell index, 32 per word)
+__device__ __forceinline__ uint32_t tour_tile_word(const uint32_t *visit_a, size_t n_ants, int n_words, int r, int tcx,
+                                                   int R, int C, int TC) {
+    if (r < 0 || r >= R || tcx < 0 || tcx >= TC) return 0u;
+    const int f = r * C + (tcx << 5), w = f >> 5, sh = f & 31;
+    const uint32_t lo = __ldcg(visit_a + (size_t)w * n_ants);
+    if (sh == 0) return lo;
+    const uint32_t hi = (w + 1 < n_words) ? __ldcg(visit_a + (size_t)(w + 1) * n_ants) : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+
+// the reverse: merge a window word into the word-major bitmap.  Rows are always handled by lane (r & 31), so a later
+// tour_tile_word of the same row is ordered after this by program order.  With C % 32 == 0 the window word IS the
+// bitmap word (and holds everything the bitmap held: it was loaded from there), so a plain store does.
+__device__ __forceinline__ void tour_tile_store(uint32_t *visit_a, size_t n_ants, int n_words, int r, int tcx, int R, int C,
+                                                int TC, uint32_t v) {
+    if (v == 0u || r < 0 || r >= R || tcx < 0 || tcx >= TC) return;
+    const int f = r * C + (tcx << 5), w = f >> 5, sh = f & 31;
+    if ((C & 31) == 0) { visit_a[(size_t)w * n_ants] = v; return; }
+    atomicOr(visit_a + (size_t)w * n_ants, v << sh);
+    if (sh != 0 && w + 1 < n_words && (v >> (32 - sh)) != 0u) atomicOr(visit_a + (size_t)(w + 1) * n_ants, v >> (32 - sh));
+}
+
+// a load the compiler may not sink to its use (it would turn "select among three loaded entries" into "one load
+// from the selected address" and put the L2 latency back on the ant's serial chain)
+__device__ __forceinline__ uint2 ldg_pinned(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+// shared-memory loads by 32-bit shared address (kept in registers; the generic form re-derives the window base)
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// shared-memory tables of the thread-per-ant kernel (per block)
+struct Tour1Move {          // one per move (order MAACO.py:98)
+    int dcur;               // flat cell delta  dr*C + dc
+    int dprow;              // byte delta of the window row pointer  dr*8
+    int dc;                 // column delta
+    int pad;
+};
+#define T1_KTH_OFF 0                        // uint8  kth[256*8]   : index of the k-th set bit
+#define T1_SPREAD_OFF 2048                  // uint2  spread[256]  : byte m = 0xFF if bit m set
+#define T1_MOVE_OFF 4096                    // Tour1Move move[8]
+#define T1_DLEN_OFF (4096 + 128)            // double dlen[8]      : 1.0 or sqrt(2) (:293)
+#define T1_RNG_OFF (4096 + 256)             // per warp: double2 u[32] (512 B) + uint32 pack[32] (128 B)
+#define T1_WIN_OFF (T1_RNG_OFF + (MPP_TOUR1_THREADS / 32) * 640)
+
+__global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(const TourArgs A, const int apw) {
+    extern __shared__ __align__(16) uint8_t t1_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int R = A.R, C = A.C, TC = (C + 31) >> 5;
+    {   // ---- tables ----
+        uint8_t *const kth = t1_smem + T1_KTH_OFF;
+        uint2 *const spread = (uint2 *)(t1_smem + T1_SPREAD_OFF);
+        for (int p = threadIdx.x; p < 256; p += MPP_TOUR1_THREADS) {
+            int idx = 0;
+            uint32_t lo = 0, hi = 0;
+            for (int b = 0; b < 8; ++b)
+                if ((p >> b) & 1) {
+                    kth[p * 8 + idx++] = (uint8_t)b;
+                    if (b < 4) lo |= 0xFFu << (8 * b); else hi |= 0xFFu << (8 * (b - 4));
+                }
+            for (; idx < 8; ++idx) kth[p * 8 + idx] = 0;
+            spread[p] = make_uint2(lo, hi);
+        }
+        if (threadIdx.x < 8) {
+            const int m = threadIdx.x;
+            const int dr = (int)((0xA940u >> (2 * m)) & 3u) - 1, dc = (int)((0x9224u >> (2 * m)) & 3u) - 1;
+            Tour1Move mv;
+            mv.dcur = dr * C + dc; mv.dprow = dr * 8; mv.dc = dc; mv.pad = 0;
+            ((Tour1Move *)(t1_smem + T1_MOVE_OFF))[m] = mv;
+            ((double *)(t1_smem + T1_DLEN_OFF))[m] = (dr != 0 && dc != 0) ? MPP_SQRT2 : 1.0;
+        }
+    }
+    double2 *const rngu = (double2 *)(t1_smem + T1_RNG_OFF + wib * 640);
+    uint32_t *const rngp = (uint32_t *)(t1_smem + T1_RNG_OFF + wib * 640 + 512);
+    uint2 *const win_w = (uint2 *)(t1_smem + T1_WIN_OFF) + (size_t)wib * apw * 64;   // the warp's windows: 64 rows x uint2 each
+    for (int i = lane; i < apw * 64; i += 32) win_w[i] = make_uint2(0u, 0u);          // visitT is zero on entry, so is the window
+    __syncthreads();
+    const int warp = (blockIdx.x * MPP_TOUR1_THREADS + threadIdx.x) >> 5;
+    const int a0 = warp * apw;                                     // first ant of this warp
+    if (a0 >= A.n_ants) return;                                    // whole warp
+    const int a = a0 + lane;
+    bool active = lane < apw && a < A.n_ants;
+    const int n_words = (R * C + 31) >> 5;
+    const int target = A.target;
+    int cur = A.start;
+    auto orient_mask = [](int dR, int dC) -> uint32_t {           // MAACO.py:146-157
+        uint32_t k = 0xffu;
+        if (dC > 0) k &= ~0x29u;
+        if (dC < 0) k &= ~0x94u;
+        if (dR > 0) k &= ~0x07u;
+        if (dR < 0) k &= ~0xE0u;
+        return k;
+    };
+    const int tr = target / C, tc = target % C;
+    const uint32_t P1 = orient_mask(tr - cur / C, tc - cur % C);  // the same for every ant: start and target are the map's
+    // the ranking entry of the next cell is fetched before the move is chosen: one load per strategy-1 move (the
+    // first three of P1; P1 has 3 moves unless start and target share a row or column)
+    int sm0 = __ffs(P1) - 1, sm1 = __ffs(P1 & (P1 - 1)) - 1, sm2 = __ffs(P1 & (P1 - 1) & ((P1 & (P1 - 1)) - 1)) - 1;
+    if (sm1 < 0) sm1 = sm0;
+    if (sm2 < 0) sm2 = sm1;
+    auto spec_off = [C](int m) -> int {
+        const int dr = (int)((0xA940u >> (2 * m)) & 3u) - 1, dc = (int)((0x9224u >> (2 * m)) & 3u) - 1;
+        return (dr * C + dc) * 9 + m + 1;
+    };
+    const int so0 = spec_off(sm0), so1 = spec_off(sm1), so2 = spec_off(sm2), rank_last = 9 * R * C - 1;
+    const size_t n_ants = (size_t)A.n_ants;
+    int32_t *cell_out = A.cells + (size_t)(active ? a : a0) * A.max_cells;
+    const uint2 *const __restrict__ rank = (const uint2 *)A.rank;
+    int n_path = 1, prev_m = -1, turns = 0;
+    double len = 0.0;
+    const int max_path = 2 * R * C + 1;
+    bool failed = false;
+    // window = tile rows {wr, wr+1} x tile cols {wc, wc+1} (64 x 64 cells); row lrow of it is the uint2 at prow,
+    // bit lcol of that 64-bit row is the cell; the ant stays in [1, 62] x [1, 62]
+    int wr, wc, lrow, lcol;
+    {
+        const int cr = cur / C, cc = cur % C;
+        wr = (cr >> 5) - (((cr & 31) < 16) ? 1 : 0);
+        wc = (cc >> 5) - (((cc & 31) < 16) ? 1 : 0);
+        lrow = cr - (wr << 5);
+        lcol = cc - (wc << 5);
+    }
+    uint2 *prow = win_w + (size_t)(lane < apw ? lane : 0) * 64 + lrow;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(t1_smem);
+    const uint32_t rngp_s = (uint32_t)__cvta_generic_to_shared(rngp) + 4u * (uint32_t)lane;
+    uint2 rw = make_uint2(0u, 0u);                                // ranking entry: x = move at each rank (nibbles), y = mask/flags
+    if (active) {
+        atomicOr(&((uint32_t *)prow)[lcol >> 5], 1u << (lcol & 31));
+        *cell_out = cur;
+        rw = rank[(size_t)cur * 9];                               // context 0: no previous move
+        if (cur == target) active = false;
+    }
+    ++cell_out;
+    __syncwarp();
+    const uint32_t gmask = (uint32_t)(32 / apw) - 1u;              // a cooperative Philox pass covers 32/apw steps
+    for (uint32_t step = 0;; ++step) {
+        const uint32_t need0 = __ballot_sync(0xffffffffu, active && ((unsigned)(lrow - 1) > 61u || (unsigned)(lcol - 1) > 61u));
+        if (!__any_sync(0xffffffffu, active)) break;
+        if ((step & gmask) == 0 || need0) {
+            if ((step & gmask) == 0) {
+                // uniforms: draws 2s (q-test) and 2s+1 (selection) of stream (seed, TOUR, it, ant) = Philox block s;
+                // lane L makes the block of ant L % apw for step + L / apw.  Besides u0/u1 (for the full rule) the
+                // pass leaves what the ranking path needs: the greedy flag u0 <= q0 (:240) and floor(u1 * n) for
+                // every pool size n = 1..8 (random.choice on n items).
+                const int la = lane & (apw - 1);
+                const mpp_u4 rb = mpp_philox(step + (uint32_t)(lane / apw), (uint32_t)(A.ant_offset + a0 + la), A.it,
+                                             MPP_CLS_MAACO_TOUR, A.k0, A.k1);
+                const double u0 = mpp_u53(rb.x, rb.y), u1 = mpp_u53(rb.z, rb.w);
+                uint32_t pack = (u0 <= A.q0) ? (1u << 24) : 0u;
+#pragma unroll
+                for (int n = 2; n <= 8; ++n) {
+                    int k = (int)(u1 * (double)n);
+                    k = k < n ? k : n - 1;
+                    pack |= (uint32_t)k << (3 * (n - 1));
+                }
+                __syncwarp();
+                rngu[lane] = make_double2(u0, u1);
+                rngp[lane] = pack;
+                __syncwarp();
+            }
+            // ---- slide the windows whose ant reached their edge (at most every 31 steps per ant) ----
+            uint32_t need = need0;
+            while (need) {
+                const int src = __ffs(need) - 1;
+                const int s_lrow = __shfl_sync(0xffffffffu, lrow, src), s_lcol = __shfl_sync(0xffffffffu, lcol, src);
+                const int s_wr = __shfl_sync(0xffffffffu, wr, src), s_wc = __shfl_sync(0xffffffffu, wc, src);
+                uint32_t *const v_s = A.visitT + (a0 + src);
+                uint2 *const w_s = win_w + src * 64;
+                int d_wr = 0, d_wc = 0;
+                if ((unsigned)(s_lrow - 1) > 61u) {                // vertical: rows move by 32, one tile row leaves, one enters
+                    const bool up = s_lrow < 1;
+                    d_wr = up ? -1 : 1;
+                    const int r_out = ((up ? s_wr + 1 : s_wr) << 5) + lane, r_in = ((up ? s_wr - 1 : s_wr + 2) << 5) + lane;
+                    const uint2 keep = w_s[up ? lane : lane + 32], out = w_s[up ? lane + 32 : lane];
+                    tour_tile_store(v_s, n_ants, n_words, r_out, s_wc, R, C, TC, out.x);
+                    tour_tile_store(v_s, n_ants, n_words, r_out, s_wc + 1, R, C, TC, out.y);
+                    uint2 nw;
+                    nw.x = tour_tile_word(v_s, n_ants, n_words, r_in, s_wc, R, C, TC);
+                    nw.y = tour_tile_word(v_s, n_ants, n_words, r_in, s_wc + 1, R, C, TC);
+                    w_s[up ? lane + 32 : lane] = keep;
+                    w_s[up ? lane : lane + 32] = nw;
+                } else {                                           // horizontal: the two words of each row shift
+                    const bool left = s_lcol < 1;
+                    d_wc = left ? -1 : 1;
+                    const int t_out = left ? s_wc + 1 : s_wc, t_in = left ? s_wc - 1 : s_wc + 2;
+                    const int r = (s_wr << 5) + lane;
+                    const uint2 o0 = w_s[lane], o1 = w_s[lane + 32];
+                    tour_tile_store(v_s, n_ants, n_words, r, t_out, R, C, TC, left ? o0.y : o0.x);
+                    tour_tile_store(v_s, n_ants, n_words, r + 32, t_out, R, C, TC, left ? o1.y : o1.x);
+                    const uint32_t x0 = tour_tile_word(v_s, n_ants, n_words, r, t_in, R, C, TC);
+                    const uint32_t x1 = tour_tile_word(v_s, n_ants, n_words, r + 32, t_in, R, C, TC);
+                    w_s[lane] = left ? make_uint2(x0, o0.x) : make_uint2(o0.y, x0);
+                    w_s[lane + 32] = left ? make_uint2(x1, o1.x) : make_uint2(o1.y, x1);
+                }
+                if (lane == src) {
+                    wr += d_wr; wc += d_wc;
+                    lrow -= d_wr << 5; lcol -= d_wc << 5;
+                    prow -= d_wr << 5;
+                }
+                __syncwarp();
+                // a diagonal step can leave through a corner: this ant may still need the other direction
+                const bool again = (lane == src) && ((unsigned)(lrow - 1) > 61u || (unsigned)(lcol - 1) > 61u);
+                need = (need & (need - 1)) | __ballot_sync(0xffffffffu, again);
+            }
+        }
+        if (active) {
+            // ---- tabu bits of the 3x3 neighbourhood (:93-95): bits lcol-1..lcol+1 of window rows lrow-1..lrow+1 ----
+            const uint32_t prow_s = (uint32_t)__cvta_generic_to_shared(prow);
+            const uint2 q0r = lds_u2(prow_s - 8u), q1r = lds_u2(prow_s), q2r = lds_u2(prow_s + 8u);
+            const uint32_t pack = lds_u32(rngp_s + 4u * ((step & gmask) * (uint32_t)apw));
+            const int rot = lcol - 1;                                 // 0..61
+            const bool sw = rot & 32;
+            const uint32_t t3 = __funnelshift_r(sw ? q0r.y : q0r.x, q0r.y, rot) & 7u;
+            const uint32_t m3 = __funnelshift_r(sw ? q1r.y : q1r.x, q1r.y, rot) & 5u;
+            const uint32_t b3 = __funnelshift_r(sw ? q2r.y : q2r.x, q2r.y, rot) & 7u;
+            const uint32_t vis = t3 | ((m3 & 1u) << 3) | ((m3 & 4u) << 2) | (b3 << 5);
+            const uint32_t valid = (rw.y >> 24) & ~vis;               // static mask: bounds/obstacle/corner (:93-120)
+            // ---- next cell's ranking entries, one per strategy-1 move (L2 latency overlaps the selection) ----
+            // (indices clamped: a move that leaves the table is never valid, whatever is read for it is not used)
+            const int rk = cur * 9;
+            const uint2 s0 = ldg_pinned(rank + min(max(rk + so0, 0), rank_last)), s1 = ldg_pinned(rank + min(max(rk + so1, 0), rank_last)),
+                        s2 = ldg_pinned(rank + min(max(rk + so2, 0), rank_last));
+            uint32_t cand = valid & P1;                               // strategy 1 :165
+            if (cand == 0u) {
+                cand = valid & orient_mask(tr - cur / C, tc - cur % C);   // strategy 2 :169
+                if (!cand) cand = valid;                              // strategy 3 :172-180
+            }
+            if (cand == 0u) {                                         // :287-288
+                failed = true;
+                active = false;
+            } else {
+                int pick;
+                if ((rw.y & 0xFFFFFFu) != 0xFFFFFFu) {
+                    // every attractiveness around this cell is < 1e-10: greedy keeps the first arg-max and every
+                    // later candidate (all within 1e-9 of the max), the roulette is uniform (sum < 1e-9) :241-254.
+                    // first arg-max = best-ranked candidate: permute the candidate flags into rank order, take the first
+                    const uint2 sp = lds_u2(sbase + T1_SPREAD_OFF + 8u * cand);
+                    const uint32_t f0 = __byte_perm(sp.x, sp.y, rw.x & 0xFFFFu), f1 = __byte_perm(sp.x, sp.y, rw.x >> 16);
+                    const uint32_t ff = f0 ? f0 : f1;
+                    const int pos4 = ((__ffs(ff) - 1) >> 1) + (f0 ? 0 : 16);   // 4 * rank position of the first flag
+                    const uint32_t best = (rw.x >> pos4) & 7u;
+                    const uint32_t pool = (pack & (1u << 24)) ? (cand & ~((1u << best) - 1u)) : cand;
+                    const int n = __popc(pool);
+                    const int k = (pack >> (3 * n - 3)) & 7u;
+                    pick = (int)lds_u8(sbase + T1_KTH_OFF + pool * 8u + (uint32_t)k);
+                } else {
+                    const double2 uu = rngu[(step & gmask) * apw + lane];
+                    pick = tour_select_slow(cand, cur / C, cur % C, C, n_path >= 2, prev_m, A.tau, A.E01, A.alpha, A.q0, uu.x, uu.y);
+                }
+                // ---- advance :293-297 ----
+                const uint4 mvv = lds_u4(sbase + T1_MOVE_OFF + 16u * (uint32_t)pick);
+                Tour1Move mv;
+                mv.dcur = (int)mvv.x; mv.dprow = (int)mvv.y; mv.dc = (int)mvv.z;
+                cur += mv.dcur;
+                // (the current entry must only ever be copied from the prefetched ones: were it also the target of a
+                // load, its first use next step would wait on a scoreboard shared with that step's prefetches)
+                uint2 s0v = s0;
+                if (pick != sm0 && pick != sm1 && pick != sm2) s0v = ldg_pinned(rank + (size_t)cur * 9 + (pick + 1));   // strategy 2/3 move
+                rw = (pick == sm1) ? s1 : (pick == sm2) ? s2 : s0v;
+                prow = (uint2 *)((uint8_t *)prow + mv.dprow);
+                lrow += mv.dprow >> 3;
+                lcol += mv.dc;
+                atomicOr(&((uint32_t *)prow)[lcol >> 5], 1u << (lcol & 31));
+                if (n_path < A.max_cells) *cell_out = cur;
+                ++cell_out;
+                len += lds_f64(sbase + T1_DLEN_OFF + 8u * (uint32_t)pick);
+                if (n_path >= 2 && pick != prev_m) ++turns;           // :264-276 counted on the fly
+                prev_m = pick;
+                ++n_path;
+                if (cur == target || n_path >= max_path) active = false;
+            }
+        }
+    }
+    // ---- the windows still hold the marks of their four tiles: merge them into visitT ----
+    for (int src = 0; src < apw && a0 + src < A.n_ants; ++src) {
+        const int s_wr = __shfl_sync(0xffffffffu, wr, src), s_wc = __shfl_sync(0xffffffffu, wc, src);
+        uint32_t *const v_s = A.visitT + (a0 + src);
+        const uint2 o0 = win_w[src * 64 + lane], o1 = win_w[src * 64 + lane + 32];
+        const int r = (s_wr << 5) + lane;
+        tour_tile_store(v_s, n_ants, n_words, r, s_wc, R, C, TC, o0.x);
+        tour_tile_store(v_s, n_ants, n_words, r, s_wc + 1, R, C, TC, o0.y);
+        tour_tile_store(v_s, n_ants, n_words, r + 32, s_wc, R, C, TC, o1.x);
+        tour_tile_store(v_s, n_ants, n_words, r + 32, s_wc + 1, R, C, TC, o1.y);
+    }
+    if (lane < apw && a < A.n_ants) {
+        const bool ok = !failed && cur == target;
+        mpp_ant_result res;
+        res.length = ok ? len : __longlong_as_double(0x7ff0000000000000ll);
+        res.n_cells = ok ? n_path : 0;
+        res.turns = ok ? turns : -1;
+        A.result[a] = res;
+        if (A.steps) atomicAdd(A.steps, (unsigned long long)(n_path - 1));
+    }
+}
+
 extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E01_dev,
                                const uint32_t *rank_dev, int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
                                uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, mpp_ant_result *result_dev,
@@ -341,9 +740,12 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
     MPP_REQUIRE(map && tau_dev && E01_dev && visitT_dev && cells_dev && result_dev, "mpp_maaco_tours: null argument");
     MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_tours: map has no start/target");
     MPP_REQUIRE(n_ants > 0 && max_cells > 0, "mpp_maaco_tours: n_ants=%d max_cells=%d", n_ants, max_cells);
-    if (lanes_per_ant == 0) lanes_per_ant = 32;  // measured on B200: one warp per ant is fastest at every colony size tried (4k..32k ants)
-    MPP_REQUIRE(lanes_per_ant == 8 || lanes_per_ant == 16 || lanes_per_ant == 32,
-                "mpp_maaco_tours: lanes_per_ant must be 8, 16 or 32");
+    if (lanes_per_ant == 0) {
+        const char *e = getenv("MPP_TOUR_LPA");
+        lanes_per_ant = e ? atoi(e) : 32;
+    }  // measured on B200: one warp per ant is fastest at every colony size tried (4k..32k ants)
+    MPP_REQUIRE(lanes_per_ant == 1 || lanes_per_ant == 8 || lanes_per_ant == 16 || lanes_per_ant == 32,
+                "mpp_maaco_tours: lanes_per_ant must be 1, 8, 16 or 32");
     MPP_CUDA(cudaSetDevice(map->device));
     TourArgs A;
     A.svalid = map->svalid_dev;
@@ -355,6 +757,21 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
     A.k0 = (uint32_t)seed; A.k1 = (uint32_t)(seed >> 32);
     A.visitT = visitT_dev; A.cells = cells_dev; A.max_cells = max_cells;
     A.result = result_dev; A.steps = steps_dev;
+    if (lanes_per_ant == 1 && !rank_dev) lanes_per_ant = 32;      // the thread-per-ant kernel needs the ranking table
+    if (lanes_per_ant == 1) {
+        // ants per warp: enough warps for every SM sub-partition first, full warps only for big colonies
+        int apw = 32;
+        const char *e = getenv("MPP_TOUR_APW");
+        if (e) apw = atoi(e);
+        else while (apw > 4 && (n_ants + apw - 1) / apw < 4 * map->sm_count) apw >>= 1;
+        MPP_REQUIRE(apw == 1 || apw == 2 || apw == 4 || apw == 8 || apw == 16 || apw == 32, "MPP_TOUR_APW must be a power of two <= 32");
+        const int warps = (n_ants + apw - 1) / apw, wpb = MPP_TOUR1_THREADS / 32;
+        const size_t smem = T1_WIN_OFF + (size_t)wpb * apw * 512;
+        MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mpp_maaco_tour1_kernel<<<(warps + wpb - 1) / wpb, MPP_TOUR1_THREADS, smem, (cudaStream_t)stream>>>(A, apw);
+        MPP_CUDA(cudaGetLastError());
+        return MPP_OK;
+    }
     const int ants_per_block = MPP_TOUR_THREADS / lanes_per_ant;
     const int blocks = (n_ants + ants_per_block - 1) / ants_per_block;
     cudaStream_t s = (cudaStream_t)stream;
@@ -370,9 +787,10 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
 // With beta = 7 the values are ~1e-8..1e-20, so the selection rules (:241-262) only depend on their ORDER
 // (|attr_i - max| < 1e-9 and sum < 1e-9 always hold); the tour kernel then needs one 4-byte word per step
 // instead of 16 fp64 loads.  Context 0 = no previous move (turn flag 0 for every candidate, :185-186),
-// context p+1 = previous move p (turn flag = (m != p)).  Word: [31:24] static move mask, [23:0] rank position
-// of each move (0 = largest attractiveness, ties -> lower move index, exactly the order the sequential scan
-// sees), or 0xFFFFFF when some attractiveness is >= 1e-10 (the tour kernel then applies the full rule).
+// context p+1 = previous move p (turn flag = (m != p)).  Entry = two words.  Word 1: [31:24] static move mask,
+// [23:0] rank position of each move (0 = largest attractiveness, ties -> lower move index, exactly the order the
+// sequential scan sees), or 0xFFFFFF when some attractiveness is >= 1e-10 (the tour kernels then apply the full
+// rule).  Word 0: the inverse permutation, nibble p = move at rank position p (a PRMT selector).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mpp_maaco_rank_kernel(const uint8_t *__restrict__ svalid,
                                                              const double *__restrict__ tau,
@@ -396,7 +814,7 @@ __global__ void __launch_bounds__(256) mpp_maaco_rank_kernel(const uint8_t *__re
             mx = a[m] > mx ? a[m] : mx;
         }
     }
-    uint32_t word = 0xFFFFFFu;
+    uint32_t word = 0xFFFFFFu, perm = 0u;
     if (mx < 1e-10) {
         word = 0u;
 #pragma unroll
@@ -405,9 +823,10 @@ __global__ void __launch_bounds__(256) mpp_maaco_rank_kernel(const uint8_t *__re
 #pragma unroll
             for (int q = 0; q < 8; ++q) pos += (a[q] > a[m]) || (a[q] == a[m] && q < m);
             word |= (uint32_t)pos << (3 * m);
+            perm |= (uint32_t)m << (4 * pos);
         }
     }
-    rank[t] = word | (sv << 24);
+    ((uint2 *)rank)[t] = make_uint2(perm, word | (sv << 24));
 }
 
 extern "C" int mpp_maaco_rank(const mpp_map *map, const double *tau_dev, const double *E01_dev, double alpha,

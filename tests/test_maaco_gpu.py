@@ -26,7 +26,7 @@ def _check_pass(dev, orc, it, N, exact_tau=True, rtol=0.0):
 
 
 @pytest.mark.parametrize("name", MAACO_CASES)
-@pytest.mark.parametrize("lpa", [32, 16, 8])
+@pytest.mark.parametrize("lpa", [1, 32, 16, 8])
 def test_golden_trajectories(name, lpa):
     """CUDA vs the reference's own recorded trajectory (per-ant paths, tau after every pass)."""
     from maaco_path_planing_b200 import MAACO
@@ -55,7 +55,7 @@ def test_golden_trajectories(name, lpa):
                 np.testing.assert_allclose(dev.pheromone_matrix, g["tau"][0], rtol=1e-12)
 
 
-@pytest.mark.parametrize("lpa", [32, 16, 8])
+@pytest.mark.parametrize("lpa", [1, 32, 16, 8])
 def test_solve_matches_oracle_and_reference_api(lpa):
     from maaco_path_planing_b200 import MAACO
     import pyoracle as O
@@ -120,7 +120,7 @@ def test_lane_layouts_agree():
     from maaco_path_planing_b200 import MAACO, blocks_map
     g = blocks_map(128, 0.2, seed=31)
     outs = []
-    for lpa in (8, 16, 32):
+    for lpa in (1, 8, 16, 32):
         dev = MAACO(g, 300, 2, rng_seed=5, lanes_per_ant=lpa, verbose=False, **MAACO_DEFAULT)
         dev.run_iteration(1)
         dev.run_iteration(2)
