@@ -89,10 +89,12 @@ double mpp_maaco_q0(int num_iterations, int iteration, double q0_initial);
 
 /* ranks, per cell and previous-move context, the 8 moves by attractiveness tau**alpha * eta'**beta
  * (MAACO.py:235-239).  Where every value is < 1e-10 the selection rules (:241-262) depend only on that order
- * and the tour kernel uses the ranking; elsewhere the word says "evaluate".  Must be re-run after every
- * pheromone update.  rank_dev: 9*rows*cols entries of two uint32. */
+ * and the tour kernels use the ranking; elsewhere the entry says "evaluate".  Must be re-run after every
+ * pheromone update.  rank_dev: mpp_maaco_rank_words(map) uint32 (opaque: a per-(cell, context) word for the
+ * moves of the start->target quadrant, padded for unchecked neighbour reads, and a full two-word entry). */
 int mpp_maaco_rank(const mpp_map *map, const double *tau_dev, const double *E01_dev, double alpha, uint32_t *rank_dev,
                    void *stream);
+long long mpp_maaco_rank_words(const mpp_map *map);
 
 /* per-ant outcome of one tour (MAACO.py:300-302): failed ants have n_cells=0, length=+inf, turns=-1 */
 typedef struct {
@@ -105,7 +107,7 @@ typedef struct {
  * orientation filter + crossing-prohibition (:100-181) and pseudo-random-proportional selection
  * (:228-262).  Ant i of this call is global ant `ant_offset + i` (its RNG stream id).
  *   tau / E01      rows*cols / 2*rows*cols doubles (mpp_maaco_tables)
- *   rank_dev       optional 9*rows*cols two-word entries from mpp_maaco_rank for the CURRENT tau (NULL = evaluate the
+ *   rank_dev       optional mpp_maaco_rank_words(map) words from mpp_maaco_rank for the CURRENT tau (NULL = evaluate the
  *                  attractiveness of every candidate at every step)
  *   visitT_dev     word-major visited bitmaps: word w of ant i at [w*n_ants + i], ceil(rows*cols/32)
  *                  words per ant; MUST be zero on entry; holds each ant's visited set on return

@@ -51,6 +51,7 @@ _SIGS = {
     "mpp_map_occ_bits": (c_void_p, [c_void_p, C.POINTER(c_int)]),
     "mpp_maaco_tables": (c_int, [c_void_p, C.POINTER(MaacoParams), c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpp_maaco_q0": (c_double, [c_int, c_int, c_double]),
+    "mpp_maaco_rank_words": (C.c_longlong, [c_void_p]),
     "mpp_maaco_rank": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p]),
     "mpp_maaco_tours": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_int, c_int,
                                 c_u64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),

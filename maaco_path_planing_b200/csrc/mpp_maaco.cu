@@ -97,9 +97,39 @@ extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, d
 // ---------------------------------------------------------------------------------------------
 // K2: tour construction
 // ---------------------------------------------------------------------------------------------
+// Buffer layout (uint32 words): [margin | 9*R*C strategy-1 words | margin | pad to even] [9*R*C full entries (2 words)].
+// The margins let the tour kernel read the word of a neighbour cell without bounds checks.
+struct RankLayout { size_t margin, fast_words, total_words; };
+static RankLayout rank_layout(int R, int C) {
+    RankLayout L;
+    L.margin = (size_t)(C + 2) * 9;
+    L.fast_words = ((size_t)9 * R * C + 2 * L.margin + 1) & ~(size_t)1;
+    L.total_words = L.fast_words + (size_t)18 * R * C;
+    return L;
+}
+static uint32_t host_orient_mask(int dR, int dC) {                // MAACO.py:146-157
+    uint32_t k = 0xffu;
+    if (dC > 0) k &= ~0x29u;
+    if (dC < 0) k &= ~0x94u;
+    if (dR > 0) k &= ~0x07u;
+    if (dR < 0) k &= ~0xE0u;
+    return k;
+}
+
+struct TourS1 {              // strategy-1 constants (P1 = orientation start -> target, MAACO.py:146-165)
+    uint32_t P1;
+    int fast_ok;            // P1 has exactly three moves
+    int sm[3];              // those moves
+    int dpr[3], dc[3];      // window row pointer delta (bytes) and column delta of each
+    int so[3];              // ranking-word offset of (neighbour cell, context move+1)
+};
+
 struct TourArgs {
+    TourS1 s1;
     const uint8_t *svalid;  // per-cell static move mask (MAACO move order)
-    const uint32_t *rank;   // per (cell, turn context) move ranking (mpp_maaco_rank) or null
+    const uint32_t *rank;   // ranking buffer (mpp_maaco_rank) or null; layout: rank_layout()
+    const uint32_t *rank_fast;   // word (cell*9 + ctx) of the strategy-1 table (margins on both sides)
+    const uint2 *rank_slow;      // entry (cell*9 + ctx) of the full ranking
     int R, C, start, target;
     const double *tau, *E01;
     uint32_t it;
@@ -233,7 +263,7 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
         // ranking word (mpp_maaco_rank): [31:24] static move mask, [23:0] rank position of each move by
         // attractiveness (3 bits/move) for this (cell, previous move); 0xFFFFFF = "not small, use the full rule"
         const uint32_t ctx = (n_path >= 2) ? (uint32_t)(prev_m + 1) : 0u;
-        const uint32_t rw = rank ? rank[2 * ((size_t)cur * 9 + ctx) + 1] : (((uint32_t)svalid[cur] << 24) | 0xFFFFFFu);
+        const uint32_t rw = rank ? A.rank_slow[(size_t)cur * 9 + ctx].y : (((uint32_t)svalid[cur] << 24) | 0xFFFFFFu);
         const uint32_t sv = rw >> 24;                                 // bounds / obstacle / corner-cut (:93-120)
         int j = cur + delta;
         j = j < 0 ? 0 : (j >= RC ? RC - 1 : j);                       // clamp: lanes outside the mask are ignored
@@ -437,9 +467,9 @@ __device__ __forceinline__ void tour_tile_store(uint32_t *visit_a, size_t n_ants
 
 // a load the compiler may not sink to its use (it would turn "select among three loaded entries" into "one load
 // from the selected address" and put the L2 latency back on the ant's serial chain)
-__device__ __forceinline__ uint2 ldg_pinned(const uint2 *p) {
-    uint2 v;
-    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+__device__ __forceinline__ uint32_t ldg32_pinned(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 // shared-memory loads by 32-bit shared address (kept in registers; the generic form re-derives the window base)
@@ -480,8 +510,18 @@ struct Tour1Move {          // one per move (order MAACO.py:98)
 #define T1_SPREAD_OFF 2048                  // uint2  spread[256]  : byte m = 0xFF if bit m set
 #define T1_MOVE_OFF 4096                    // Tour1Move move[8]
 #define T1_DLEN_OFF (4096 + 128)            // double dlen[8]      : 1.0 or sqrt(2) (:293)
-#define T1_RNG_OFF (4096 + 256)             // per warp: double2 u[32] (512 B) + uint32 pack[32] (128 B)
+#define T1_FAST_OFF (4096 + 256)            // uint4 fast[4*8]     : (k, subset) -> {dcur, dprow, dc, which | move << 8}
+#define T1_RNG_OFF (4096 + 256 + 512)       // per warp: double2 u[32] (512 B) + uint32 pack[32] (128 B)
 #define T1_WIN_OFF (T1_RNG_OFF + (MPP_TOUR1_THREADS / 32) * 640)
+
+__device__ __forceinline__ uint32_t t1_orient_mask(int dR, int dC) {   // MAACO.py:146-157
+    uint32_t k = 0xffu;
+    if (dC > 0) k &= ~0x29u;
+    if (dC < 0) k &= ~0x94u;
+    if (dR > 0) k &= ~0x07u;
+    if (dR < 0) k &= ~0xE0u;
+    return k;
+}
 
 __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(const TourArgs A, const int apw) {
     extern __shared__ __align__(16) uint8_t t1_smem[];
@@ -509,6 +549,21 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
             ((Tour1Move *)(t1_smem + T1_MOVE_OFF))[m] = mv;
             ((double *)(t1_smem + T1_DLEN_OFF))[m] = (dr != 0 && dc != 0) ? MPP_SQRT2 : 1.0;
         }
+        if (threadIdx.x < 32) {                                    // (k, subset of P1's three moves) -> k-th member
+            const int k = threadIdx.x >> 3, p3 = threadIdx.x & 7;
+            const uint32_t P1t = A.s1.P1;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (__popc(P1t) == 3) {
+                const int s[3] = {__ffs(P1t) - 1, __ffs(P1t & (P1t - 1)) - 1, 31 - __clz(P1t)};
+                int seen = 0, which = 2;
+                for (int i = 0; i < 3; ++i)
+                    if ((p3 >> i) & 1) { if (seen == k) { which = i; break; } ++seen; }
+                const int mm = s[which];
+                const int dr = (int)((0xA940u >> (2 * mm)) & 3u) - 1, dc = (int)((0x9224u >> (2 * mm)) & 3u) - 1;
+                v = make_uint4((uint32_t)(dr * C + dc), (uint32_t)(dr * 8), (uint32_t)dc, (uint32_t)which | ((uint32_t)mm << 8));
+            }
+            ((uint4 *)(t1_smem + T1_FAST_OFF))[threadIdx.x] = v;
+        }
     }
     double2 *const rngu = (double2 *)(t1_smem + T1_RNG_OFF + wib * 640);
     uint32_t *const rngp = (uint32_t *)(t1_smem + T1_RNG_OFF + wib * 640 + 512);
@@ -532,20 +587,24 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
         return k;
     };
     const int tr = target / C, tc = target % C;
-    const uint32_t P1 = orient_mask(tr - cur / C, tc - cur % C);  // the same for every ant: start and target are the map's
+    const uint32_t P1 = A.s1.P1;                                  // the same for every ant: start and target are the map's
     // the ranking entry of the next cell is fetched before the move is chosen: one load per strategy-1 move (the
     // first three of P1; P1 has 3 moves unless start and target share a row or column)
-    int sm0 = __ffs(P1) - 1, sm1 = __ffs(P1 & (P1 - 1)) - 1, sm2 = __ffs(P1 & (P1 - 1) & ((P1 & (P1 - 1)) - 1)) - 1;
-    if (sm1 < 0) sm1 = sm0;
-    if (sm2 < 0) sm2 = sm1;
-    auto spec_off = [C](int m) -> int {
-        const int dr = (int)((0xA940u >> (2 * m)) & 3u) - 1, dc = (int)((0x9224u >> (2 * m)) & 3u) - 1;
-        return (dr * C + dc) * 9 + m + 1;
-    };
-    const int so0 = spec_off(sm0), so1 = spec_off(sm1), so2 = spec_off(sm2), rank_last = 9 * R * C - 1;
+    // strategy 1 usually leaves three moves (a quadrant); then each step works on those three only
+    const bool fast_ok = A.s1.fast_ok;
+    const int sm0 = A.s1.sm[0], sm1 = A.s1.sm[1], sm2 = A.s1.sm[2];
+    const int dpr0 = A.s1.dpr[0], dpr1 = A.s1.dpr[1], dpr2 = A.s1.dpr[2];
+    const int dc0 = A.s1.dc[0], dc1 = A.s1.dc[1], dc2 = A.s1.dc[2];
+    const int so0 = A.s1.so[0], so1 = A.s1.so[1], so2 = A.s1.so[2];
+    // (kept in registers: re-reading kernel parameters inside the step costs a constant-bank round trip each time)
+#define T1_KEEP(x) asm volatile("" : "+r"(x))
+    int k_sm0 = sm0, k_sm1 = sm1, k_sm2 = sm2, k_dpr0 = dpr0, k_dpr1 = dpr1, k_dpr2 = dpr2;
+    int k_dc0 = dc0, k_dc1 = dc1, k_dc2 = dc2, k_so0 = so0, k_so1 = so1, k_so2 = so2;
+    T1_KEEP(k_sm0); T1_KEEP(k_sm1); T1_KEEP(k_sm2); T1_KEEP(k_dpr0); T1_KEEP(k_dpr1); T1_KEEP(k_dpr2);
+    T1_KEEP(k_dc0); T1_KEEP(k_dc1); T1_KEEP(k_dc2); T1_KEEP(k_so0); T1_KEEP(k_so1); T1_KEEP(k_so2);
     const size_t n_ants = (size_t)A.n_ants;
-    int32_t *cell_out = A.cells + (size_t)(active ? a : a0) * A.max_cells;
-    const uint2 *const __restrict__ rank = (const uint2 *)A.rank;
+    int32_t *const cells_a = A.cells + (size_t)(active ? a : a0) * A.max_cells;
+    const uint32_t *const __restrict__ rank_fast = A.rank_fast;
     int n_path = 1, prev_m = -1, turns = 0;
     double len = 0.0;
     const int max_path = 2 * R * C + 1;
@@ -560,17 +619,26 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
         lrow = cr - (wr << 5);
         lcol = cc - (wc << 5);
     }
-    uint2 *prow = win_w + (size_t)(lane < apw ? lane : 0) * 64 + lrow;
+    uint32_t prow_s = (uint32_t)__cvta_generic_to_shared(win_w + (size_t)(lane < apw ? lane : 0) * 64 + lrow);   // the ant's window row
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(t1_smem);
-    const uint32_t rngp_s = (uint32_t)__cvta_generic_to_shared(rngp) + 4u * (uint32_t)lane;
-    uint2 rw = make_uint2(0u, 0u);                                // ranking entry: x = move at each rank (nibbles), y = mask/flags
+    uint32_t rngp_s = (uint32_t)__cvta_generic_to_shared(rngp) + 4u * (uint32_t)lane;
+    uint32_t sbase_k = sbase;                                    // (opaque copies: otherwise re-derived from %cluster_ctaid every use)
+    asm volatile("" : "+r"(rngp_s));
+    asm volatile("" : "+r"(sbase_k));
+    uint32_t fw = 0u;                                             // strategy-1 word of (cell, previous move)
+    uint32_t pf0 = 0u, pf1 = 0u, pf2 = 0u;                        // ... of the three strategy-1 neighbours, prefetched
     if (active) {
-        atomicOr(&((uint32_t *)prow)[lcol >> 5], 1u << (lcol & 31));
-        *cell_out = cur;
-        rw = rank[(size_t)cur * 9];                               // context 0: no previous move
-        if (cur == target) active = false;
+        asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(prow_s + 4u * ((uint32_t)lcol >> 5)), "r"(1u << (lcol & 31)) : "memory");
+        cells_a[0] = cur;
+        fw = rank_fast[(size_t)cur * 9];                          // context 0: no previous move
+        // (read it here: a first use inside the loop would make every step wait on this load's scoreboard, which the
+        // loop's own prefetches share.)  Field 0 is 0 or 7, so the test is never true.
+        if (cur == target || (fw & 7u) == 3u) active = false;
+        if (fast_ok) {
+            const uint32_t *const rk = rank_fast + (size_t)cur * 9;
+            pf0 = ldg32_pinned(rk + so0); pf1 = ldg32_pinned(rk + so1); pf2 = ldg32_pinned(rk + so2);
+        }
     }
-    ++cell_out;
     __syncwarp();
     const uint32_t gmask = (uint32_t)(32 / apw) - 1u;              // a cooperative Philox pass covers 32/apw steps
     for (uint32_t step = 0;; ++step) {
@@ -635,7 +703,7 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                 if (lane == src) {
                     wr += d_wr; wc += d_wc;
                     lrow -= d_wr << 5; lcol -= d_wc << 5;
-                    prow -= d_wr << 5;
+                    prow_s -= (uint32_t)(d_wr * 256);
                 }
                 __syncwarp();
                 // a diagonal step can leave through a corner: this ant may still need the other direction
@@ -644,68 +712,99 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
             }
         }
         if (active) {
-            // ---- tabu bits of the 3x3 neighbourhood (:93-95): bits lcol-1..lcol+1 of window rows lrow-1..lrow+1 ----
-            const uint32_t prow_s = (uint32_t)__cvta_generic_to_shared(prow);
-            const uint2 q0r = lds_u2(prow_s - 8u), q1r = lds_u2(prow_s), q2r = lds_u2(prow_s + 8u);
+            int m = -1, dcur = 0, dpr = 0, dcc = 0;                   // the move taken this step and its deltas
+            uint32_t pi = 0u;                                         // which prefetched word applies next step
             const uint32_t pack = lds_u32(rngp_s + 4u * ((step & gmask) * (uint32_t)apw));
-            const int rot = lcol - 1;                                 // 0..61
-            const bool sw = rot & 32;
-            const uint32_t t3 = __funnelshift_r(sw ? q0r.y : q0r.x, q0r.y, rot) & 7u;
-            const uint32_t m3 = __funnelshift_r(sw ? q1r.y : q1r.x, q1r.y, rot) & 5u;
-            const uint32_t b3 = __funnelshift_r(sw ? q2r.y : q2r.x, q2r.y, rot) & 7u;
-            const uint32_t vis = t3 | ((m3 & 1u) << 3) | ((m3 & 4u) << 2) | (b3 << 5);
-            const uint32_t valid = (rw.y >> 24) & ~vis;               // static mask: bounds/obstacle/corner (:93-120)
-            // ---- next cell's ranking entries, one per strategy-1 move (L2 latency overlaps the selection) ----
-            // (indices clamped: a move that leaves the table is never valid, whatever is read for it is not used)
-            const int rk = cur * 9;
-            const uint2 s0 = ldg_pinned(rank + min(max(rk + so0, 0), rank_last)), s1 = ldg_pinned(rank + min(max(rk + so1, 0), rank_last)),
-                        s2 = ldg_pinned(rank + min(max(rk + so2, 0), rank_last));
-            uint32_t cand = valid & P1;                               // strategy 1 :165
-            if (cand == 0u) {
-                cand = valid & orient_mask(tr - cur / C, tc - cur % C);   // strategy 2 :169
-                if (!cand) cand = valid;                              // strategy 3 :172-180
-            }
-            if (cand == 0u) {                                         // :287-288
-                failed = true;
-                active = false;
-            } else {
-                int pick;
-                if ((rw.y & 0xFFFFFFu) != 0xFFFFFFu) {
-                    // every attractiveness around this cell is < 1e-10: greedy keeps the first arg-max and every
-                    // later candidate (all within 1e-9 of the max), the roulette is uniform (sum < 1e-9) :241-254.
-                    // first arg-max = best-ranked candidate: permute the candidate flags into rank order, take the first
-                    const uint2 sp = lds_u2(sbase + T1_SPREAD_OFF + 8u * cand);
-                    const uint32_t f0 = __byte_perm(sp.x, sp.y, rw.x & 0xFFFFu), f1 = __byte_perm(sp.x, sp.y, rw.x >> 16);
-                    const uint32_t ff = f0 ? f0 : f1;
-                    const int pos4 = ((__ffs(ff) - 1) >> 1) + (f0 ? 0 : 16);   // 4 * rank position of the first flag
-                    const uint32_t best = (rw.x >> pos4) & 7u;
-                    const uint32_t pool = (pack & (1u << 24)) ? (cand & ~((1u << best) - 1u)) : cand;
-                    const int n = __popc(pool);
-                    const int k = (pack >> (3 * n - 3)) & 7u;
-                    pick = (int)lds_u8(sbase + T1_KTH_OFF + pool * 8u + (uint32_t)k);
-                } else {
-                    const double2 uu = rngu[(step & gmask) * apw + lane];
-                    pick = tour_select_slow(cand, cur / C, cur % C, C, n_path >= 2, prev_m, A.tau, A.E01, A.alpha, A.q0, uu.x, uu.y);
+            if (fast_ok) {
+                // ---- strategy 1 (:165) on the three moves of P1 only ----
+                const uint2 ra = lds_u2(prow_s + k_dpr0), rb = lds_u2(prow_s + k_dpr1), rc = lds_u2(prow_s + k_dpr2);
+                const int c0 = lcol + k_dc0, c1 = lcol + k_dc1, c2 = lcol + k_dc2;           // 0..63
+                const uint32_t v0 = ((c0 & 32) ? ra.y : ra.x) >> (c0 & 31);            // tabu bit (:93-95) in bit 0
+                const uint32_t v1 = ((c1 & 32) ? rb.y : rb.x) >> (c1 & 31);
+                const uint32_t v2 = ((c2 & 32) ? rc.y : rc.x) >> (c2 & 31);
+                const uint32_t sv = fw >> 24;                                          // static mask (:93-120)
+                const uint32_t c3 = (((sv >> k_sm0) & ~v0) & 1u) | ((((sv >> k_sm1) & ~v1) & 1u) << 1) |
+                                    ((((sv >> k_sm2) & ~v2) & 1u) << 2);                 // candidate subset of {k_sm0, k_sm1, k_sm2}
+                if (c3 != 0u && (fw & 7u) == 0u) {
+                    // greedy (:241-250): field c3 of the word = first arg-max + every later candidate, precomputed;
+                    // roulette (:251-254): all candidates.  Then random.choice: the floor(u1*n)-th member.
+                    const uint32_t p3 = (pack & (1u << 24)) ? ((fw >> (3u * c3)) & 7u) : c3;
+                    const uint32_t sh = (0x63303000u >> (4u * p3)) & 15u;              // 3 * (popc(p3) - 1)
+                    const uint32_t k = (pack >> sh) & 7u;
+                    // k-th member of subset p3 and everything that follows from the move: one table row
+                    const uint4 fv = lds_u4(sbase_k + T1_FAST_OFF + 16u * ((k << 3) | p3));
+                    dcur = (int)fv.x; dpr = (int)fv.y; dcc = (int)fv.z;
+                    pi = fv.w & 3u;
+                    m = (int)(fv.w >> 8);
                 }
+            }
+            if (m < 0) {
+                // ---- general step: all eight moves, strategies 1-3, full ranking entry or the literal rules ----
+                const uint2 rws = A.rank_slow[(size_t)cur * 9 + (n_path >= 2 ? prev_m + 1 : 0)];
+                const uint2 q0r = lds_u2(prow_s - 8u), q1r = lds_u2(prow_s), q2r = lds_u2(prow_s + 8u);
+                const int rot = lcol - 1;                             // 0..61
+                const bool sw = rot & 32;
+                const uint32_t t3 = __funnelshift_r(sw ? q0r.y : q0r.x, q0r.y, rot) & 7u;
+                const uint32_t m3 = __funnelshift_r(sw ? q1r.y : q1r.x, q1r.y, rot) & 5u;
+                const uint32_t b3 = __funnelshift_r(sw ? q2r.y : q2r.x, q2r.y, rot) & 7u;
+                const uint32_t vis = t3 | ((m3 & 1u) << 3) | ((m3 & 4u) << 2) | (b3 << 5);
+                const uint32_t valid = (rws.y >> 24) & ~vis;
+                uint32_t cand = valid & P1;                           // strategy 1 :165
+                if (cand == 0u) {
+                    cand = valid & orient_mask(tr - cur / C, tc - cur % C);   // strategy 2 :169
+                    if (!cand) cand = valid;                          // strategy 3 :172-180
+                }
+                if (cand == 0u) {                                     // :287-288
+                    failed = true;
+                    active = false;
+                } else {
+                    if ((rws.y & 0xFFFFFFu) != 0xFFFFFFu) {
+                        // first arg-max = best-ranked candidate: permute the candidate flags into rank order
+                        const uint2 sp = lds_u2(sbase_k + T1_SPREAD_OFF + 8u * cand);
+                        const uint32_t f0 = __byte_perm(sp.x, sp.y, rws.x & 0xFFFFu), f1 = __byte_perm(sp.x, sp.y, rws.x >> 16);
+                        const uint32_t ff = f0 ? f0 : f1;
+                        const int pos4 = ((__ffs(ff) - 1) >> 1) + (f0 ? 0 : 16);
+                        const uint32_t best = (rws.x >> pos4) & 7u;
+                        const uint32_t pool = (pack & (1u << 24)) ? (cand & ~((1u << best) - 1u)) : cand;
+                        const int n = __popc(pool);
+                        const int k = (pack >> (3 * n - 3)) & 7u;
+                        m = (int)lds_u8(sbase_k + T1_KTH_OFF + pool * 8u + (uint32_t)k);
+                    } else {
+                        const double2 uu = rngu[(step & gmask) * apw + lane];
+                        m = tour_select_slow(cand, cur / C, cur % C, C, n_path >= 2, prev_m, A.tau, A.E01, A.alpha, A.q0, uu.x, uu.y);
+                    }
+                    const uint4 mvv = lds_u4(sbase_k + T1_MOVE_OFF + 16u * (uint32_t)m);
+                    dcur = (int)mvv.x; dpr = (int)mvv.y; dcc = (int)mvv.z;
+                    // (loaded into a prefetch register, never straight into fw: see the note at the first load)
+                    pf0 = ldg32_pinned(rank_fast + (size_t)(cur + dcur) * 9 + (m + 1));
+                    pi = 0u;
+                }
+            }
+            if (active) {
                 // ---- advance :293-297 ----
-                const uint4 mvv = lds_u4(sbase + T1_MOVE_OFF + 16u * (uint32_t)pick);
-                Tour1Move mv;
-                mv.dcur = (int)mvv.x; mv.dprow = (int)mvv.y; mv.dc = (int)mvv.z;
-                cur += mv.dcur;
-                // (the current entry must only ever be copied from the prefetched ones: were it also the target of a
-                // load, its first use next step would wait on a scoreboard shared with that step's prefetches)
-                uint2 s0v = s0;
-                if (pick != sm0 && pick != sm1 && pick != sm2) s0v = ldg_pinned(rank + (size_t)cur * 9 + (pick + 1));   // strategy 2/3 move
-                rw = (pick == sm1) ? s1 : (pick == sm2) ? s2 : s0v;
-                prow = (uint2 *)((uint8_t *)prow + mv.dprow);
-                lrow += mv.dprow >> 3;
-                lcol += mv.dc;
-                atomicOr(&((uint32_t *)prow)[lcol >> 5], 1u << (lcol & 31));
-                if (n_path < A.max_cells) *cell_out = cur;
-                ++cell_out;
-                len += lds_f64(sbase + T1_DLEN_OFF + 8u * (uint32_t)pick);
-                if (n_path >= 2 && pick != prev_m) ++turns;           // :264-276 counted on the fly
-                prev_m = pick;
+                cur += dcur;
+                // bitwise select on `pi`, opaque to the compiler: as a ternary the default operand is copied early,
+                // and that copy waits for the prefetches a whole selection too soon
+                {
+                    const uint32_t m1 = 0u - (pi & 1u), m2 = 0u - (pi >> 1);
+                    uint32_t t;
+                    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(t) : "r"(pf0), "r"(pf1), "r"(m1));
+                    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(fw) : "r"(t), "r"(pf2), "r"(m2));
+                }
+                if (fast_ok) {
+                    // the word of each strategy-1 neighbour of the NEW cell, for the end of the next step (the table has
+                    // margins: every index is readable); a whole step of work hides the L2 latency
+                    const uint32_t *const rk = rank_fast + (size_t)cur * 9;
+                    pf0 = ldg32_pinned(rk + k_so0); pf1 = ldg32_pinned(rk + k_so1); pf2 = ldg32_pinned(rk + k_so2);
+                }
+                prow_s += (uint32_t)dpr;
+                lrow += dpr >> 3;
+                lcol += dcc;
+                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(prow_s + 4u * ((uint32_t)lcol >> 5)), "r"(1u << (lcol & 31)) : "memory");
+                if (n_path < A.max_cells) cells_a[n_path] = cur;
+                len += lds_f64(sbase_k + T1_DLEN_OFF + 8u * (uint32_t)m);
+                if (n_path >= 2 && m != prev_m) ++turns;              // :264-276 counted on the fly
+                prev_m = m;
                 ++n_path;
                 if (cur == target || n_path >= max_path) active = false;
             }
@@ -742,14 +841,31 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
     MPP_REQUIRE(n_ants > 0 && max_cells > 0, "mpp_maaco_tours: n_ants=%d max_cells=%d", n_ants, max_cells);
     if (lanes_per_ant == 0) {
         const char *e = getenv("MPP_TOUR_LPA");
-        lanes_per_ant = e ? atoi(e) : 32;
-    }  // measured on B200: one warp per ant is fastest at every colony size tried (4k..32k ants)
+        lanes_per_ant = e ? atoi(e) : 1;   // measured on B200: thread-per-ant beats the cooperative forms from 256 to 16k ants
+    }
     MPP_REQUIRE(lanes_per_ant == 1 || lanes_per_ant == 8 || lanes_per_ant == 16 || lanes_per_ant == 32,
                 "mpp_maaco_tours: lanes_per_ant must be 1, 8, 16 or 32");
     MPP_CUDA(cudaSetDevice(map->device));
     TourArgs A;
     A.svalid = map->svalid_dev;
     A.rank = rank_dev;
+    {
+        TourS1 &S = A.s1;
+        S.P1 = host_orient_mask(map->target / map->cols - map->start / map->cols, map->target % map->cols - map->start % map->cols);
+        S.fast_ok = __builtin_popcount(S.P1) == 3;
+        uint32_t rest = S.P1;
+        for (int i = 0; i < 3; ++i) {
+            const int m = S.fast_ok ? __builtin_ctz(rest) : __builtin_ctz(S.P1);
+            rest &= rest - 1;
+            const int dr = (int)((0xA940u >> (2 * m)) & 3u) - 1, dc = (int)((0x9224u >> (2 * m)) & 3u) - 1;
+            S.sm[i] = m; S.dpr[i] = dr * 8; S.dc[i] = dc; S.so[i] = (dr * map->cols + dc) * 9 + m + 1;
+        }
+    }
+    {
+        const RankLayout L = rank_layout(map->rows, map->cols);
+        A.rank_fast = rank_dev ? rank_dev + L.margin : nullptr;
+        A.rank_slow = rank_dev ? (const uint2 *)(rank_dev + L.fast_words) : nullptr;
+    }
     A.R = map->rows; A.C = map->cols; A.start = map->start; A.target = map->target;
     A.tau = tau_dev; A.E01 = E01_dev;
     A.it = (uint32_t)iteration; A.q0 = q0; A.alpha = alpha;
@@ -763,10 +879,10 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
         int apw = 32;
         const char *e = getenv("MPP_TOUR_APW");
         if (e) apw = atoi(e);
-        else while (apw > 4 && (n_ants + apw - 1) / apw < 4 * map->sm_count) apw >>= 1;
+        else while (apw > 2 && (n_ants + apw - 1) / apw < 12 * map->sm_count) apw >>= 1;   // measured: 2 ants/warp at 4096 ants
         MPP_REQUIRE(apw == 1 || apw == 2 || apw == 4 || apw == 8 || apw == 16 || apw == 32, "MPP_TOUR_APW must be a power of two <= 32");
         const int warps = (n_ants + apw - 1) / apw, wpb = MPP_TOUR1_THREADS / 32;
-        const size_t smem = T1_WIN_OFF + (size_t)wpb * apw * 512;
+        const size_t smem = T1_WIN_OFF + (size_t)wpb * apw * 512;   // tables + per-warp RNG + 512-byte windows
         MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mpp_maaco_tour1_kernel<<<(warps + wpb - 1) / wpb, MPP_TOUR1_THREADS, smem, (cudaStream_t)stream>>>(A, apw);
         MPP_CUDA(cudaGetLastError());
@@ -792,10 +908,20 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
 // sequential scan sees), or 0xFFFFFF when some attractiveness is >= 1e-10 (the tour kernels then apply the full
 // rule).  Word 0: the inverse permutation, nibble p = move at rank position p (a PRMT selector).
 // ---------------------------------------------------------------------------------------------
+
+extern "C" long long mpp_maaco_rank_words(const mpp_map *map) {
+    if (!map) return 0;
+    return (long long)rank_layout(map->rows, map->cols).total_words;
+}
+
+// Strategy-1 word (one per (cell, context)): [31:24] static move mask; field c (3 bits at 3c, c = 1..7 = a subset of
+// P1's three moves in move order) = what greedy selection (:241-250) keeps of candidate set c, as a subset again;
+// field 0 = 0 when the ranking applies (all attractiveness < 1e-10), 7 when it does not (or P1 has not three moves).
 __global__ void __launch_bounds__(256) mpp_maaco_rank_kernel(const uint8_t *__restrict__ svalid,
                                                              const double *__restrict__ tau,
                                                              const double *__restrict__ E01, double alpha, int R, int C,
-                                                             uint32_t *__restrict__ rank) {
+                                                             uint32_t P1, uint32_t *__restrict__ rank_fast,
+                                                             uint2 *__restrict__ rank_slow) {
     const int t = blockIdx.x * 256 + threadIdx.x;
     if (t >= R * C * 9) return;
     const int cell = t / 9, ctx = t - cell * 9;
@@ -814,7 +940,7 @@ __global__ void __launch_bounds__(256) mpp_maaco_rank_kernel(const uint8_t *__re
             mx = a[m] > mx ? a[m] : mx;
         }
     }
-    uint32_t word = 0xFFFFFFu, perm = 0u;
+    uint32_t word = 0xFFFFFFu, perm = 0u, fast = 7u;
     if (mx < 1e-10) {
         word = 0u;
 #pragma unroll
@@ -825,17 +951,37 @@ __global__ void __launch_bounds__(256) mpp_maaco_rank_kernel(const uint8_t *__re
             word |= (uint32_t)pos << (3 * m);
             perm |= (uint32_t)m << (4 * pos);
         }
+        if (__popc(P1) == 3) {
+            const int s0 = __ffs(P1) - 1, s1 = __ffs(P1 & (P1 - 1)) - 1, s2 = 31 - __clz(P1);
+            const uint32_t p0 = (word >> (3 * s0)) & 7u, p1 = (word >> (3 * s1)) & 7u, p2 = (word >> (3 * s2)) & 7u;
+            fast = 0u;
+#pragma unroll
+            for (uint32_t c = 1; c < 8; ++c) {
+                // best-ranked member of subset c (rank positions are distinct)
+                uint32_t bp = 8u, bi = 0u;
+                if ((c & 1u) && p0 < bp) { bp = p0; bi = 0u; }
+                if ((c & 2u) && p1 < bp) { bp = p1; bi = 1u; }
+                if ((c & 4u) && p2 < bp) { bp = p2; bi = 2u; }
+                fast |= (c & ~((1u << bi) - 1u)) << (3u * c);     // the best one and every later member
+            }
+        }
     }
-    ((uint2 *)rank)[t] = make_uint2(perm, word | (sv << 24));
+    rank_fast[t] = fast | (sv << 24);
+    rank_slow[t] = make_uint2(perm, word | (sv << 24));
 }
 
 extern "C" int mpp_maaco_rank(const mpp_map *map, const double *tau_dev, const double *E01_dev, double alpha,
                               uint32_t *rank_dev, void *stream) {
     MPP_REQUIRE(map && tau_dev && E01_dev && rank_dev, "mpp_maaco_rank: null argument");
+    MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_rank: map has no start/target");
     MPP_CUDA(cudaSetDevice(map->device));
     const int total = map->rows * map->cols * 9;
-    mpp_maaco_rank_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(map->svalid_dev, tau_dev, E01_dev, alpha,
-                                                                              map->rows, map->cols, rank_dev);
+    const RankLayout L = rank_layout(map->rows, map->cols);
+    const uint32_t P1 = host_orient_mask(map->target / map->cols - map->start / map->cols,
+                                         map->target % map->cols - map->start % map->cols);
+    mpp_maaco_rank_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        map->svalid_dev, tau_dev, E01_dev, alpha, map->rows, map->cols, P1, rank_dev + L.margin,
+        (uint2 *)(rank_dev + L.fast_words));
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }

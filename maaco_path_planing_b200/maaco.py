@@ -89,7 +89,8 @@ class MAACO:
         self._E01 = torch.empty(2 * n, dtype=f64, device=dev)       # eta'**beta, interleaved by turn flag
         self._dist_t = torch.empty(n, dtype=f64, device=dev)
         self.use_rank = use_rank
-        self._rank = torch.empty(18 * n, dtype=i32, device=dev) if use_rank else None
+        self._rank = (torch.empty(_lib.lib().mpp_maaco_rank_words(self.map.handle), dtype=i32, device=dev)
+                      if use_rank else None)
         self._params = _lib.MaacoParams(alpha, beta, rho, Q, a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
                                         C0_initial_pheromone, num_iterations)
         stream = torch.cuda.current_stream(dev).cuda_stream
