@@ -597,14 +597,21 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
     const int dc0 = A.s1.dc[0], dc1 = A.s1.dc[1], dc2 = A.s1.dc[2];
     const int so0 = A.s1.so[0], so1 = A.s1.so[1], so2 = A.s1.so[2];
     // (kept in registers: re-reading kernel parameters inside the step costs a constant-bank round trip each time)
-#define T1_KEEP(x) asm volatile("" : "+r"(x))
+#define T1_KEEP(x) x = __shfl_sync(0xffffffffu, x, 0)   /* a value ptxas cannot re-derive from the parameter bank */
     int k_sm0 = sm0, k_sm1 = sm1, k_sm2 = sm2, k_dpr0 = dpr0, k_dpr1 = dpr1, k_dpr2 = dpr2;
     int k_dc0 = dc0, k_dc1 = dc1, k_dc2 = dc2, k_so0 = so0, k_so1 = so1, k_so2 = so2;
     T1_KEEP(k_sm0); T1_KEEP(k_sm1); T1_KEEP(k_sm2); T1_KEEP(k_dpr0); T1_KEEP(k_dpr1); T1_KEEP(k_dpr2);
     T1_KEEP(k_dc0); T1_KEEP(k_dc1); T1_KEEP(k_dc2); T1_KEEP(k_so0); T1_KEEP(k_so1); T1_KEEP(k_so2);
     const size_t n_ants = (size_t)A.n_ants;
     int32_t *const cells_a = A.cells + (size_t)(active ? a : a0) * A.max_cells;
-    const uint32_t *const __restrict__ rank_fast = A.rank_fast;
+    const uint32_t *__restrict__ rank_fast = A.rank_fast;
+    {
+        unsigned long long rf = (unsigned long long)rank_fast;
+        rf = __shfl_sync(0xffffffffu, rf, 0);
+        rank_fast = (const uint32_t *)rf;
+    }
+    int k_target = A.target, k_max_cells = A.max_cells;
+    T1_KEEP(k_target); T1_KEEP(k_max_cells);
     int n_path = 1, prev_m = -1, turns = 0;
     double len = 0.0;
     const int max_path = 2 * R * C + 1;
@@ -622,9 +629,8 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
     uint32_t prow_s = (uint32_t)__cvta_generic_to_shared(win_w + (size_t)(lane < apw ? lane : 0) * 64 + lrow);   // the ant's window row
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(t1_smem);
     uint32_t rngp_s = (uint32_t)__cvta_generic_to_shared(rngp) + 4u * (uint32_t)lane;
-    uint32_t sbase_k = sbase;                                    // (opaque copies: otherwise re-derived from %cluster_ctaid every use)
-    asm volatile("" : "+r"(rngp_s));
-    asm volatile("" : "+r"(sbase_k));
+    uint32_t sbase_k = sbase;                                    // (opaque copy: otherwise re-derived from %cluster_ctaid every use)
+    sbase_k = __shfl_sync(0xffffffffu, sbase_k, 0);
     uint32_t fw = 0u;                                             // strategy-1 word of (cell, previous move)
     uint32_t pf0 = 0u, pf1 = 0u, pf2 = 0u;                        // ... of the three strategy-1 neighbours, prefetched
     if (active) {
@@ -801,12 +807,12 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                 lrow += dpr >> 3;
                 lcol += dcc;
                 asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(prow_s + 4u * ((uint32_t)lcol >> 5)), "r"(1u << (lcol & 31)) : "memory");
-                if (n_path < A.max_cells) cells_a[n_path] = cur;
+                if (n_path < k_max_cells) cells_a[n_path] = cur;
                 len += lds_f64(sbase_k + T1_DLEN_OFF + 8u * (uint32_t)m);
                 if (n_path >= 2 && m != prev_m) ++turns;              // :264-276 counted on the fly
                 prev_m = m;
                 ++n_path;
-                if (cur == target || n_path >= max_path) active = false;
+                if (cur == k_target || n_path >= max_path) active = false;
             }
         }
     }
@@ -917,57 +923,70 @@ extern "C" long long mpp_maaco_rank_words(const mpp_map *map) {
 // Strategy-1 word (one per (cell, context)): [31:24] static move mask; field c (3 bits at 3c, c = 1..7 = a subset of
 // P1's three moves in move order) = what greedy selection (:241-250) keeps of candidate set c, as a subset again;
 // field 0 = 0 when the ranking applies (all attractiveness < 1e-10), 7 when it does not (or P1 has not three moves).
-__global__ void __launch_bounds__(256) mpp_maaco_rank_kernel(const uint8_t *__restrict__ svalid,
+__global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__restrict__ svalid,
                                                              const double *__restrict__ tau,
                                                              const double *__restrict__ E01, double alpha, int R, int C,
                                                              uint32_t P1, uint32_t *__restrict__ rank_fast,
                                                              uint2 *__restrict__ rank_slow) {
-    const int t = blockIdx.x * 256 + threadIdx.x;
-    if (t >= R * C * 9) return;
-    const int cell = t / 9, ctx = t - cell * 9;
+    // one thread per cell: the eight neighbours' tau / eta' are read once and serve all nine contexts
+    const int cell = blockIdx.x * 128 + threadIdx.x;
+    if (cell >= R * C) return;
     const uint32_t sv = svalid[cell];
-    double a[8];
+    double a0[8], a1[8];                                          // attractiveness without / with the turn factor (:238)
     double mx = 0.0;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-        a[m] = -1.0;
+        a0[m] = a1[m] = -1.0;
         if ((sv >> m) & 1u) {
             const int j = cell + ((int)((0xA940u >> (2 * m)) & 3u) - 1) * C + ((int)((0x9224u >> (2 * m)) & 3u) - 1);
             const double tv = tau[j];
             const double ta = (alpha == 1.0) ? tv : pow_slow(tv, alpha);
-            const bool turn = ctx > 0 && m != ctx - 1;
-            a[m] = ta * E01[2 * (size_t)j + (turn ? 1 : 0)];
-            mx = a[m] > mx ? a[m] : mx;
+            const double2 e = *(const double2 *)(E01 + 2 * (size_t)j);
+            a0[m] = ta * e.x;
+            a1[m] = ta * e.y;
+            mx = fmax(mx, fmax(a0[m], a1[m]));
         }
     }
-    uint32_t word = 0xFFFFFFu, perm = 0u, fast = 7u;
-    if (mx < 1e-10) {
-        word = 0u;
+    const bool p1_three = __popc(P1) == 3;
+    const int s0 = __ffs(P1) - 1, s1 = __ffs(P1 & (P1 - 1)) - 1, s2 = 31 - __clz(P1);
+    for (int ctx = 0; ctx < 9; ++ctx) {
+        double a[8];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            int pos = 0;
+        for (int m = 0; m < 8; ++m) a[m] = (ctx > 0 && m != ctx - 1) ? a1[m] : a0[m];   // turn flag :184-195
+        // "small" is decided per context on the values that context uses (as the tour's full rule would see them)
+        double cmx = 0.0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) pos += (a[q] > a[m]) || (a[q] == a[m] && q < m);
-            word |= (uint32_t)pos << (3 * m);
-            perm |= (uint32_t)m << (4 * pos);
-        }
-        if (__popc(P1) == 3) {
-            const int s0 = __ffs(P1) - 1, s1 = __ffs(P1 & (P1 - 1)) - 1, s2 = 31 - __clz(P1);
-            const uint32_t p0 = (word >> (3 * s0)) & 7u, p1 = (word >> (3 * s1)) & 7u, p2 = (word >> (3 * s2)) & 7u;
-            fast = 0u;
+        for (int m = 0; m < 8; ++m) cmx = fmax(cmx, a[m]);
+        uint32_t word = 0xFFFFFFu, perm = 0u, fast = 7u;
+        if (cmx < 1e-10) {
+            word = 0u;
 #pragma unroll
-            for (uint32_t c = 1; c < 8; ++c) {
-                // best-ranked member of subset c (rank positions are distinct)
-                uint32_t bp = 8u, bi = 0u;
-                if ((c & 1u) && p0 < bp) { bp = p0; bi = 0u; }
-                if ((c & 2u) && p1 < bp) { bp = p1; bi = 1u; }
-                if ((c & 4u) && p2 < bp) { bp = p2; bi = 2u; }
-                fast |= (c & ~((1u << bi) - 1u)) << (3u * c);     // the best one and every later member
+            for (int m = 0; m < 8; ++m) {
+                int pos = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) pos += (a[q] > a[m]) || (a[q] == a[m] && q < m);
+                word |= (uint32_t)pos << (3 * m);
+                perm |= (uint32_t)m << (4 * pos);
+            }
+            if (p1_three) {
+                const uint32_t p0 = (word >> (3 * s0)) & 7u, p1 = (word >> (3 * s1)) & 7u, p2 = (word >> (3 * s2)) & 7u;
+                fast = 0u;
+#pragma unroll
+                for (uint32_t c = 1; c < 8; ++c) {
+                    // best-ranked member of subset c (rank positions are distinct)
+                    uint32_t bp = 8u, bi = 0u;
+                    if ((c & 1u) && p0 < bp) { bp = p0; bi = 0u; }
+                    if ((c & 2u) && p1 < bp) { bp = p1; bi = 1u; }
+                    if ((c & 4u) && p2 < bp) { bp = p2; bi = 2u; }
+                    fast |= (c & ~((1u << bi) - 1u)) << (3u * c);     // the best one and every later member
+                }
             }
         }
+        const size_t t = (size_t)cell * 9 + ctx;
+        rank_fast[t] = fast | (sv << 24);
+        rank_slow[t] = make_uint2(perm, word | (sv << 24));
     }
-    rank_fast[t] = fast | (sv << 24);
-    rank_slow[t] = make_uint2(perm, word | (sv << 24));
+    (void)mx;
 }
 
 extern "C" int mpp_maaco_rank(const mpp_map *map, const double *tau_dev, const double *E01_dev, double alpha,
@@ -975,11 +994,11 @@ extern "C" int mpp_maaco_rank(const mpp_map *map, const double *tau_dev, const d
     MPP_REQUIRE(map && tau_dev && E01_dev && rank_dev, "mpp_maaco_rank: null argument");
     MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_rank: map has no start/target");
     MPP_CUDA(cudaSetDevice(map->device));
-    const int total = map->rows * map->cols * 9;
+    const int total = map->rows * map->cols;
     const RankLayout L = rank_layout(map->rows, map->cols);
     const uint32_t P1 = host_orient_mask(map->target / map->cols - map->start / map->cols,
                                          map->target % map->cols - map->start % map->cols);
-    mpp_maaco_rank_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+    mpp_maaco_rank_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         map->svalid_dev, tau_dev, E01_dev, alpha, map->rows, map->cols, P1, rank_dev + L.margin,
         (uint2 *)(rank_dev + L.fast_words));
     MPP_CUDA(cudaGetLastError());

@@ -131,6 +131,32 @@ def test_lane_layouts_agree():
         assert np.array_equal(outs[0][1], other[1])
 
 
+def test_ants_per_warp_and_table_modes_agree(monkeypatch):
+    """The thread-per-ant kernel gives the same colony for every packing of ants into warps, and the
+    table-free path (use_rank=False: literal selection rules at every step) is the same function."""
+    from maaco_path_planing_b200 import MAACO, blocks_map
+    import pyoracle as O
+    g = blocks_map(150, 0.2, seed=77)                      # 150 columns: window words straddle bitmap words
+    N = 200
+    orc = O.MaacoOracle(g, N, 2, seed=9, threads=0, **MAACO_DEFAULT)
+    ref = [orc.iterate(1), orc.iterate(2)]
+    tau_ref = orc.tau.copy()
+    for apw, use_rank in ((1, True), (4, True), (32, True), (0, False)):
+        if apw:
+            monkeypatch.setenv("MPP_TOUR_APW", str(apw))
+        else:
+            monkeypatch.delenv("MPP_TOUR_APW", raising=False)
+        dev = MAACO(g, N, 2, rng_seed=9, use_rank=use_rank, verbose=False, **MAACO_DEFAULT)
+        for it in (1, 2):
+            dev.run_iteration(it)
+            nc, ln, tn, cells = dev.last_tours()
+            ocells, onc, oln, otn, _ = ref[it - 1]
+            assert np.array_equal(nc, onc) and np.array_equal(ln, oln) and np.array_equal(tn, otn)
+            for a in range(N):
+                assert np.array_equal(cells[a, :nc[a]], ocells[a, :onc[a]])
+        assert np.array_equal(dev.pheromone_matrix.ravel(), tau_ref)
+
+
 def test_errors_like_reference():
     from maaco_path_planing_b200 import MAACO
     g = np.zeros((5, 5), int)
