@@ -746,7 +746,6 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
             }
             if (m < 0) {
                 // ---- general step: all eight moves, strategies 1-3, full ranking entry or the literal rules ----
-                const uint2 rws = A.rank_slow[(size_t)cur * 9 + (n_path >= 2 ? prev_m + 1 : 0)];
                 const uint2 q0r = lds_u2(prow_s - 8u), q1r = lds_u2(prow_s), q2r = lds_u2(prow_s + 8u);
                 const int rot = lcol - 1;                             // 0..61
                 const bool sw = rot & 32;
@@ -754,7 +753,7 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                 const uint32_t m3 = __funnelshift_r(sw ? q1r.y : q1r.x, q1r.y, rot) & 5u;
                 const uint32_t b3 = __funnelshift_r(sw ? q2r.y : q2r.x, q2r.y, rot) & 7u;
                 const uint32_t vis = t3 | ((m3 & 1u) << 3) | ((m3 & 4u) << 2) | (b3 << 5);
-                const uint32_t valid = (rws.y >> 24) & ~vis;
+                const uint32_t valid = (fw >> 24) & ~vis;             // static mask (:93-120) minus tabu (:93-95)
                 uint32_t cand = valid & P1;                           // strategy 1 :165
                 if (cand == 0u) {
                     cand = valid & orient_mask(tr - cur / C, tc - cur % C);   // strategy 2 :169
@@ -764,20 +763,27 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                     failed = true;
                     active = false;
                 } else {
-                    if ((rws.y & 0xFFFFFFu) != 0xFFFFFFu) {
-                        // first arg-max = best-ranked candidate: permute the candidate flags into rank order
-                        const uint2 sp = lds_u2(sbase_k + T1_SPREAD_OFF + 8u * cand);
-                        const uint32_t f0 = __byte_perm(sp.x, sp.y, rws.x & 0xFFFFu), f1 = __byte_perm(sp.x, sp.y, rws.x >> 16);
-                        const uint32_t ff = f0 ? f0 : f1;
-                        const int pos4 = ((__ffs(ff) - 1) >> 1) + (f0 ? 0 : 16);
-                        const uint32_t best = (rws.x >> pos4) & 7u;
-                        const uint32_t pool = (pack & (1u << 24)) ? (cand & ~((1u << best) - 1u)) : cand;
+                    if ((cand & (cand - 1u)) == 0u) {
+                        m = __ffs(cand) - 1;                          // one candidate: every rule picks it
+                    } else if ((fw & 7u) != 0u) {                     // some attractiveness >= 1e-10: literal rules
+                        const double2 uu = rngu[(step & gmask) * apw + lane];
+                        m = tour_select_slow(cand, cur / C, cur % C, C, n_path >= 2, prev_m, A.tau, A.E01, A.alpha, A.q0, uu.x, uu.y);
+                    } else {
+                        uint32_t pool = cand;                         // roulette over tiny values: uniform (:253-254)
+                        if (pack & (1u << 24)) {
+                            // greedy: first arg-max = best-ranked candidate (full entry: permute the candidate flags
+                            // into rank order, take the first) and every later candidate
+                            const uint2 rws = A.rank_slow[(size_t)cur * 9 + (n_path >= 2 ? prev_m + 1 : 0)];
+                            const uint2 sp = lds_u2(sbase_k + T1_SPREAD_OFF + 8u * cand);
+                            const uint32_t f0 = __byte_perm(sp.x, sp.y, rws.x & 0xFFFFu), f1 = __byte_perm(sp.x, sp.y, rws.x >> 16);
+                            const uint32_t ff = f0 ? f0 : f1;
+                            const int pos4 = ((__ffs(ff) - 1) >> 1) + (f0 ? 0 : 16);
+                            const uint32_t best = (rws.x >> pos4) & 7u;
+                            pool = cand & ~((1u << best) - 1u);
+                        }
                         const int n = __popc(pool);
                         const int k = (pack >> (3 * n - 3)) & 7u;
                         m = (int)lds_u8(sbase_k + T1_KTH_OFF + pool * 8u + (uint32_t)k);
-                    } else {
-                        const double2 uu = rngu[(step & gmask) * apw + lane];
-                        m = tour_select_slow(cand, cur / C, cur % C, C, n_path >= 2, prev_m, A.tau, A.E01, A.alpha, A.q0, uu.x, uu.y);
                     }
                     const uint4 mvv = lds_u4(sbase_k + T1_MOVE_OFF + 16u * (uint32_t)m);
                     dcur = (int)mvv.x; dpr = (int)mvv.y; dcc = (int)mvv.z;
@@ -922,7 +928,8 @@ extern "C" long long mpp_maaco_rank_words(const mpp_map *map) {
 
 // Strategy-1 word (one per (cell, context)): [31:24] static move mask; field c (3 bits at 3c, c = 1..7 = a subset of
 // P1's three moves in move order) = what greedy selection (:241-250) keeps of candidate set c, as a subset again;
-// field 0 = 0 when the ranking applies (all attractiveness < 1e-10), 7 when it does not (or P1 has not three moves).
+// field 0 = 0 when the ranking applies (all attractiveness < 1e-10), 7 when it does not; fields 1..7 are only
+// filled when P1 has exactly three moves.
 __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__restrict__ svalid,
                                                              const double *__restrict__ tau,
                                                              const double *__restrict__ E01, double alpha, int R, int C,
@@ -968,9 +975,9 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
                 word |= (uint32_t)pos << (3 * m);
                 perm |= (uint32_t)m << (4 * pos);
             }
+            fast = 0u;                                            // field 0: the ranking applies
             if (p1_three) {
                 const uint32_t p0 = (word >> (3 * s0)) & 7u, p1 = (word >> (3 * s1)) & 7u, p2 = (word >> (3 * s2)) & 7u;
-                fast = 0u;
 #pragma unroll
                 for (uint32_t c = 1; c < 8; ++c) {
                     // best-ranked member of subset c (rank positions are distinct)
