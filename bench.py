@@ -181,23 +181,25 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
     t_wall0 = time.time()
     sync_all()
     for k in range(K):
         flush.fill_(k & 0xff)                                   # evict L2 between timed steps (untimed)
         it += 1
-        solver._enqueue_iteration(it, events=ev[k])             # events: start / after tours / before pheromone / end
+        solver._enqueue_iteration(it, events=ev[k])             # events: start / after tours / before pheromone / end / after ranking
     sync_all()
     t_wall1 = time.time()
     step_ms = [e[0].elapsed_time(e[3]) for e in ev]
-    tour_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    tour_ms = [e[4].elapsed_time(e[1]) for e in ev]             # the tour kernel alone
+    rank_ms = [e[0].elapsed_time(e[4]) for e in ev]             # the move-ranking kernel before it
     pher_ms = [e[2].elapsed_time(e[3]) for e in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX, group=group)
     total_ms = float(total_ms.item())
     ant_steps_local = solver.total_steps() - steps_before
+    launches_timed = solver.kernel_launches - launches_before      # kernels of this library inside the timed region
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
     # ---- e2e: the colony pass called with HOST buffers (pinned tau in, results + tau out) ----------
@@ -236,7 +238,7 @@ def run_gpu(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if world == 1 and args.ants == 4096 and args.size == 512 and os.path.exists(tp):
-        traffic = json.load(open(tp))["mpp_maaco_tour_kernel"]["dram_bytes_per_launch"]   # from the committed ncu capture
+        traffic = json.load(open(tp))["mpp_maaco_tour1_kernel"]["dram_bytes_per_launch"]   # from the committed ncu capture
     value = total_ants * K / (total_ms / 1e3)
     tour_avg_ms = sum(tour_ms) / K
     achieved = BYTES_PER_ANT_STEP * (ant_steps_local / K) / (tour_avg_ms / 1e3) / 1e9
@@ -247,12 +249,13 @@ def run_gpu(args):
         "e2e": {"value": total_ants * K2 / e2e_s, "unit": "path evals/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": K2,
                 "note": "host pheromone field in, per-ant results + best path + updated field out, every pass"},
-        "gpu_launches": solver.kernel_launches - launches_before - 3 * K2,
+        "gpu_launches": launches_timed,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "mpp_maaco_tour_kernel", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "mpp_maaco_tour1_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_unit": BYTES_PER_ANT_STEP, "units_per_launch": ant_steps_local / K,
                      "kernel_ms": tour_avg_ms,
+                     "rank_kernel_ms": sum(rank_ms) / K,
                      "pheromone_kernel": {"ms": sum(pher_ms) / K,
                                           "achieved": (16.0 * n + 4.0 * solver.n_words * total_ants / world
                                                        + 16.0 * total_ants) / (sum(pher_ms) / K / 1e3) / 1e9,

@@ -141,11 +141,13 @@ class MAACO:
         return _lib.lib().mpp_maaco_q0(self.num_iterations, int(current_iteration_num), self.q0_initial)
 
     # ---- one colony pass (MAACO.py:336-359), fully asynchronous ----------------------------
-    def _enqueue_tours(self, it, stream):
+    def _enqueue_tours(self, it, stream, mid_event=None):
         nl, off = self.n_local, self.ant_offset
         if self.use_rank:                                            # move ranking for the current tau
             _lib.check(_lib.lib().mpp_maaco_rank(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E01), self.alpha,
                                                  _lib.ptr(self._rank), stream), "mpp_maaco_rank")
+        if mid_event is not None:
+            mid_event.record()
         _lib.check(_lib.lib().mpp_maaco_tours(
             self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E01), _lib.ptr(self._rank) if self.use_rank else None, it,
             self._calculate_adaptive_q0(it), self.alpha, nl, off, C.c_uint64(self.rng_seed),
@@ -173,14 +175,15 @@ class MAACO:
                                              stream), "mpp_maaco_pheromone")
 
     def _enqueue_iteration(self, it, events=None):
-        """One colony pass.  `events`: optional 4 CUDA events recorded at (start, after tours, before the
-        pheromone update, end) on the launching stream -- used by bench.py for per-kernel timing."""
+        """One colony pass.  `events`: optional CUDA events recorded at (start, after tours, before the
+        pheromone update, end[, after the ranking kernel]) on the launching stream -- used by bench.py for
+        per-kernel timing."""
         import torch
         cur = torch.cuda.current_stream(self.device)
         stream = C.c_void_p(cur.cuda_stream)
         if events:
             events[0].record(cur)
-        self._enqueue_tours(it, stream)
+        self._enqueue_tours(it, stream, events[4] if events and len(events) > 4 else None)
         if events:
             events[1].record(cur)
         if self.world > 1:
@@ -212,7 +215,7 @@ class MAACO:
                                                       _lib.ptr(self._offsets), _lib.ptr(self._result), self.world, nl,
                                                       self.rank * wn, wn, _lib.ptr(self._visit_recv), stream),
                            "mpp_maaco_rebuild_visits")
-                self.kernel_launches += 4 if self.use_rank else 3
+                self.kernel_launches += 3
             # the local bitmaps are free again: clear them off the critical path
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
