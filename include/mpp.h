@@ -115,7 +115,9 @@ typedef struct {
  *                  counts them)
  *   result_dev     n_ants x mpp_ant_result (:288,:292,:300-302)
  *   steps_dev      optional counter, += number of ant steps taken
- *   lanes_per_ant  1 = one thread per ant; 8, 16 or 32 lanes cooperate on one ant; 0 = library default              */
+ *   lanes_per_ant  0 = library default; 1 = one thread per ant (needs rank_dev), ants per warp chosen from n_ants;
+ *                  -k (k = 1,2,4,..,32) = one thread per ant, k ants per warp (for callers that overlap several
+ *                  colonies and know the total load); 8, 16 or 32 = that many lanes cooperate on one ant              */
 int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E01_dev, const uint32_t *rank_dev,
                     int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
                     uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, mpp_ant_result *result_dev,

@@ -27,6 +27,9 @@ def solve_maaco_batch(grids, num_ants, num_iterations, params, seeds=None, concu
     from .maaco import MAACO
     lo, hi = shard_maps(len(grids), group)
     out = []
+    # the overlapped colonies fill the GPU together: pack the ants as one colony of that total size would be packed
+    in_flight = max(1, min(concurrent, hi - lo)) * num_ants
+    apw = 2 if in_flight <= 4096 else (4 if in_flight <= 8192 else 8)
     for w0 in range(lo, hi, concurrent):
         idx = list(range(w0, min(hi, w0 + concurrent)))
         solvers, streams = [], []
@@ -34,7 +37,7 @@ def solve_maaco_batch(grids, num_ants, num_iterations, params, seeds=None, concu
             g = grids[i]
             mc = max_cells or min(g.shape[0] * g.shape[1], 16 * (g.shape[0] + g.shape[1]))
             solvers.append(MAACO(g, num_ants, num_iterations, rng_seed=None if seeds is None else seeds[i],
-                                 device=device, verbose=False, max_cells=mc, **params))
+                                 device=device, verbose=False, max_cells=mc, ants_per_warp=apw, **params))
             streams.append(torch.cuda.Stream(device=solvers[-1].device))
         cur = torch.cuda.current_stream(solvers[0].device)
         for st in streams:

@@ -851,6 +851,8 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
     MPP_REQUIRE(map && tau_dev && E01_dev && visitT_dev && cells_dev && result_dev, "mpp_maaco_tours: null argument");
     MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_tours: map has no start/target");
     MPP_REQUIRE(n_ants > 0 && max_cells > 0, "mpp_maaco_tours: n_ants=%d max_cells=%d", n_ants, max_cells);
+    int apw_hint = 0;                                             // lanes_per_ant = -k: thread per ant, k ants per warp
+    if (lanes_per_ant < 0) { apw_hint = -lanes_per_ant; lanes_per_ant = 1; }
     if (lanes_per_ant == 0) {
         const char *e = getenv("MPP_TOUR_LPA");
         lanes_per_ant = e ? atoi(e) : 1;   // measured on B200: thread-per-ant beats the cooperative forms from 256 to 16k ants
@@ -891,11 +893,19 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
         int apw = 32;
         const char *e = getenv("MPP_TOUR_APW");
         if (e) apw = atoi(e);
+        else if (apw_hint) apw = apw_hint;
         else while (apw > 2 && (n_ants + apw - 1) / apw < 12 * map->sm_count) apw >>= 1;   // measured: 2 ants/warp at 4096 ants
-        MPP_REQUIRE(apw == 1 || apw == 2 || apw == 4 || apw == 8 || apw == 16 || apw == 32, "MPP_TOUR_APW must be a power of two <= 32");
+        MPP_REQUIRE(apw == 1 || apw == 2 || apw == 4 || apw == 8 || apw == 16 || apw == 32, "ants per warp (MPP_TOUR_APW / -lanes_per_ant) must be a power of two <= 32");
         const int warps = (n_ants + apw - 1) / apw, wpb = MPP_TOUR1_THREADS / 32;
         const size_t smem = T1_WIN_OFF + (size_t)wpb * apw * 512;   // tables + per-warp RNG + 512-byte windows
-        MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {   // raise the kernel's dynamic shared-memory limit only when it grows (the call is slow; devices tracked apart)
+            static size_t smem_set[64] = {0};
+            const int dv = map->device & 63;
+            if (smem > smem_set[dv]) {
+                MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                smem_set[dv] = smem;
+            }
+        }
         mpp_maaco_tour1_kernel<<<(warps + wpb - 1) / wpb, MPP_TOUR1_THREADS, smem, (cudaStream_t)stream>>>(A, apw);
         MPP_CUDA(cudaGetLastError());
         return MPP_OK;

@@ -30,7 +30,8 @@ class MAACO:
                  alpha, beta, rho, Q,
                  a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
                  C0_initial_pheromone=0.1, *,
-                 rng_seed=None, device=None, max_cells=None, lanes_per_ant=0, group=None, exchange="moves",
+                 rng_seed=None, device=None, max_cells=None, lanes_per_ant=0, ants_per_warp=0, group=None,
+                 exchange="moves",
                  use_rank=True, verbose=True):
         import torch
         self.grid = np.array(grid, dtype=int)                       # MAACO.py:15
@@ -54,7 +55,8 @@ class MAACO:
         self.dist_S_to_T_overall = d if d >= 1e-9 else 1e-9
         self.rng_seed = _fresh_seed() if rng_seed is None else int(rng_seed)
         self.verbose = verbose
-        self.lanes_per_ant = lanes_per_ant
+        # ants_per_warp: hint for the thread-per-ant kernel when several colonies share the GPU (batch.py)
+        self.lanes_per_ant = -int(ants_per_warp) if ants_per_warp and lanes_per_ant in (0, 1) else lanes_per_ant
         if exchange not in ("moves", "dense"):
             raise ValueError("exchange must be 'moves' or 'dense'")
         self.exchange = exchange
