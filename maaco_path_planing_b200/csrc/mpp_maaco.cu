@@ -647,8 +647,12 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
     }
     __syncwarp();
     const uint32_t gmask = (uint32_t)(32 / apw) - 1u;              // a cooperative Philox pass covers 32/apw steps
-    for (uint32_t step = 0;; ++step) {
-        const uint32_t need0 = __ballot_sync(0xffffffffu, active && ((unsigned)(lrow - 1) > 61u || (unsigned)(lcol - 1) > 61u));
+    // U steps per pass of the warp-level bookkeeping below (liveness vote, Philox refill, window slides): an ant may
+    // then be U cells from where the checks saw it, so the window keeps a margin of U cells instead of one
+    const int U = (apw <= 16) ? 2 : 1;                             // a refill covers 32 / apw steps: must be a multiple of U
+    const unsigned edge_lo = (unsigned)U, edge_span = 63u - 2u * (unsigned)U;
+    for (uint32_t step = 0;; step += (uint32_t)U) {
+        const uint32_t need0 = __ballot_sync(0xffffffffu, active && ((unsigned)lrow - edge_lo > edge_span || (unsigned)lcol - edge_lo > edge_span));
         if (!__any_sync(0xffffffffu, active)) break;
         if ((step & gmask) == 0 || need0) {
             if ((step & gmask) == 0) {
@@ -681,8 +685,8 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                 uint32_t *const v_s = A.visitT + (a0 + src);
                 uint2 *const w_s = win_w + src * 64;
                 int d_wr = 0, d_wc = 0;
-                if ((unsigned)(s_lrow - 1) > 61u) {                // vertical: rows move by 32, one tile row leaves, one enters
-                    const bool up = s_lrow < 1;
+                if ((unsigned)s_lrow - edge_lo > edge_span) {      // vertical: rows move by 32, one tile row leaves, one enters
+                    const bool up = s_lrow < U;
                     d_wr = up ? -1 : 1;
                     const int r_out = ((up ? s_wr + 1 : s_wr) << 5) + lane, r_in = ((up ? s_wr - 1 : s_wr + 2) << 5) + lane;
                     const uint2 keep = w_s[up ? lane : lane + 32], out = w_s[up ? lane + 32 : lane];
@@ -694,7 +698,7 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                     w_s[up ? lane + 32 : lane] = keep;
                     w_s[up ? lane : lane + 32] = nw;
                 } else {                                           // horizontal: the two words of each row shift
-                    const bool left = s_lcol < 1;
+                    const bool left = s_lcol < U;
                     d_wc = left ? -1 : 1;
                     const int t_out = left ? s_wc + 1 : s_wc, t_in = left ? s_wc - 1 : s_wc + 2;
                     const int r = (s_wr << 5) + lane;
@@ -713,14 +717,15 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                 }
                 __syncwarp();
                 // a diagonal step can leave through a corner: this ant may still need the other direction
-                const bool again = (lane == src) && ((unsigned)(lrow - 1) > 61u || (unsigned)(lcol - 1) > 61u);
+                const bool again = (lane == src) && ((unsigned)lrow - edge_lo > edge_span || (unsigned)lcol - edge_lo > edge_span);
                 need = (need & (need - 1)) | __ballot_sync(0xffffffffu, again);
             }
         }
+        for (uint32_t su = step; su < step + (uint32_t)U; ++su)
         if (active) {
             int m = -1, dcur = 0, dpr = 0, dcc = 0;                   // the move taken this step and its deltas
             uint32_t pi = 0u;                                         // which prefetched word applies next step
-            const uint32_t pack = lds_u32(rngp_s + 4u * ((step & gmask) * (uint32_t)apw));
+            const uint32_t pack = lds_u32(rngp_s + 4u * ((su & gmask) * (uint32_t)apw));
             if (fast_ok) {
                 // ---- strategy 1 (:165) on the three moves of P1 only ----
                 const uint2 ra = lds_u2(prow_s + k_dpr0), rb = lds_u2(prow_s + k_dpr1), rc = lds_u2(prow_s + k_dpr2);
@@ -766,7 +771,7 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                     if ((cand & (cand - 1u)) == 0u) {
                         m = __ffs(cand) - 1;                          // one candidate: every rule picks it
                     } else if ((fw & 7u) != 0u) {                     // some attractiveness >= 1e-10: literal rules
-                        const double2 uu = rngu[(step & gmask) * apw + lane];
+                        const double2 uu = rngu[(su & gmask) * apw + lane];
                         m = tour_select_slow(cand, cur / C, cur % C, C, n_path >= 2, prev_m, A.tau, A.E01, A.alpha, A.q0, uu.x, uu.y);
                     } else {
                         uint32_t pool = cand;                         // roulette over tiny values: uniform (:253-254)
