@@ -89,3 +89,41 @@ def test_waypoint_chain_properties(case, W):
         order = [pos.get(int(w), -1) for w in wps[i]]
         assert all(o >= 0 for o in order)                       # every waypoint is on the path ...
         assert stats[i, 4] >= stats[i, 0]                       # ... and penalties only add
+
+
+# ---- the ranking shortcut of the MAACO tour kernels (mpp_maaco_rank) -------------------
+def _literal_pool(attr, greedy):
+    """Candidate indices the final uniform draw picks from, by the literal rules MAACO.py:241-254
+    (attr: attractiveness of the candidates in move order)."""
+    if greedy:                                             # :241-250
+        mx, best = -1.0, []
+        for i, a in enumerate(attr):
+            if a > mx:
+                mx, best = a, [i]
+            elif abs(a - mx) < 1e-9:
+                best.append(i)
+        return best
+    assert sum(attr) < 1e-9                                # :252-254: the roulette degenerates to uniform
+    return list(range(len(attr)))
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.floats(min_value=0.0, max_value=9.9e-11, allow_nan=False), min_size=8, max_size=8),
+       st.integers(1, 255), st.booleans(), st.sampled_from([0, 1, 2]))
+def test_rank_order_decides_selection_when_attractiveness_is_tiny(vals, cand_mask, greedy, dup):
+    """With every attractiveness < 1e-10 the pool of MAACO.py:241-254 is a function of the ORDER of the
+    values only: greedy = the best-ranked candidate (ties -> lower move index) and every later candidate."""
+    vals = list(vals)
+    if dup:                                                # force ties
+        vals[dup] = vals[0]
+    cand = [m for m in range(8) if (cand_mask >> m) & 1]
+    attr = [vals[m] for m in cand]
+    want = [cand[i] for i in _literal_pool(attr, greedy)]
+    # ranking as mpp_maaco_rank_kernel builds it: position = number of moves sorting before (value desc, index asc)
+    pos = [sum((vals[q] > vals[m]) or (vals[q] == vals[m] and q < m) for q in range(8)) for m in range(8)]
+    if greedy:
+        best = min(cand, key=lambda m: pos[m])
+        got = [m for m in cand if m >= best]
+    else:
+        got = cand
+    assert got == want
