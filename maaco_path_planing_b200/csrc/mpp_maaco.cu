@@ -1346,6 +1346,120 @@ mpp_maaco_pheromone_block_kernel(const uint32_t *__restrict__ occ, int pitch, in
     if (wid == 0 && live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
 }
 
+// Super-round variant (default).  What bounded the block-per-word kernel above was not bandwidth but one DRAM round
+// trip per 1024-ant round (ncu: half of all stalls at the round barrier): here a block issues the loads of 4096 ants
+// (16 words per lane) at once, so a word costs ONE round trip.  The hits -- typically a few dozen per word -- are
+// compacted in ant order into a small list (warp-count prefix over shared memory) that warp 0 folds; words with more
+// hits than the list holds (around the start cell) fall back to one warp's 512 ants at a time.
+#define MPP_PHER_SR 4096
+#define MPP_PHER_SRU (MPP_PHER_SR / 8 / 32)   // loads per lane per super-round (8 warps)
+#define MPP_PHER_CAP 512                     // list entries per buffer (>= ants per warp per super-round)
+
+__device__ __forceinline__ double pher_fold_list(const PherEntry *lst, int n, int lane, double t) {
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+        // select the operand, not the sum: the loop-carried chain is a bare DADD (t + 0.0 == t exactly)
+        const PherEntry x0 = lst[i], x1 = lst[i + 1], x2 = lst[i + 2], x3 = lst[i + 3];
+        const double a0 = ((x0.w >> lane) & 1u) ? x0.d : 0.0, a1 = ((x1.w >> lane) & 1u) ? x1.d : 0.0;
+        const double a2 = ((x2.w >> lane) & 1u) ? x2.d : 0.0, a3 = ((x3.w >> lane) & 1u) ? x3.d : 0.0;
+        t += a0;                                                             // :311
+        t += a1;
+        t += a2;
+        t += a3;
+    }
+    for (; i < n; ++i) {
+        const PherEntry x = lst[i];
+        t += ((x.w >> lane) & 1u) ? x.d : 0.0;
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(MPP_PHER_THREADS, 3)
+mpp_maaco_pheromone_sr_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
+                              uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg,
+                              int seg_ants, int word0, int n_words, double rho,
+                              const mpp_maaco_state *__restrict__ state, int clear_visit) {
+    __shared__ PherEntry s_list[2][MPP_PHER_CAP];
+    __shared__ int s_cnt[2][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int wl = blockIdx.x;                               // one bitmap word (32 cells) per block
+    const int cell = (word0 + wl) * 32 + lane;
+    const bool live = cell < R * C;
+    double t = 0.0;
+    if (wid == 0 && live) t = tau[cell] * (1.0 - rho);       // :305
+    const int sr_per_seg = (seg_ants + MPP_PHER_SR - 1) / MPP_PHER_SR;
+    const int n_sr = n_seg * sr_per_seg;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int sr = 0; sr < n_sr; ++sr) {
+        const int buf = sr & 1;
+        const int seg = sr / sr_per_seg, a_base = (sr % sr_per_seg) * MPP_PHER_SR + wid * (MPP_PHER_SR / 8);
+        uint32_t *const row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
+        const double *const dep = deposit + (size_t)seg * seg_ants;
+        uint32_t wd[MPP_PHER_SRU];
+#pragma unroll
+        for (int u = 0; u < MPP_PHER_SRU; ++u) {
+            const int a = a_base + u * 32 + lane;
+            wd[u] = (a < seg_ants) ? row[a] : 0u;
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < MPP_PHER_SRU; ++u) cnt += __popc(__ballot_sync(0xffffffffu, wd[u] != 0u));
+        if (lane == 0) s_cnt[buf][wid] = cnt;
+        double dv[MPP_PHER_SRU];                             // deposits of the hits: all loads in flight before the barrier
+#pragma unroll
+        for (int u = 0; u < MPP_PHER_SRU; ++u) {
+            dv[u] = 0.0;
+            if (wd[u] != 0u) {
+                const int a = a_base + u * 32 + lane;
+                dv[u] = dep[a];
+                if (clear_visit) row[a] = 0u;
+            }
+        }
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = s_cnt[buf][k];
+            if (k < wid) off += c;
+            total += c;
+        }
+        if (total <= MPP_PHER_CAP) {
+            int o = off;
+#pragma unroll
+            for (int u = 0; u < MPP_PHER_SRU; ++u) {
+                const uint32_t nz = __ballot_sync(0xffffffffu, wd[u] != 0u);
+                if (wd[u] != 0u) {
+                    PherEntry e; e.d = dv[u]; e.w = wd[u]; e.pad = 0u;
+                    s_list[buf][o + __popc(nz & lt)] = e;
+                }
+                o += __popc(nz);
+            }
+            __syncthreads();
+            if (wid == 0) t = pher_fold_list(s_list[buf], total, lane, t);   // ants in index order :306
+        } else {
+            // crowded word: one warp's ants (<= 512 hits) at a time through the same list
+            for (int c = 0; c < 8; ++c) {
+                if (wid == c) {
+                    int o = 0;
+#pragma unroll
+                    for (int u = 0; u < MPP_PHER_SRU; ++u) {
+                        const uint32_t nz = __ballot_sync(0xffffffffu, wd[u] != 0u);
+                        if (wd[u] != 0u) {
+                            PherEntry e; e.d = dv[u]; e.w = wd[u]; e.pad = 0u;
+                            s_list[buf][o + __popc(nz & lt)] = e;
+                        }
+                        o += __popc(nz);
+                    }
+                }
+                __syncthreads();
+                if (wid == 0) t = pher_fold_list(s_list[buf], s_cnt[buf][c], lane, t);
+                __syncthreads();
+            }
+        }
+    }
+    if (wid == 0 && live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
+}
+
 // Sharded colony: one warp per (bitmap word, segment).  Every warp first streams its segment's words (no
 // dependency: this is the HBM-bound part and runs fully in parallel over words x segments), then receives
 // the 32 running cell values from the previous segment's warp through global memory (flag = launch epoch),
@@ -1412,7 +1526,12 @@ extern "C" int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t
     const int blocks = (n_words + warps_per_block - 1) / warps_per_block;
     static const bool use_chain = getenv("MPP_PHER_CHAIN") != nullptr;  // experimental: measured no gain on 8xB200
     static const bool use_warp = getenv("MPP_PHER_WARP") != nullptr;    // previous warp-per-word kernel
-    if (!use_chain && !use_warp) {
+    static const bool use_block = getenv("MPP_PHER_BLOCK") != nullptr;  // previous block-per-word kernel (1024-ant rounds)
+    if (!use_chain && !use_warp && !use_block) {
+        mpp_maaco_pheromone_sr_kernel<<<n_words, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
+            map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
+            word0, n_words, rho, state_dev, clear_visit);
+    } else if (!use_chain && !use_warp) {
         const size_t list_bytes = 2 * (size_t)MPP_PHER_ROUND * sizeof(PherEntry);
         static bool attr_set = false;
         if (!attr_set && list_bytes > 48 * 1024) {
