@@ -1,5 +1,6 @@
-// mpp_maaco.cu -- MAACO colony pass on B200: tour construction (one warp or one 8-lane
-// group per ant), order-dependent best tracking, and the atomics-free ordered pheromone update.
+// mpp_maaco.cu -- MAACO colony pass on B200: per-pass move ranking, tour construction (one thread per
+// ant by default; warp / 16- / 8-lane cooperative forms kept), order-dependent best tracking, and the
+// atomics-free ordered pheromone update.
 // Reference semantics: MAACO.py:58-91 (tables), :100-181 (filter), :197-262 (selection),
 // :278-302 (tour), :304-332 (pheromone), :343-358 (best tracking).
 #include <cmath>
@@ -365,19 +366,24 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2, thread-per-ant form.  One ant step is a serial chain (position -> tabu bits -> candidate set ->
-// selection -> position) and a colony pass lasts as long as its longest tour times the latency of that
-// chain, so the chain stays inside ONE thread (no shuffles / votes / warp reductions on it) and touches
-// only shared memory and one L2-resident ranking word:
-//   * tabu bits (:93-95) come from a 64x64-cell WINDOW of the ant's visited set kept in shared memory
-//     (toroidal: cell (r,c) -> row r&63, bit c&63).  A global store to a line evicts it from L1 (measured:
-//     tools/ubench/l1_store.cu, 123 -> 432 cycles per dependent load), so re-reading a bitmap the ant
-//     itself keeps writing costs an L2 round trip per step; the window never re-reads what it wrote.
-//     Every mark is also RED.OR'ed into the word-major visitT (what the pheromone update streams); when
-//     the ant comes within one cell of the window edge the window slides by one 32-cell tile and the warp
-//     reloads the entering tiles from visitT;
-//   * selection: the ranking word of (cell, previous move) when usable, else the literal rules on
-//     tau**alpha * eta'**beta (tour_select_slow);
+// K2, thread-per-ant form (default).  One ant step is a serial chain (position -> tabu bits -> candidate
+// set -> selection -> position) and a colony pass lasts as long as its longest tour times the latency of that
+// chain, so the chain stays inside ONE thread (no shuffles / votes / warp reductions on it) and touches only
+// shared memory; a lone warp issues about one instruction per 5 cycles here, so what counts is the number of
+// instructions on the chain and every exposed memory latency (profiles/r01_tour1_summary.md):
+//   * tabu bits (:93-95) come from a 64x64-cell WINDOW of the ant's visited set in shared memory (rows of two
+//     words; the ant stays at least U cells inside it).  A global store to a line evicts it from L1 (measured:
+//     tools/ubench/l1_store.cu, 123 -> 432 cycles per dependent load), so re-reading a bitmap the ant itself
+//     keeps writing costs an L2 round trip per step wherever it lives in global memory.  When the ant reaches
+//     the window's edge the window slides by one 32-cell tile: the warp writes the leaving tile to the
+//     word-major visitT (what the pheromone update streams) and reloads the entering one from there; the four
+//     tiles still in the window are written at the end of the tour;
+//   * strategy 1 (:165, almost every step): the strategy-1 word of (cell, previous move) from mpp_maaco_rank
+//     -- static move mask + what greedy selection keeps of every subset of P1's three moves -- plus the
+//     precomputed greedy flag / floor(u1*n) of the step index one shared-memory table row that yields the move
+//     and all its deltas.  The words of the three possible next cells are prefetched one step ahead;
+//   * every other step (no strategy-1 candidate, P1 without three moves, a cell whose attractiveness is not
+//     tiny): all eight moves, strategies 2/3, the full ranking entry or the literal rules (tour_select_slow);
 //   * the warp's lanes generate Philox blocks together: lane L makes the block of ant L%apw, step s+L/apw.
 // `apw` lanes of each warp own an ant: fewer ants per warp = more warps to spread over the SMs.
 // ---------------------------------------------------------------------------------------------
@@ -928,7 +934,7 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
 // ---------------------------------------------------------------------------------------------
 // K2a: per (cell, turn context) ranking of the 8 moves by attractiveness tau**alpha * eta'**beta (MAACO.py:238).
 // With beta = 7 the values are ~1e-8..1e-20, so the selection rules (:241-262) only depend on their ORDER
-// (|attr_i - max| < 1e-9 and sum < 1e-9 always hold); the tour kernel then needs one 4-byte word per step
+// (|attr_i - max| < 1e-9 and sum < 1e-9 always hold); the tour kernels then need one or two words per step
 // instead of 16 fp64 loads.  Context 0 = no previous move (turn flag 0 for every candidate, :185-186),
 // context p+1 = previous move p (turn flag = (m != p)).  Entry = two words.  Word 1: [31:24] static move mask,
 // [23:0] rank position of each move (0 = largest attractiveness, ties -> lower move index, exactly the order the
@@ -1258,7 +1264,7 @@ mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, i
     if (live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
 }
 
-// Block-per-word variant (default): 8 warps scan 1024 ants per round for nonzero words and compact the hits
+// Block-per-word variant (MPP_PHER_BLOCK; the default before the super-round kernel): 8 warps scan 1024 ants per round for nonzero words and compact the hits
 // -- (deposit, word) in ant order -- into shared memory, double buffered; warp 0 then folds only the hits.
 // The streaming / zero-skipping (HBM-bound) is spread over 8 warps per word and overlapped with the fold, and
 // the sequential part is proportional to the number of ants that actually visited the word.
