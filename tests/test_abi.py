@@ -28,6 +28,26 @@ def test_library_exports_every_declared_symbol():
     assert not unbound, f"declared in mpp.h but not bound in _lib.py: {unbound}"
 
 
+def header_prototypes():
+    """name -> number of parameters, parsed from include/mpp.h."""
+    src = open(os.path.join(ROOT, "include", "mpp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(mpp_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_ctypes_signatures_match_header_arity():
+    """Every binding in _lib.py passes exactly as many arguments as the prototype in mpp.h takes (a stale
+    binding would shift every later argument and still load)."""
+    from maaco_path_planing_b200 import _lib
+    protos = header_prototypes()
+    bad = {n: (len(sig[1]), protos.get(n)) for n, sig in _lib._SIGS.items() if protos.get(n) != len(sig[1])}
+    assert not bad, f"(ctypes argtypes, header parameters) differ: {bad}"
+
+
 def test_abi_version_and_error_string():
     from maaco_path_planing_b200 import _lib
     L = _lib.lib()
