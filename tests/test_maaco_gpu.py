@@ -131,6 +131,21 @@ def test_lane_layouts_agree():
         assert np.array_equal(outs[0][1], other[1])
 
 
+def test_large_unaligned_map_vs_oracle():
+    """1000 columns (not a multiple of 32: window words straddle bitmap words, write-back by atomics) and tours of
+    ~1800 steps: dozens of window slides per ant in every direction."""
+    from maaco_path_planing_b200 import MAACO, blocks_map
+    import pyoracle as O
+    g = blocks_map(1000, 0.2, seed=2003)
+    N = 512
+    dev = MAACO(g, N, 2, rng_seed=3, verbose=False, **MAACO_DEFAULT)
+    orc = O.MaacoOracle(g, N, 2, seed=3, threads=0, **MAACO_DEFAULT)
+    for it in (1, 2):
+        _check_pass(dev, orc, it, N)
+    nc = dev.last_tours()[0]
+    assert (nc > 0).sum() > N // 2 and nc.max() > 1200
+
+
 def test_ants_per_warp_and_table_modes_agree(monkeypatch):
     """The thread-per-ant kernel gives the same colony for every packing of ants into warps, and the
     table-free path (use_rank=False: literal selection rules at every step) is the same function."""
