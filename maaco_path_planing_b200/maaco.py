@@ -4,6 +4,15 @@
 Same constructor arguments, attributes and return values as the reference; additive keyword-only
 arguments select the RNG stream seed, the device and the (optional) ``torch.distributed`` group
 over which the colony is sharded.  No CPU fallback: without libmpp_b200.so or a B200 this raises.
+
+Keyword-only additions (none changes a result; every combination is bit-identical, see tests/test_maaco_gpu.py):
+  rng_seed        seed of the Philox streams; None = from os.urandom
+  device, group   CUDA device index; torch.distributed group to shard the colony over
+  exchange        "moves" (default) or "dense": how a sharded colony ships its tours between ranks
+  use_rank        per-pass move-ranking tables (mpp_maaco_rank); False = literal selection rules at every step
+  lanes_per_ant   tour kernel form: 0 = library default (one thread per ant), 8 / 16 / 32 = cooperative lanes
+  ants_per_warp   packing hint for the thread-per-ant kernel when several colonies share the GPU (batch.py)
+  max_cells       capacity of the per-ant path buffers (default rows*cols)
 """
 from __future__ import annotations
 
