@@ -281,9 +281,31 @@ def dijkstra_cases(n_cases=120):
     print("dijkstra cases", n_cases)
 
 
+def maaco_extra_cases():
+    """Orientations other than start-top-left / target-bottom-right: a start and target on one row (the
+    orientation filter MAACO.py:146-157 then leaves five moves, not three) and a target up-left of the start
+    behind walls with gaps (other quadrant; dead ends force strategies 2 and 3, :169-180)."""
+    row = np.zeros((14, 30), int)
+    row[3:11, 12] = 1
+    row[0:6, 20] = 1
+    row[8:14, 24] = 1
+    row[7, 0], row[7, 29] = 2, 3
+    maaco_case("aligned_row", row, 24, 5, 107, MAACO_DEFAULT)
+    rev = H.blocks_map(0, 0.18, 21, rows=40, cols=70)
+    rev[rev == 2] = 0
+    rev[rev == 3] = 0
+    rev[20, 10:60] = 1
+    rev[20, 33:36] = 0
+    rev[39, 69], rev[0, 0] = 2, 3
+    maaco_case("reverse_diag", rev, 32, 4, 108, MAACO_DEFAULT)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "dijkstra":
         dijkstra_cases()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "maaco_extra":
+        maaco_extra_cases()
         return
     dijkstra_cases()
     solver_cases()
@@ -302,6 +324,7 @@ def main():
     maaco_case("near_alpha2", near, 24, 4, 105, dict(MAACO_DEFAULT, beta=1.5, alpha=2.0, Q=50.0))
     rect = H.blocks_map(0, 0.15, 9, rows=24, cols=40)
     maaco_case("rect24x40", rect, 16, 4, 106, MAACO_DEFAULT)
+    maaco_extra_cases()
 
 
 if __name__ == "__main__":
