@@ -520,15 +520,6 @@ struct Tour1Move {          // one per move (order MAACO.py:98)
 #define T1_RNG_OFF (4096 + 256 + 512)       // per warp: double2 u[32] (512 B) + uint32 pack[32] (128 B)
 #define T1_WIN_OFF (T1_RNG_OFF + (MPP_TOUR1_THREADS / 32) * 640)
 
-__device__ __forceinline__ uint32_t t1_orient_mask(int dR, int dC) {   // MAACO.py:146-157
-    uint32_t k = 0xffu;
-    if (dC > 0) k &= ~0x29u;
-    if (dC < 0) k &= ~0x94u;
-    if (dR > 0) k &= ~0x07u;
-    if (dR < 0) k &= ~0xE0u;
-    return k;
-}
-
 __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(const TourArgs A, const int apw) {
     extern __shared__ __align__(16) uint8_t t1_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
