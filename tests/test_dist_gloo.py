@@ -85,6 +85,14 @@ def _worker(rank, world, port, ret):
             mine.tau[:] = tau_full.numpy()[:n]
             assert np.array_equal(mine.tau, full.tau), f"rank {rank}: tau differs after pass {it}"
             assert mine.best_len == full.best_len and mine.best_turns == full.best_turns
+        # independent maps (config 5) are sharded by contiguous index ranges that cover every map exactly once
+        from maaco_path_planing_b200.batch import shard_maps
+        for n_maps in (1, 5, 48):
+            lo_m, hi_m = shard_maps(n_maps, dist.group.WORLD)
+            owned = torch.zeros(n_maps, dtype=torch.int64)
+            owned[lo_m:hi_m] = 1
+            dist.all_reduce(owned)
+            assert bool((owned == 1).all()), f"maps not covered exactly once: {owned.tolist()}"
         ret[rank] = True
     finally:
         dist.destroy_process_group()
@@ -106,3 +114,5 @@ def test_shard_helpers():
     with pytest.raises(ValueError):
         dm.shard_range(10, 4, 0)
     assert dm.padded_words(512 * 512, 8) == 8192 and dm.padded_words(20 * 20, 8) == 16
+    from maaco_path_planing_b200.batch import shard_maps
+    assert shard_maps(7) == (0, 7)
