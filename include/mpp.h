@@ -186,8 +186,9 @@ typedef struct {
 } mpp_policy;
 
 /* replaces calculate_path_safety_penalty's O(len x n_obstacles) scan (helper.py:67-80) by a per-cell class
- * table (min squared distance to an obstacle within floor(msd)) + a 256-entry LUT of (msd - d)**2 evaluated
- * with libm on the host.  Cached in the map for one msd at a time; called implicitly by the stats entry points. */
+ * table (u16: min squared distance to an obstacle within floor(msd)) + a LUT of (msd - d)**2 per class, evaluated
+ * with libm on the host.  0 <= msd <= 180 (u16 classes).  Cached in the map for one msd at a time; called
+ * implicitly by the stats entry points. */
 int mpp_map_safety_table(mpp_map *map, double min_safe_distance, void *stream);
 
 /* replaces helper.calculate_path_stats (helper.py:98-113; count_turns :58-65, safety :67-80, diagonal

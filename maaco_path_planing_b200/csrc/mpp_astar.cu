@@ -2,6 +2,7 @@
 // Reference semantics: astar.py:33-101, MPA.py:106-151, helper.py:58-113, MPA.py:176-229,
 // pso.py:56-94, ga_solver.py:58-93.
 #include <cmath>
+#include <vector>
 
 #include "mpp_astar.cuh"
 #include "mpp_stats.cuh"
@@ -11,12 +12,13 @@
 
 // ---------------------------------------------------------------------------------------------
 // K1b: safety-class table (helper.py:67-80 as a per-cell function of the map)
-//   class[cell] = min squared distance to an obstacle within radius floor(msd), capped at 255; 0 = none.
+//   class[cell] = min squared distance to an obstacle within the (2*radius+1)^2 stencil, radius = floor(msd); 0 = none.
 //   lut[d2]     = (msd - sqrt(d2))**2 if sqrt(d2) < msd else 0   -- evaluated on the host with libm pow.
+// Only obstacles nearer than msd contribute (helper.py:76), and those lie inside the stencil.
 // Out-of-bounds is NOT an obstacle here (obstacle_nodes = argwhere(grid == 1), helper.py:125).
 // ---------------------------------------------------------------------------------------------
 __global__ void mpp_safety_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, int radius,
-                                  uint8_t *__restrict__ cls) {
+                                  uint16_t *__restrict__ cls) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R * C) return;
     const int r = i / C, c = i % C;
@@ -34,27 +36,33 @@ __global__ void mpp_safety_kernel(const uint32_t *__restrict__ occ, int pitch, i
             }
         }
     }
-    cls[i] = (best == (1 << 30)) ? 0 : (uint8_t)(best > 255 ? 255 : best);
+    cls[i] = (best == (1 << 30)) ? 0 : (uint16_t)best;          // best <= 2*radius^2 < 65536 (radius <= 180)
 }
 
 extern "C" int mpp_map_safety_table(mpp_map *map, double msd, void *stream) {
     MPP_REQUIRE(map, "mpp_map_safety_table: null map");
-    MPP_REQUIRE(msd >= 0.0 && msd < 15.9, "mpp_map_safety_table: min_safe_distance %g unsupported (0 <= msd < 15.9)", msd);
+    MPP_REQUIRE(msd >= 0.0 && msd <= 180.0, "mpp_map_safety_table: min_safe_distance %g unsupported (0 <= msd <= 180)", msd);
     if (map->safety_msd == msd && map->safety_d2_dev) return MPP_OK;
     MPP_CUDA(cudaSetDevice(map->device));
     const int n = map->rows * map->cols;
-    if (!map->safety_d2_dev) MPP_CUDA(cudaMalloc(&map->safety_d2_dev, (size_t)n));
-    if (!map->safety_lut_dev) MPP_CUDA(cudaMalloc(&map->safety_lut_dev, 256 * sizeof(double)));
-    double lut[256];
-    lut[0] = 0.0;
-    for (int d2 = 1; d2 < 256; ++d2) {
+    const int radius = (int)msd;                               // an obstacle nearer than msd has |dr|, |dc| <= floor(msd)
+    const int lut_n = 2 * radius * radius + 2;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!map->safety_d2_dev) MPP_CUDA(cudaMalloc(&map->safety_d2_dev, (size_t)n * sizeof(uint16_t)));
+    if (map->safety_lut_n < lut_n) {
+        MPP_CUDA(cudaStreamSynchronize(s));                     // a kernel of an earlier call may still read the old table
+        if (map->safety_lut_dev) MPP_CUDA(cudaFree(map->safety_lut_dev));
+        map->safety_lut_dev = nullptr;
+        MPP_CUDA(cudaMalloc(&map->safety_lut_dev, (size_t)lut_n * sizeof(double)));
+        map->safety_lut_n = lut_n;
+    }
+    std::vector<double> lut((size_t)lut_n, 0.0);
+    for (int d2 = 1; d2 < lut_n; ++d2) {
         const double d = std::sqrt((double)d2);
         lut[d2] = (d < msd) ? std::pow(msd - d, 2.0) : 0.0;     // helper.py:77-78 (float ** 2 -> libm pow)
     }
-    cudaStream_t s = (cudaStream_t)stream;
-    MPP_CUDA(cudaMemcpyAsync(map->safety_lut_dev, lut, sizeof(lut), cudaMemcpyHostToDevice, s));
+    MPP_CUDA(cudaMemcpyAsync(map->safety_lut_dev, lut.data(), (size_t)lut_n * sizeof(double), cudaMemcpyHostToDevice, s));
     MPP_CUDA(cudaStreamSynchronize(s));
-    const int radius = (int)msd;
     mpp_safety_kernel<<<(n + 255) / 256, 256, 0, s>>>(map->occ_dev, map->pitch_words, map->rows, map->cols, radius,
                                                       map->safety_d2_dev);
     MPP_CUDA(cudaGetLastError());
@@ -155,6 +163,9 @@ __global__ void __launch_bounds__(MPP_AS_THREADS, 3) mpp_astar_batch_kernel(Batc
 }
 
 static int check_scratch(const mpp_map *map, size_t scratch_bytes, int n_slots, int heap_cap) {
+    // the searches pack a node as (row << 16 | col) in a signed int (same (r, c) order as the reference's tuples)
+    MPP_REQUIRE(map->rows < 32768 && map->cols < 65536, "A*: map %dx%d exceeds the packed-node limit (rows < 32768, cols < 65536)",
+                map->rows, map->cols);
     MPP_REQUIRE(n_slots > 0 && heap_cap >= 64, "A*: n_slots=%d heap_cap=%d", n_slots, heap_cap);
     MPP_REQUIRE(scratch_bytes >= mpp_astar_scratch_bytes(map, n_slots, heap_cap),
                 "A*: scratch too small (%zu < %zu)", scratch_bytes, mpp_astar_scratch_bytes(map, n_slots, heap_cap));

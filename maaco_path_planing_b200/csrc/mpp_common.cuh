@@ -43,15 +43,11 @@ struct mpp_map {
     uint8_t *grid_host;     // host copy of the caller's grid (rows*cols) for host-side table builds
     int n_obstacles;
     int sm_count;
-    // safety-class cache (helper.py:67-80): per cell min d^2 to an obstacle if < 256 else 0
+    // safety-class cache (helper.py:67-80): per cell min d^2 to an obstacle inside the (2*floor(msd)+1)^2 stencil, 0 = none
     double safety_msd;      // msd the table was built for (<0 = none)
-    uint8_t *safety_d2_dev; // rows*cols
-    double *safety_lut_dev; // 256 doubles: penalty contribution for class d^2
-    // hand-over scratch of the chained (sharded-colony) pheromone update
-    double *chain_tbuf;
-    uint32_t *chain_flags;
-    size_t chain_cap;
-    uint32_t chain_epoch;
+    uint16_t *safety_d2_dev; // rows*cols
+    double *safety_lut_dev; // safety_lut_n doubles: penalty contribution for class d^2
+    int safety_lut_n;
 };
 
 int mpp_check_device(int device);

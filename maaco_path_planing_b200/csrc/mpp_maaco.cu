@@ -1158,64 +1158,6 @@ extern "C" int mpp_maaco_best(const mpp_ant_result *result_dev, const int32_t *c
 #define MPP_PHER_THREADS 256
 struct __align__(16) PherEntry { double d; uint32_t w; uint32_t pad; };
 
-// Fold the deposits of one segment's ants (index order) into this lane's cell.  row = that segment's words of
-// this warp's bitmap word ([seg_ants] uint32), dep = its deposits.
-__device__ __forceinline__ double pher_fold_segment(uint32_t *__restrict__ row, const double *__restrict__ dep,
-                                                    int n_ants, int lane, PherEntry *sb, double t, int clear_visit) {
-    // software pipeline: the next 128 ants' words are in flight while the current ones are folded
-    uint32_t nx[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int a = u * 32 + lane; nx[u] = (a < n_ants) ? row[a] : 0u; }
-    for (int a0 = 0; a0 < n_ants; a0 += 128) {
-        uint32_t wd[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) wd[u] = nx[u];
-        if (a0 + 128 < n_ants) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { const int a = a0 + 128 + u * 32 + lane; nx[u] = (a < n_ants) ? row[a] : 0u; }
-        }
-        uint32_t nz[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) nz[u] = __ballot_sync(0xffffffffu, wd[u] != 0u);
-        if ((nz[0] | nz[1] | nz[2] | nz[3]) == 0u) continue;             // ~92 % of the words
-        double d[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {                                    // deposits of the chunks that need them
-            const int a = a0 + u * 32 + lane;
-            d[u] = (nz[u] && a < n_ants) ? dep[a] : 0.0;
-            if (clear_visit && wd[u] != 0u) row[a] = 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            uint32_t m = nz[u];
-            if (!m) continue;
-            if (__popc(m) >= 6) {
-                // dense word (cells near S/T are visited by most ants): stage (deposit, word) of the 32
-                // ants in shared memory and walk them in index order with broadcast reads; what remains
-                // is the dependent DADD chain.  t + 0.0 == t exactly, so non-depositing ants are harmless.
-                __syncwarp();
-                PherEntry e; e.d = d[u]; e.w = wd[u]; e.pad = 0u;
-                sb[lane] = e;
-                __syncwarp();
-#pragma unroll 8
-                for (int l = 0; l < 32; ++l) {
-                    const PherEntry x = sb[l];
-                    if ((x.w >> lane) & 1u) t += x.d;                    // :311
-                }
-            } else {
-                while (m) {                                              // ants in index order :306
-                    const int l = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t wv = __shfl_sync(0xffffffffu, wd[u], l);
-                    const double dv = __shfl_sync(0xffffffffu, d[u], l);
-                    if ((wv >> lane) & 1u) t += dv;                      // :311
-                }
-            }
-        }
-    }
-    return t;
-}
-
 // MMAS clip + obstacle reset (MAACO.py:312-332) for one cell
 __device__ __forceinline__ double pher_finalize(double t, int cell, const uint32_t *occ, int pitch, int R, int C,
                                                 double rho, const mpp_maaco_state *state) {
@@ -1233,118 +1175,7 @@ __device__ __forceinline__ double pher_finalize(double t, int cell, const uint32
     return t < tmax ? t : tmax;
 }
 
-__global__ void __launch_bounds__(MPP_PHER_THREADS)
-mpp_maaco_pheromone_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
-                           uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg, int seg_ants,
-                           int word0, int n_words, double rho, const mpp_maaco_state *__restrict__ state,
-                           int clear_visit) {
-    // visitT is [n_seg][n_words][seg_ants]; global ant = seg*seg_ants + a; this launch owns the
-    // cells of words [word0, word0 + n_words)
-    __shared__ PherEntry s_buf[MPP_PHER_THREADS / 32][32];
-    const int lane = threadIdx.x & 31;
-    const int wl = (blockIdx.x * MPP_PHER_THREADS + threadIdx.x) >> 5;
-    if (wl >= n_words) return;
-    PherEntry *sb = s_buf[threadIdx.x >> 5];
-    const int cell = (word0 + wl) * 32 + lane;
-    const bool live = cell < R * C;
-    double t = 0.0;
-    if (live) t = tau[cell] * (1.0 - rho);                                   // :305
-    for (int seg = 0; seg < n_seg; ++seg)
-        t = pher_fold_segment(visitT + ((size_t)seg * n_words + wl) * seg_ants, deposit + (size_t)seg * seg_ants,
-                              seg_ants, lane, sb, t, clear_visit);
-    if (live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
-}
-
-// Block-per-word variant (MPP_PHER_BLOCK; the default before the super-round kernel): 8 warps scan 1024 ants per round for nonzero words and compact the hits
-// -- (deposit, word) in ant order -- into shared memory, double buffered; warp 0 then folds only the hits.
-// The streaming / zero-skipping (HBM-bound) is spread over 8 warps per word and overlapped with the fold, and
-// the sequential part is proportional to the number of ants that actually visited the word.
-#ifndef MPP_PHER_ROUND
-#define MPP_PHER_ROUND 1024
-#endif
-#define MPP_PHER_PW (MPP_PHER_ROUND / 8)   // ants per warp per round
-#define MPP_PHER_U (MPP_PHER_PW / 32)     // loads per lane per round
-__global__ void __launch_bounds__(MPP_PHER_THREADS)
-mpp_maaco_pheromone_block_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
-                                 uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg,
-                                 int seg_ants, int word0, int n_words, double rho,
-                                 const mpp_maaco_state *__restrict__ state, int clear_visit) {
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    PherEntry (*s_list)[MPP_PHER_ROUND] = reinterpret_cast<PherEntry (*)[MPP_PHER_ROUND]>(s_dyn);  // [2][ROUND]; warp k owns [PW*k, PW*(k+1))
-    __shared__ int s_cnt[2][8];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int wl = blockIdx.x;                               // one bitmap word (32 cells) per block
-    const int cell = (word0 + wl) * 32 + lane;
-    const bool live = cell < R * C;
-    double t = 0.0;
-    if (wid == 0 && live) t = tau[cell] * (1.0 - rho);       // :305
-    const int rounds_per_seg = (seg_ants + MPP_PHER_ROUND - 1) / MPP_PHER_ROUND;
-    const int n_rounds = n_seg * rounds_per_seg;
-    // the words of round r+1 are loaded while round r is compacted (one DRAM latency per round otherwise)
-    auto load_round = [&](int r, uint32_t (&v)[MPP_PHER_U]) {
-        const int seg = r / rounds_per_seg, a_base = (r % rounds_per_seg) * MPP_PHER_ROUND + wid * MPP_PHER_PW;
-        const uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
-#pragma unroll
-        for (int u = 0; u < MPP_PHER_U; ++u) { const int a = a_base + u * 32 + lane; v[u] = (a < seg_ants) ? row[a] : 0u; }
-    };
-    uint32_t nx[MPP_PHER_U] = {};
-    if (n_rounds > 0) load_round(0, nx);
-    for (int r = 0; r <= n_rounds; ++r) {
-        const int buf = r & 1;
-        if (r < n_rounds) {
-            // ---- produce round r: this warp's MPP_PHER_PW ants ----
-            const int seg = r / rounds_per_seg, a_base = (r % rounds_per_seg) * MPP_PHER_ROUND + wid * MPP_PHER_PW;
-            uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
-            const double *dep = deposit + (size_t)seg * seg_ants;
-            uint32_t wd[MPP_PHER_U];
-#pragma unroll
-            for (int u = 0; u < MPP_PHER_U; ++u) wd[u] = nx[u];
-            if (r + 1 < n_rounds) load_round(r + 1, nx);
-            int cnt = 0;
-#pragma unroll
-            for (int u = 0; u < MPP_PHER_U; ++u) {
-                const uint32_t nz = __ballot_sync(0xffffffffu, wd[u] != 0u);
-                if (wd[u] != 0u) {
-                    const int a = a_base + u * 32 + lane;
-                    PherEntry e; e.d = dep[a]; e.w = wd[u]; e.pad = 0u;
-                    s_list[buf][wid * MPP_PHER_PW + cnt + __popc(nz & ((1u << lane) - 1u))] = e;
-                    if (clear_visit) row[a] = 0u;
-                }
-                cnt += __popc(nz);
-            }
-            if (lane == 0) s_cnt[buf][wid] = cnt;
-        }
-        if (r > 0 && wid == 0) {
-            // ---- consume round r-1 (filled before the previous barrier): ants in index order :306 ----
-            const int pb = buf ^ 1;
-#pragma unroll 1
-            for (int k = 0; k < 8; ++k) {
-                const int n = s_cnt[pb][k];
-                const PherEntry *lst = &s_list[pb][k * MPP_PHER_PW];
-                int i = 0;
-                for (; i + 4 <= n; i += 4) {
-                    // select the operand, not the sum: the loop-carried chain is a bare DADD (t + 0.0 == t exactly)
-                    const PherEntry x0 = lst[i], x1 = lst[i + 1], x2 = lst[i + 2], x3 = lst[i + 3];
-                    const double a0 = ((x0.w >> lane) & 1u) ? x0.d : 0.0, a1 = ((x1.w >> lane) & 1u) ? x1.d : 0.0;
-                    const double a2 = ((x2.w >> lane) & 1u) ? x2.d : 0.0, a3 = ((x3.w >> lane) & 1u) ? x3.d : 0.0;
-                    t += a0;                                                 // :311
-                    t += a1;
-                    t += a2;
-                    t += a3;
-                }
-                for (; i < n; ++i) {
-                    const PherEntry x = lst[i];
-                    t += ((x.w >> lane) & 1u) ? x.d : 0.0;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (wid == 0 && live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
-}
-
-// Super-round variant (default).  What bounded the block-per-word kernel above was not bandwidth but one DRAM round
-// trip per 1024-ant round (ncu: half of all stalls at the round barrier): here a block issues the loads of 4096 ants
+// One CTA per bitmap word.  A block issues the loads of 4096 ants
 // (16 words per lane) at once, so a word costs ONE round trip.  The hits -- typically a few dozen per word -- are
 // compacted in ant order into a small list (warp-count prefix over shared memory) that warp 0 folds; words with more
 // hits than the list holds (around the start cell) fall back to one warp's 512 ants at a time.
@@ -1457,109 +1288,15 @@ mpp_maaco_pheromone_sr_kernel(const uint32_t *__restrict__ occ, int pitch, int R
     if (wid == 0 && live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
 }
 
-// Sharded colony: one warp per (bitmap word, segment).  Every warp first streams its segment's words (no
-// dependency: this is the HBM-bound part and runs fully in parallel over words x segments), then receives
-// the 32 running cell values from the previous segment's warp through global memory (flag = launch epoch),
-// folds its own ants in order and hands over.  Blocks are ordered segment-major, so a warp only ever waits
-// for a block with a lower index (already dispatched).  The fold order per cell is the global ant order.
-__global__ void __launch_bounds__(MPP_PHER_THREADS)
-mpp_maaco_pheromone_chain_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
-                                 uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg,
-                                 int seg_ants, int word0, int n_words, double rho,
-                                 const mpp_maaco_state *__restrict__ state, int clear_visit, double *tbuf,
-                                 volatile uint32_t *flags, uint32_t epoch) {
-    __shared__ PherEntry s_buf[MPP_PHER_THREADS / 32][32];
-    const int lane = threadIdx.x & 31;
-    const int wpb = MPP_PHER_THREADS / 32;
-    const int wb_count = (n_words + wpb - 1) / wpb;
-    const int seg = blockIdx.x / wb_count;
-    const int wl = (blockIdx.x % wb_count) * wpb + (threadIdx.x >> 5);
-    if (wl >= n_words) return;
-    PherEntry *sb = s_buf[threadIdx.x >> 5];
-    const int cell = (word0 + wl) * 32 + lane;
-    const bool live = cell < R * C;
-    uint32_t *row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
-    // phase 1: does this segment touch the word at all?  (also pulls the row into L2 for the fold)
-    uint32_t any = 0u;
-    for (int a0 = 0; a0 < seg_ants; a0 += 256) {
-        uint32_t v = 0u;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const int a = a0 + u * 32 + lane; if (a < seg_ants) v |= row[a]; }
-        any |= v;
-    }
-    any = __ballot_sync(0xffffffffu, any != 0u);
-    // phase 2: running values from the previous segment
-    double t = 0.0;
-    if (seg == 0) {
-        if (live) t = tau[cell] * (1.0 - rho);                               // :305
-    } else {
-        const size_t prev = (size_t)(seg - 1) * n_words + wl;
-        if (lane == 0) while (flags[prev] != epoch) __nanosleep(64);
-        __syncwarp();
-        __threadfence();
-        t = __ldcg(tbuf + prev * 32 + lane);
-    }
-    // phase 3: this segment's ants in index order
-    if (any) t = pher_fold_segment(row, deposit + (size_t)seg * seg_ants, seg_ants, lane, sb, t, clear_visit);
-    // phase 4: hand over / finish
-    if (seg == n_seg - 1) {
-        if (live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
-    } else {
-        const size_t me = (size_t)seg * n_words + wl;
-        __stcg(tbuf + me * 32 + lane, t);
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) flags[me] = epoch;
-    }
-}
-
 extern "C" int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t *visitT_dev,
                                    const double *deposit_dev, int n_seg, int seg_ants, int word0, int n_words,
                                    double rho, const mpp_maaco_state *state_dev, int clear_visit, void *stream) {
     MPP_REQUIRE(map && tau_dev && visitT_dev && deposit_dev && state_dev, "mpp_maaco_pheromone: null argument");
     MPP_REQUIRE(n_seg > 0 && seg_ants > 0 && word0 >= 0 && n_words > 0, "mpp_maaco_pheromone: bad shape");
     MPP_CUDA(cudaSetDevice(map->device));
-    const int warps_per_block = MPP_PHER_THREADS / 32;
-    const int blocks = (n_words + warps_per_block - 1) / warps_per_block;
-    static const bool use_chain = getenv("MPP_PHER_CHAIN") != nullptr;  // experimental: measured no gain on 8xB200
-    static const bool use_warp = getenv("MPP_PHER_WARP") != nullptr;    // previous warp-per-word kernel
-    static const bool use_block = getenv("MPP_PHER_BLOCK") != nullptr;  // previous block-per-word kernel (1024-ant rounds)
-    if (!use_chain && !use_warp && !use_block) {
-        mpp_maaco_pheromone_sr_kernel<<<n_words, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
-            map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
-            word0, n_words, rho, state_dev, clear_visit);
-    } else if (!use_chain && !use_warp) {
-        const size_t list_bytes = 2 * (size_t)MPP_PHER_ROUND * sizeof(PherEntry);
-        static bool attr_set = false;
-        if (!attr_set && list_bytes > 48 * 1024) {
-            MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_pheromone_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)list_bytes));
-            attr_set = true;
-        }
-        mpp_maaco_pheromone_block_kernel<<<n_words, MPP_PHER_THREADS, list_bytes, (cudaStream_t)stream>>>(
-            map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
-            word0, n_words, rho, state_dev, clear_visit);
-    } else if (n_seg == 1 || !use_chain) {
-        mpp_maaco_pheromone_kernel<<<blocks, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
-            map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
-            word0, n_words, rho, state_dev, clear_visit);
-    } else {
-        // chained (word, segment) warps: scratch for the hand-over values + epoch flags lives in the map handle
-        mpp_map *m = const_cast<mpp_map *>(map);
-        const size_t need = (size_t)(n_seg - 1) * n_words;
-        if (m->chain_cap < need) {
-            if (m->chain_tbuf) { MPP_CUDA(cudaFree(m->chain_tbuf)); MPP_CUDA(cudaFree(m->chain_flags)); }
-            MPP_CUDA(cudaMalloc(&m->chain_tbuf, need * 32 * sizeof(double)));
-            MPP_CUDA(cudaMalloc(&m->chain_flags, need * sizeof(uint32_t)));
-            MPP_CUDA(cudaMemset(m->chain_flags, 0, need * sizeof(uint32_t)));
-            m->chain_cap = need;
-            m->chain_epoch = 0;
-        }
-        m->chain_epoch += 1;
-        mpp_maaco_pheromone_chain_kernel<<<blocks * n_seg, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
-            map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
-            word0, n_words, rho, state_dev, clear_visit, m->chain_tbuf, m->chain_flags, m->chain_epoch);
-    }
+    mpp_maaco_pheromone_sr_kernel<<<n_words, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
+        map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
+        word0, n_words, rho, state_dev, clear_visit);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }

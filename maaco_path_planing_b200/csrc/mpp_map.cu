@@ -136,8 +136,6 @@ extern "C" void mpp_map_destroy(mpp_map *m) {
     if (m->svalid_dev) cudaFree(m->svalid_dev);
     if (m->safety_d2_dev) cudaFree(m->safety_d2_dev);
     if (m->safety_lut_dev) cudaFree(m->safety_lut_dev);
-    if (m->chain_tbuf) cudaFree(m->chain_tbuf);
-    if (m->chain_flags) cudaFree(m->chain_flags);
     free(m->grid_host);
     free(m);
 }

@@ -292,6 +292,8 @@ extern "C" int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_p
     MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_mpa_iteration: map has no start/target");
     MPP_REQUIRE(n_slots > 0 && heap_cap >= 64 && scratch_bytes >= mpp_astar_scratch_bytes(map, n_slots, heap_cap),
                 "mpp_mpa_iteration: scratch too small");
+    MPP_REQUIRE(map->rows < 32768 && map->cols < 65536, "mpp_mpa_iteration: map %dx%d exceeds the packed-node limit "
+                "(rows < 32768, cols < 65536)", map->rows, map->cols);
     MPP_CUDA(cudaSetDevice(map->device));
     cudaStream_t s = (cudaStream_t)stream;
     MpaArgs A;

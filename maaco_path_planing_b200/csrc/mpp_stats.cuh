@@ -9,7 +9,7 @@
 struct StatsCtx {
     const uint32_t *occ;
     int pitch, R, C;
-    const uint8_t *cls;     // safety classes (may be null when mode == 1 or spf table not needed)
+    const uint16_t *cls;    // safety classes (may be null when mode == 1 or spf table not needed)
     const double *lut;
     mpp_policy pol;
 };

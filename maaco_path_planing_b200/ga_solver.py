@@ -48,6 +48,7 @@ class GASolver(BasePathfinder):
         self.best_solution_overall = {'fitness': INF, 'path': []}
         self.fitness_evaluations = 0
         self._pop = None
+        self._fallback = None       # the single direct-path individual of ga_solver.py:111-117 (or the dummy of :123)
 
     # ---- reference-named single-individual helper ----------------------------------------------
     def _reconstruct_path_from_chromosome(self, chromosome):                # ga_solver.py:58-93
@@ -97,10 +98,22 @@ class GASolver(BasePathfinder):
                 n_acc += take.size
         self.init_attempts = attempts
         if n_acc == 0:
+            # ga_solver.py:111-117: ONE individual {chromosome: [], path: direct S->T path}; padding :129-130 copies it
             path_direct = self._reconstruct_path_from_chromosome([]) if W > 0 else []
             if path_direct and path_direct[0] == self.start_node and path_direct[-1] == self.target_node:
-                raise NotImplementedError("GA direct-path fallback individual (ga_solver.py:111-117) is not supported")
-            print("GA Error: Could not initialize any valid individuals.")
+                st = self._calculate_stats_for_path(path_direct)
+                ind = {'chromosome': [], 'path': list(path_direct), 'fitness': float(st[5]), 'length': float(st[1]),
+                       'turns': int(st[2]), 'safety_penalty': float(st[3]), 'diag_penalty': float(st[4])}
+                print("GA Warning: Population init failed, used a direct A* path as one individual.")
+                # Every later generation reproduces this individual: crossover of two empty chromosomes is empty
+                # (:144-152), _mutate returns [] (:155), and the child's path is the same direct path -- so the
+                # population is a fixed point and no kernel has anything to evaluate.
+                self._fallback = ind
+                return True
+            print("GA Error: Could not initialize any valid individuals.")            # :120-126
+            self._fallback = {'chromosome': [], 'path': [], 'fitness': INF, 'length': INF, 'turns': 0,
+                              'safety_penalty': 0, 'diag_penalty': 0}
+            self._fallback_failed = True
             return False
         mc = max(a[2].shape[1] for a in acc)
         pad = lambda c: c if c.shape[1] == mc else t.nn.functional.pad(c, (0, mc - c.shape[1]))
@@ -132,6 +145,8 @@ class GASolver(BasePathfinder):
 
     @property
     def population(self):
+        if self._fallback is not None:
+            return [dict(self._fallback) for _ in range(self.population_size)]
         return [] if self._pop is None else [self._individual(i) for i in range(self.population_size)]
 
     def _generation(self, gen):                                             # ga_solver.py:178-209
@@ -175,12 +190,13 @@ class GASolver(BasePathfinder):
         if not self._initialize_population():
             print("GA: Population initialization failed completely. Returning empty result.")
             return [], INF, 0, 0.0, 0.0, INF
-        self.best_solution_overall = self._individual(0)
+        self.best_solution_overall = dict(self._fallback) if self._fallback is not None else self._individual(0)
         self.convergence_curve.append(self.best_solution_overall['fitness'])
         for gen in range(self.num_generations):
-            self._generation(gen)
-            if float(self._pop["stats"][0, 4]) < self.best_solution_overall['fitness']:    # :211-213
-                self.best_solution_overall = self._individual(0)
+            if self._fallback is None:
+                self._generation(gen)
+                if float(self._pop["stats"][0, 4]) < self.best_solution_overall['fitness']:    # :211-213
+                    self.best_solution_overall = self._individual(0)
             self.convergence_curve.append(self.best_solution_overall['fitness'])
             if self.verbose and ((gen + 1) % 10 == 0 or gen == 0 or gen == self.num_generations - 1):
                 b = self.best_solution_overall

@@ -12,7 +12,8 @@ Keyword-only additions (none changes a result; every combination is bit-identica
   use_rank        per-pass move-ranking tables (mpp_maaco_rank); False = literal selection rules at every step
   lanes_per_ant   tour kernel form: 0 = library default (one thread per ant), 8 / 16 / 32 = cooperative lanes
   ants_per_warp   packing hint for the thread-per-ant kernel when several colonies share the GPU (batch.py)
-  max_cells       capacity of the per-ant path buffers (default rows*cols)
+  max_cells       capacity of the per-ant path buffers (default 8*(rows+cols); the solve repeats itself with rows*cols
+                  if the best path did not fit)
 """
 from __future__ import annotations
 
@@ -31,6 +32,11 @@ INF = float("inf")
 
 
 def _fresh_seed():
+    """Seed of a solver built without rng_seed=: fresh entropy, like the reference's never-seeded RNGs -- unless
+    MPP_RNG_SEED is set, which makes unmodified callers (the reference's main.py) reproducible."""
+    env = os.environ.get("MPP_RNG_SEED")
+    if env:
+        return int(env, 0)
     return int.from_bytes(os.urandom(8), "little")
 
 
@@ -43,6 +49,11 @@ class MAACO:
                  exchange="moves",
                  use_rank=True, verbose=True):
         import torch
+        self._ctor = dict(grid=grid, num_ants=num_ants, num_iterations=num_iterations, alpha=alpha, beta=beta, rho=rho,
+                          Q=Q, a_turn_coef=a_turn_coef, wh_max=wh_max, wh_min=wh_min, k_h_adaptive=k_h_adaptive,
+                          q0_initial=q0_initial, C0_initial_pheromone=C0_initial_pheromone, rng_seed=rng_seed,
+                          device=device, lanes_per_ant=lanes_per_ant, ants_per_warp=ants_per_warp, group=group,
+                          exchange=exchange, use_rank=use_rank, verbose=verbose)
         self.grid = np.array(grid, dtype=int)                       # MAACO.py:15
         self.rows, self.cols = self.grid.shape
         self.num_ants = num_ants
@@ -63,6 +74,7 @@ class MAACO:
         d = math.sqrt((self.start_node[0] - self.target_node[0]) ** 2 + (self.start_node[1] - self.target_node[1]) ** 2)
         self.dist_S_to_T_overall = d if d >= 1e-9 else 1e-9
         self.rng_seed = _fresh_seed() if rng_seed is None else int(rng_seed)
+        self._ctor["rng_seed"] = self.rng_seed
         self.verbose = verbose
         # ants_per_warp: hint for the thread-per-ant kernel when several colonies share the GPU (batch.py)
         self.lanes_per_ant = -int(ants_per_warp) if ants_per_warp and lanes_per_ant in (0, 1) else lanes_per_ant
@@ -88,10 +100,12 @@ class MAACO:
         n = self.rows * self.cols
         self.n_words = padded_words(n, self.world)                  # bitmap words per ant (padded to split evenly)
         self.words_per_rank = self.n_words // self.world
+        # per-ant path capacity: tours are a few (R+C) cells long (no backtracking, MAACO.py:278-302); a tour that
+        # outgrows the buffer is still constructed and counted exactly -- only its cell list is truncated -- and
+        # solve_path_planning() re-runs the (deterministic) solve with full capacity if the best path was cut
+        self._auto_cells = max_cells is None
         if max_cells is None:
-            max_cells = n
-            if self.n_local * n * 4 > (8 << 30):                    # keep the path buffer under 8 GiB
-                max_cells = max(1024, min(n, (8 << 30) // (4 * self.n_local)))
+            max_cells = min(n, max(1024, 8 * (self.rows + self.cols)))
         self.max_cells = int(max_cells)
         dev = self.device
         f64, i32, i64 = torch.float64, torch.int32, torch.int64
@@ -190,6 +204,8 @@ class MAACO:
         pheromone update, end[, after the ranking kernel]) on the launching stream -- used by bench.py for
         per-kernel timing."""
         import torch
+        if not 1 <= it <= max(1, self.num_iterations):               # the per-iteration log has num_iterations rows
+            raise ValueError(f"iteration {it} outside 1..{self.num_iterations}")
         cur = torch.cuda.current_stream(self.device)
         stream = C.c_void_p(cur.cuda_stream)
         if events:
@@ -255,12 +271,25 @@ class MAACO:
         torch.cuda.synchronize(self.device)
         self._iter_done = K
         st = self._read_state()
-        if self.world > 1 and self.exchange == "moves" and int(self._xstatus.item()) != 0:
-            raise _lib.MppError("a tour exceeded max_cells and could not be exchanged; re-run with a larger max_cells")
+        overflow = st.best_n_cells > self.max_cells
+        if self.world > 1:
+            import torch.distributed as dist
+            # every rank must take the same decision: the flag of the move-code exchange is rank-local
+            flag = torch.tensor([int(overflow) | (int(self._xstatus.item()) if self.exchange == "moves" else 0)],
+                                dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            overflow = bool(flag.item())
+        if overflow:
+            if not self._auto_cells or self.max_cells >= self.rows * self.cols:
+                raise _lib.MppError(f"a tour outgrew max_cells={self.max_cells} (best path: {st.best_n_cells} cells); "
+                                    "re-run with a larger max_cells")
+            # the solve is a deterministic function of (grid, parameters, seed): repeat it with full path capacity
+            again = MAACO(max_cells=self.rows * self.cols, **self._ctor)
+            launches = self.kernel_launches + again.kernel_launches
+            self.__dict__.update(again.__dict__)
+            self.kernel_launches = launches
+            return self.solve_path_planning()
         log = self._log.cpu().numpy().reshape(-1, 4)[:K]
-        if st.best_n_cells > self.max_cells:
-            raise _lib.MppError(f"best path has {st.best_n_cells} cells but max_cells={self.max_cells}; "
-                                "re-run with a larger max_cells")
         if self.world > 1 and st.best_n_cells > 0:
             import torch.distributed as dist
             owner = st.best_ant // self.n_local                     # rank that constructed the best ant
@@ -300,10 +329,13 @@ class MAACO:
         return rec["n_cells"].copy(), rec["length"].copy(), rec["turns"].copy()
 
     def last_tours(self):
-        """(n_cells, length, turns, cells[n_local, max_cells]) of this rank's ants in the last pass."""
+        """(n_cells, length, turns, cells[n_local, <= max_cells]) of this rank's ants in the last pass (only the
+        columns some tour reached are copied to the host)."""
         nc, ln, tn = self.last_results()
         sl = slice(self.ant_offset, self.ant_offset + self.n_local)
-        return nc[sl], ln[sl], tn[sl], self._cells.cpu().numpy().reshape(self.n_local, self.max_cells)
+        used = int(min(self.max_cells, max(1, nc[sl].max(initial=1))))
+        cells = self._cells.view(self.n_local, self.max_cells)[:, :used].cpu().numpy()
+        return nc[sl], ln[sl], tn[sl], cells
 
     def total_steps(self):
         return int(self._steps.cpu().item())

@@ -105,11 +105,21 @@ class PSOSolver(BasePathfinder):
                 n_acc += take.size
         self.init_attempts = attempts
         if n_acc == 0:
-            # pso.py:128-157: direct-path fallback / total failure.  (Not reached on maps where a waypoint
-            # chain exists; kept for the reference's observable behaviour.)
+            # pso.py:128-145: no waypoint chain was valid -> ONE particle built from the direct S->T path, with
+            # position = velocity = pbest_position = [[0.0, 0.0]] * W; the padding loop :159-160 then copies it
             path_direct = self._reconstruct_path_from_position([]) if W > 0 else []
             if path_direct and path_direct[0] == self.start_node and path_direct[-1] == self.target_node:
-                raise NotImplementedError("PSO direct-path fallback particle (pso.py:128-145) is not supported")
+                st = self._calculate_stats_for_path(path_direct)
+                row = t.as_tensor(np.array([[r * self.cols + c for r, c in path_direct]], np.int32), device=dev)
+                acc_pos.append(t.zeros((1, W, 2), dtype=t.float64, device=dev))
+                acc_vel.append(t.zeros((1, W, 2), dtype=t.float64, device=dev))
+                acc_stats.append(t.as_tensor(np.array([[float(st[1]), float(st[2]), float(st[3]), float(st[4]),
+                                                        float(st[5])]]), device=dev))
+                acc_cells.append(row)
+                acc_ncell.append(t.as_tensor(np.array([len(path_direct)], np.int32), device=dev))
+                n_acc = 1
+                print("PSO Warning: Population init failed, used a direct A* path as one particle.")
+        if n_acc == 0:                                                          # pso.py:147-157
             print("PSO Error: Could not initialize any valid particles.")
             self.gbest_particle_data = {'fitness': INF, 'path': [], 'position': [], 'length': INF, 'turns': 0,
                                         'safety_penalty': 0, 'diag_penalty': 0}

@@ -32,5 +32,7 @@ def load_golden(name):
 
 
 MAACO_CASES = ["fig7", "fig13", "blocks64", "near_roulette", "near_alpha2", "rect24x40", "aligned_row", "reverse_diag"]
+# main.py's own parameters (50 ants x 100 iterations) on every 20x20 demo map + grid_map_from_image_data5 (256x256)
+MAACO_DEFAULT_CASES = ["fig7_default", "fig13_default", "image1_default", "image2_default", "image3_default", "image5"]
 MAACO_DEFAULT = dict(alpha=1.0, beta=7.0, rho=0.1, Q=2.5, a_turn_coef=1.0, wh_max=0.9, wh_min=0.2,
                      k_h_adaptive=0.9, q0_initial=0.5, C0_initial_pheromone=0.1)

@@ -32,6 +32,19 @@ def env_grids():
     return {k: v.astype(np.uint8) for k, v in out.items()}
 
 
+def env_raw_data():
+    """The reference's demo maps exactly as env.py defines them (before main.py marks start/target), stored as
+    data for the drop-in `env` module (maaco_path_planing_b200/dropin/env.py): key = the reference's variable name."""
+    e = H.load_reference().env
+    names = ["grid_fig7_layout_data", "grid_map_fig13_base_data", "grid_map_from_image_data",
+             "grid_map_from_image_data2", "grid_map_from_image_data3", "grid_map_from_image_data5"]
+    out = {n: np.array(getattr(e, n)).astype(np.uint8) for n in names}
+    d = os.path.join(ROOT, "maaco_path_planing_b200", "data")
+    os.makedirs(d, exist_ok=True)
+    np.savez_compressed(os.path.join(d, "env_grids.npz"), **out)
+    print("env data", {k: v.shape for k, v in out.items()})
+
+
 def maaco_case(name, grid, N, K, seed, params):
     out = H.run_maaco(grid, dict(num_ants=N, num_iterations=K, **params), seed=seed)
     C = grid.shape[1]
@@ -240,6 +253,71 @@ def solver_cases():
     np.savez_compressed(os.path.join(HERE, "solver_cases.npz"), **out)
 
 
+def snake_map(n=9):
+    """One-cell-wide corridor from (0,0) to (n-1,n-1): almost no random waypoint chain is feasible (a segment may not
+    re-enter the cells of the earlier ones), the direct start -> target search is."""
+    g = np.ones((n, n), int)
+    for r in range(0, n, 2):
+        g[r, :] = 0
+        if r + 1 < n:
+            g[r + 1, n - 1 if (r // 2) % 2 == 0 else 0] = 0
+    g[0, 0], g[n - 1, n - 1] = 2, 3
+    return g
+
+
+def fallback_cases():
+    """PSO / GA runs of the reference whose initialisation finds no valid waypoint chain in N*20 attempts and
+    falls back to the direct-path individual (pso.py:128-145, ga_solver.py:111-117); plus the total failure
+    (start walled in: pso.py:147-157, ga_solver.py:120-126)."""
+    g = snake_map(9)
+    out = {"grid": g.astype(np.uint8)}
+    seed = 500
+    while True:
+        kw = dict(num_iterations=3, num_particles=3, num_waypoints_per_particle=5, w=0.7, c1=1.5, c2=1.5,
+                  allow_diagonal_moves=True, restrict_diagonal_near_obstacle_policy=True, **POLICY)
+        r = H.run_pso(g, kw, seed)
+        if np.all(r["init"]["pos"] == 0.0) and r["result"][0]:
+            break
+        seed += 1
+    out["pso_meta"] = np.array([3, 3, seed])
+    out["pso_curve"] = np.array(r["curve"])
+    out["pso_stats"] = np.array([float(x) for x in r["result"][1:]])
+    out["pso_best"] = r["best_cells"]
+    out["pso_pos"] = r["pos"]
+    out["pso_cur_fit"] = r["cur_fit"]
+    print("pso fallback seed", seed, r["result"][1:], r["curve"])
+    seed = 600
+    while True:
+        kw = dict(num_generations=3, population_size=2, num_waypoints_per_chromosome=5, mutation_rate=0.1,
+                  crossover_rate=0.8, tournament_size=3, allow_diagonal_moves=True,
+                  restrict_diagonal_near_obstacle_policy=True, **POLICY)
+        r = H.run_ga(g, kw, seed)
+        if r["init"]["chrom"].size == 0 and r["result"][0]:
+            break
+        seed += 1
+    out["ga_meta"] = np.array([2, 3, seed])
+    out["ga_curve"] = np.array(r["curve"])
+    out["ga_stats"] = np.array([float(x) for x in r["result"][1:]])
+    out["ga_best"] = r["best_cells"]
+    out["ga_fit"] = r["fit"]
+    print("ga fallback seed", seed, r["result"][1:], r["curve"])
+    # total failure: the start is walled in
+    w = snake_map(9)
+    w[0, 1] = 1
+    w[1, 0] = 1
+    w[1, 1] = 1
+    out["walled_grid"] = w.astype(np.uint8)
+    kw = dict(num_iterations=2, num_particles=2, num_waypoints_per_particle=3, w=0.7, c1=1.5, c2=1.5, **POLICY)
+    r = H.run_pso(w, kw, 701)
+    out["walled_pso_stats"] = np.array([float(x) for x in r["result"][1:]])
+    kw = dict(num_generations=2, population_size=2, num_waypoints_per_chromosome=3, mutation_rate=0.1,
+              crossover_rate=0.8, **POLICY)
+    r2 = H.run_ga(w, kw, 702)
+    out["walled_ga_stats"] = np.array([float(x) for x in r2["result"][1:]])
+    print("walled", r["result"], r2["result"])
+    np.savez_compressed(os.path.join(HERE, "fallback_cases.npz"), **out)
+
+
 def dijkstra_cases(n_cases=120):
     """Reference outputs of DijkstraSolver.solve (dijkstra.py:32-97) on random (grid, src, dst, avoid) tuples."""
     ref = H.load_reference()
@@ -300,19 +378,40 @@ def maaco_extra_cases():
     maaco_case("reverse_diag", rev, 32, 4, 108, MAACO_DEFAULT)
 
 
+def maaco_default_cases():
+    """BASELINE config 1 and its siblings: MAACO at main.py's own parameters (main.py:34-38: 50 ants x 100
+    iterations) on every 20x20 demo map main.py / env.py define, and 32 ants x 3 iterations on the 256x256
+    grid_map_from_image_data5 (env.py:114-371)."""
+    grids = env_grids()
+    for name in ("fig7", "fig13", "image1", "image2", "image3"):
+        maaco_case(name + "_default", grids[name].astype(int), 50, 100, 120 + len(name), MAACO_DEFAULT)
+    maaco_case("image5", grids["image5"].astype(int), 32, 3, 131, MAACO_DEFAULT)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "maaco_default":
+        maaco_default_cases()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "dijkstra":
         dijkstra_cases()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "fallback":
+        fallback_cases()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "env_raw":
+        env_raw_data()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "maaco_extra":
         maaco_extra_cases()
         return
     dijkstra_cases()
+    fallback_cases()
     solver_cases()
     astar_cases()
     fitness_cases()
     grids = env_grids()
     np.savez_compressed(os.path.join(HERE, "env_grids.npz"), **grids)
+    env_raw_data()
     maaco_case("fig7", grids["fig7"].astype(int), 20, 8, 101, MAACO_DEFAULT)
     maaco_case("fig13", grids["fig13"].astype(int), 16, 5, 102, MAACO_DEFAULT)
     maaco_case("blocks64", H.blocks_map(64, 0.2, 7), 32, 4, 103, MAACO_DEFAULT)
@@ -325,6 +424,7 @@ def main():
     rect = H.blocks_map(0, 0.15, 9, rows=24, cols=40)
     maaco_case("rect24x40", rect, 16, 4, 106, MAACO_DEFAULT)
     maaco_extra_cases()
+    maaco_default_cases()
 
 
 if __name__ == "__main__":

@@ -121,7 +121,7 @@ def test_path_stats_edge_cases():
     for i, p in enumerate(paths):
         buf[i, :len(p)] = p
     for mode, tpf in ((0, 0.3), (1, 0.1)):
-        for msd in (1.8, 3.2, 0.0):
+        for msd in (1.8, 3.2, 0.0, 16.0, 23.7):                     # (>= 15.9 was rejected in round 1)
             st = eng.path_stats(buf, n, make_policy(tpf, 0.8, msd, 100.0, mode=mode)).cpu().numpy()
             for i, p in enumerate(paths):
                 want = O.path_stats(grid, p, tpf, 0.8, msd, 100.0, True, mode=mode)

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import pyoracle as O
-from conftest import MAACO_CASES, load_golden
+from conftest import MAACO_CASES, MAACO_DEFAULT_CASES, load_golden
 
 KAT = [  # Random123 known-answer vectors for Philox4x32-10
     ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
@@ -24,7 +24,7 @@ def test_uniform_mapping_in_unit_interval():
     assert all(0.0 <= u < 1.0 for u in us) and len(set(us)) == len(us)
 
 
-@pytest.mark.parametrize("name", MAACO_CASES)
+@pytest.mark.parametrize("name", MAACO_CASES + MAACO_DEFAULT_CASES)
 def test_maaco_oracle_reproduces_reference(name):
     g = load_golden("maaco_" + name)
     N, K = int(g["N"]), int(g["K"])

@@ -94,6 +94,41 @@ def test_solver_errors_like_reference():
         GASolver(g, 2, 4, 2, 0.1, 0.8)
 
 
+def test_fallback_individuals_match_reference(capsys):
+    """pso.py:128-145 / ga_solver.py:111-117: when none of the N*20 random waypoint chains is feasible the reference
+    carries on with ONE individual built from the direct start -> target path; pso.py:147-157 /
+    ga_solver.py:120-126: no path at all -> ([], inf, 0, 0.0, 0.0, inf).  Recorded from the reference on a
+    one-cell-wide snake corridor (tests/golden/make_golden.py::fallback_cases)."""
+    from maaco_path_planing_b200.ga_solver import GASolver
+    from maaco_path_planing_b200.pso import PSOSolver
+    g = load_golden("fallback_cases")
+    grid = g["grid"].astype(int)
+    C = grid.shape[1]
+    N, K, seed = (int(x) for x in g["pso_meta"])
+    s = PSOSolver(grid, K, N, 5, 0.7, 1.5, 1.5, rng_seed=seed, verbose=False, **POLICY)
+    res = s.solve()
+    assert "PSO Warning: Population init failed, used a direct A* path as one particle." in capsys.readouterr().out
+    assert [r * C + c for r, c in res[0]] == g["pso_best"].tolist()
+    assert np.array_equal(np.array([float(x) for x in res[1:]]), g["pso_stats"])
+    assert np.array_equal(np.array(s.convergence_curve), g["pso_curve"])
+    assert np.array_equal(np.array([p["position"] for p in s.particles], dtype=float), g["pso_pos"])
+    assert np.array_equal(np.array([p["current_fitness"] for p in s.particles]), g["pso_cur_fit"])
+    N, K, seed = (int(x) for x in g["ga_meta"])
+    s = GASolver(grid, K, N, 5, 0.1, 0.8, 3, rng_seed=seed, verbose=False, **POLICY)
+    res = s.solve()
+    assert "GA Warning: Population init failed, used a direct A* path as one individual." in capsys.readouterr().out
+    assert [r * C + c for r, c in res[0]] == g["ga_best"].tolist()
+    assert np.array_equal(np.array([float(x) for x in res[1:]]), g["ga_stats"])
+    assert np.array_equal(np.array(s.convergence_curve), g["ga_curve"])
+    assert np.array_equal(np.array([ind["fitness"] for ind in s.population]), g["ga_fit"])
+    assert all(ind["chromosome"] == [] for ind in s.population)
+    walled = g["walled_grid"].astype(int)
+    r1 = PSOSolver(walled, 2, 2, 3, 0.7, 1.5, 1.5, rng_seed=701, verbose=False, **POLICY).solve()
+    r2 = GASolver(walled, 2, 2, 3, 0.1, 0.8, rng_seed=702, verbose=False, **POLICY).solve()
+    for r, want in ((r1, g["walled_pso_stats"]), (r2, g["walled_ga_stats"])):
+        assert r[0] == [] and np.array_equal(np.array([float(x) for x in r[1:]]), want)
+
+
 @pytest.mark.parametrize("name,N", [(m, n) for m in ("fig7", "blocks40") for n in (20, 24)])
 def test_mpa_trajectory(name, N):
     """MPA: phases 1-3 (Brownian / Levy targets, private-A* reconstruction), memory, FADs, sorts and the
