@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPP_ABI_VERSION 1
+#define MPP_ABI_VERSION 2
 
 #define MPP_OK 0
 #define MPP_EINVAL (-1)
@@ -69,32 +69,24 @@ int mpp_map_device(const mpp_map *map);
  * bit (r+1, c+1); the border is marked occupied) and its row pitch in 32-bit words */
 const uint32_t *mpp_map_occ_bits(const mpp_map *map, int *pitch_words);
 
+/* ---- batches of independent same-shape maps (BASELINE config 5: "batched sweep over independent maps") --------
+ * Every MAACO entry point below works on a batch (one launch covers all maps: grid.y = map).  A single map is a
+ * batch of one: mpp_map_as_batch(map) returns that view (owned by the map, no copy).
+ * replaces: a Python loop `for grid in grids: MAACO(grid, ...)` around MAACO.py:11-53.
+ * grids_host: n_maps x rows x cols bytes.  Synchronous. */
+typedef struct mpp_map_batch mpp_map_batch;
+int mpp_map_batch_create(const uint8_t *grids_host, int n_maps, int rows, int cols, int device, mpp_map_batch **out);
+void mpp_map_batch_destroy(mpp_map_batch *maps);
+int mpp_map_batch_size(const mpp_map_batch *maps);
+int mpp_map_batch_start(const mpp_map_batch *maps, int k);  /* cell id of map k's start or -1 */
+int mpp_map_batch_target(const mpp_map_batch *maps, int k);
+const mpp_map_batch *mpp_map_as_batch(const mpp_map *map);
+
 /* ---- MAACO (MAACO.py) -------------------------------------------------------------------- */
 typedef struct {
     double alpha, beta, rho, Q, a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial, C0_initial_pheromone;
     int num_iterations;
 } mpp_maaco_params;
-
-/* replaces MAACO._initialize_pheromones_maaco (MAACO.py:58-84), _precompute_dist_to_target
- * (:86-91) and the per-candidate heuristic eta'**beta (:197-210, :238) folded into two per-cell
- * tables E[cell][c], c = turn flag (interleaved: E01_dev[2*cell + c], 2*rows*cols doubles).  exp/pow
- * are evaluated on the host with libm (the same functions CPython/NumPy call) so the tables are
- * bit-identical to the reference; tau0_dev / dist_t_dev are rows*cols doubles (dist_t_dev may be
- * NULL).  Synchronous. */
-int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, double *tau0_dev, double *E01_dev,
-                     double *dist_t_dev, void *stream);
-
-/* replaces MAACO._calculate_adaptive_q0 (MAACO.py:212-226); pure host function */
-double mpp_maaco_q0(int num_iterations, int iteration, double q0_initial);
-
-/* ranks, per cell and previous-move context, the 8 moves by attractiveness tau**alpha * eta'**beta
- * (MAACO.py:235-239).  Where every value is < 1e-10 the selection rules (:241-262) depend only on that order
- * and the tour kernels use the ranking; elsewhere the entry says "evaluate".  Must be re-run after every
- * pheromone update.  rank_dev: mpp_maaco_rank_words(map) uint32 (opaque: a per-(cell, context) word for the
- * moves of the start->target quadrant, padded for unchecked neighbour reads, and a full two-word entry). */
-int mpp_maaco_rank(const mpp_map *map, const double *tau_dev, const double *E01_dev, double alpha, uint32_t *rank_dev,
-                   void *stream);
-long long mpp_maaco_rank_words(const mpp_map *map);
 
 /* per-ant outcome of one tour (MAACO.py:300-302): failed ants have n_cells=0, length=+inf, turns=-1 */
 typedef struct {
@@ -102,26 +94,6 @@ typedef struct {
     int32_t n_cells;
     int32_t turns;
 } mpp_ant_result;
-
-/* replaces the ant loop MAACO.py:340-342 -> _construct_ant_solution_maaco (:278-302) with the
- * orientation filter + crossing-prohibition (:100-181) and pseudo-random-proportional selection
- * (:228-262).  Ant i of this call is global ant `ant_offset + i` (its RNG stream id).
- *   tau / E01      rows*cols / 2*rows*cols doubles (mpp_maaco_tables)
- *   rank_dev       optional mpp_maaco_rank_words(map) words from mpp_maaco_rank for the CURRENT tau (NULL = evaluate the
- *                  attractiveness of every candidate at every step)
- *   visitT_dev     word-major visited bitmaps: word w of ant i at [w*n_ants + i], ceil(rows*cols/32)
- *                  words per ant; MUST be zero on entry; holds each ant's visited set on return
- *   cells_dev      n_ants x max_cells path cells (cells beyond max_cells are dropped; n_cells still
- *                  counts them)
- *   result_dev     n_ants x mpp_ant_result (:288,:292,:300-302)
- *   steps_dev      optional counter, += number of ant steps taken
- *   lanes_per_ant  0 = library default; 1 = one thread per ant (needs rank_dev), ants per warp chosen from n_ants;
- *                  -k (k = 1,2,4,..,32) = one thread per ant, k ants per warp (for callers that overlap several
- *                  colonies and know the total load); 8, 16 or 32 = that many lanes cooperate on one ant              */
-int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E01_dev, const uint32_t *rank_dev,
-                    int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
-                    uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, mpp_ant_result *result_dev,
-                    unsigned long long *steps_dev, int lanes_per_ant, void *stream);
 
 /* colony state kept on the device so an entire solve can be enqueued without host syncs */
 typedef struct {
@@ -135,47 +107,121 @@ typedef struct {
     int32_t iter_best_ant; /* -1 = all ants failed */
 } mpp_maaco_state;
 
-/* replaces the order-dependent best tracking MAACO.py:343-358 for one iteration over all
- * n_ants results (in global ant order) and prepares the per-ant deposit Q/length (:307-308; 0 for
- * ants that do not deposit).  Updates *state_dev and appends to the per-iteration log
- * log_dev[4*(iteration-1) + {0: iter best len, 1: iter best turns, 2: overall len, 3: overall turns}]
- * (log_dev may be NULL).  cells_dev holds the paths of ants [cells_ant_offset, cells_ant_offset +
- * cells_n_ants) (a sharded colony keeps only its own); the new overall-best path is copied into
- * best_cells_dev (capacity max_cells) when the best ant lies in that range. */
-int mpp_maaco_best(const mpp_ant_result *result_dev, const int32_t *cells_dev, int max_cells, int cells_ant_offset,
-                   int cells_n_ants, int n_ants, double Q, int iteration, mpp_maaco_state *state_dev,
-                   int32_t *best_cells_dev, double *deposit_dev, double *log_dev, void *stream);
+/* The device buffers of a colony (or of one colony per map of a batch), all owned by the caller.  n_ants below is
+ * the number of ants THIS process constructs per map (a sharded colony: its shard), n_total the colony size.
+ * TR = ceil(rows/32), TC = ceil(cols/32): the map as tiles of 32 x 32 cells. */
+typedef struct {
+    double *tau;               /* [n_maps][tau_stride] pheromone field (MAACO.pheromone_matrix), tau_stride >= rows*cols */
+    long long tau_stride;
+    const double *E01;         /* [n_maps or 1][2*rows*cols] eta'**beta by turn flag, interleaved (mpp_maaco_tables) */
+    long long E01_stride;      /* 0 = one table shared by every map of the batch */
+    uint32_t *rank;            /* [n_maps][mpp_maaco_rank_words(rows, cols)] (mpp_maaco_rank) */
+    uint32_t *slabs;           /* [n_maps][TR*TC][n_ants][32]: visited bits of one ant inside one tile, a word per tile row;
+                                  mpp_maaco_slab_words(TR, cols, n_ants) words per map.  Never needs clearing. */
+    uint32_t *touched;         /* [2][n_maps][TR*TC][ceil(n_ants/32)]: (tile, ant) has a slab this pass, double buffered by
+                                  iteration parity; mpp_maaco_touched_words(TR, cols, n_ants) words per map; zero before the
+                                  first pass (the pheromone update keeps clearing the buffer of the next pass) */
+    uint8_t *moves;            /* [n_maps][n_ants][max_cells] tours as move codes (move order MAACO.py:98) */
+    int max_cells;
+    int log_rows;              /* rows of `log` per map (= num_iterations), 0 if log is NULL */
+    mpp_ant_result *result;    /* [n_maps][n_total] */
+    double *deposit;           /* [n_maps][n_total] Q/length per ant, 0 = deposits nothing (MAACO.py:307-308) */
+    uint32_t *okbits;          /* [n_maps][ceil(n_total/32)] bit = ant deposits */
+    mpp_maaco_state *state;    /* [n_maps] */
+    int32_t *best_cells;       /* [n_maps][max_cells + 1] best path so far, decoded */
+    double *log;               /* [n_maps][log_rows][4] = iter best len, iter best turns, overall len, overall turns; or NULL */
+    unsigned long long *steps; /* [1] += ant steps taken; or NULL */
+    const uint64_t *seeds;     /* [n_maps] Philox seed of each map's colony */
+    const int32_t *latch;      /* NULL, or (sharded colony) != 0 once an exchange overflowed: every kernel is then a no-op */
+} mpp_colony;
 
-/* replaces MAACO._update_pheromone_trails_maaco (MAACO.py:304-332) for the cells of bitmap words
- * [word0, word0 + n_words): evaporate, deposit in global ant order (bit-exact, atomics-free: one warp
- * per 32 cells streams the visited words of every ant), MMAS clip with tau_max from state->best_len,
- * obstacles <- 1e-9.  visitT_dev is [n_seg][n_words][seg_ants] (word-major per segment; global ant =
- * seg*seg_ants + a; one segment per source rank in a sharded colony; n_seg=1, word0=0,
- * n_words=ceil(rows*cols/32) on a single GPU); deposit_dev is indexed by global ant.  Clears
- * visitT_dev behind itself when clear_visit != 0. */
-int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t *visitT_dev, const double *deposit_dev,
-                        int n_seg, int seg_ants, int word0, int n_words, double rho,
-                        const mpp_maaco_state *state_dev, int clear_visit, void *stream);
+long long mpp_maaco_rank_words(int rows, int cols);
+long long mpp_maaco_slab_words(int tile_rows, int cols, int n_ants);
+long long mpp_maaco_touched_words(int tile_rows, int cols, int n_ants);
+
+/* replaces MAACO._initialize_pheromones_maaco (MAACO.py:58-84), _precompute_dist_to_target
+ * (:86-91) and the per-candidate heuristic eta'**beta (:197-210, :238) folded into two per-cell
+ * tables E[cell][c], c = turn flag (interleaved: E01_dev[2*cell + c], 2*rows*cols doubles).  exp/pow
+ * are evaluated on the host with libm (the same functions CPython/NumPy call) so the tables are
+ * bit-identical to the reference.  The tables depend on (shape, start, target, parameters) only, so the maps of a
+ * batch -- which must share start and target -- share ONE E01 / dist_t table (computed once), and tau0 of map k is
+ * the shared free-cell table with map k's obstacles set to 1e-9 (a device kernel).  tau0_dev: [n_maps][tau_stride];
+ * E01_dev: 2*rows*cols; dist_t_dev: rows*cols or NULL.  Synchronous. */
+int mpp_maaco_tables(const mpp_map_batch *maps, const mpp_maaco_params *p, double *tau0_dev, long long tau_stride,
+                     double *E01_dev, double *dist_t_dev, void *stream);
+
+/* replaces MAACO._calculate_adaptive_q0 (MAACO.py:212-226); pure host function */
+double mpp_maaco_q0(int num_iterations, int iteration, double q0_initial);
+
+/* ranks, per cell and previous-move context, the 8 moves by attractiveness tau**alpha * eta'**beta
+ * (MAACO.py:235-239) into colony->rank.  Where every value is < 1e-10 the selection rules (:241-262) depend only on
+ * that order and the tour kernel uses the ranking; elsewhere the entry says "evaluate".  Must be re-run after every
+ * pheromone update.
+ * alpha != 1: tau**alpha is CUDA's pow() (<= 2 ulp from glibc's, which is what NumPy calls at MAACO.py:238), so the
+ * attractiveness values agree with the reference to ~4e-16 relative, NOT bit for bit: a discrete choice can differ
+ * only where two candidate moves' attractiveness agree to that precision without being equal by symmetry.  alpha == 1
+ * (the reference's default, x**1.0 == x) is exact. */
+int mpp_maaco_rank(const mpp_map_batch *maps, const mpp_colony *colony, double alpha, void *stream);
+
+/* replaces the ant loop MAACO.py:340-342 -> _construct_ant_solution_maaco (:278-302) with the
+ * orientation filter + crossing-prohibition (:100-181) and pseudo-random-proportional selection
+ * (:228-262), for ants [ant_offset, ant_offset + n_ants) of every map's colony (global ant id = RNG stream id).
+ * Needs colony->rank of the CURRENT tau.  Writes slabs / touched (parity = iteration & 1) / moves of the n_ants local
+ * ants and result[map][ant_offset + i].  ants_per_warp: 0 = chosen from the total load, or 1,2,4,..,32. */
+int mpp_maaco_tours(const mpp_map_batch *maps, const mpp_colony *colony, int iteration, double q0, double alpha,
+                    int n_ants, int ant_offset, int n_ants_total, int ants_per_warp, void *stream);
+
+/* replaces the order-dependent best tracking MAACO.py:343-358 for one iteration over all n_ants_total results of each
+ * map (global ant order) and prepares deposit / okbits (:307-308).  Updates state and appends to log.  colony->moves
+ * holds the tours of ants [moves_ant_offset, moves_ant_offset + moves_n_ants) (a sharded colony keeps only its own);
+ * the new overall-best path is decoded into best_cells when the best ant lies in that range. */
+int mpp_maaco_best(const mpp_map_batch *maps, const mpp_colony *colony, int moves_ant_offset, int moves_n_ants,
+                   int n_ants_total, double Q, int iteration, void *stream);
+
+/* replaces MAACO._update_pheromone_trails_maaco (MAACO.py:304-332) for the cells of tile rows
+ * [tile_row0, tile_row0 + buf_tile_rows): evaporate, deposit in global ant order (bit-exact, atomics-free: one warp per
+ * row of 32 cells walks the ants that have a slab for its tile), MMAS clip with tau_max from state->best_len,
+ * obstacles <- 1e-9.  slabs_dev / touched_dev are laid out like colony->slabs / touched but cover buf_tile_rows tile rows
+ * starting at tile_row0 and n_ants_total ants (single GPU: the colony's own buffers, tile_row0 = 0,
+ * buf_tile_rows = TR; sharded: the receive buffers mpp_maaco_xunpack fills).  Clears the `touched` buffer of the next
+ * pass, and (clear_slabs != 0) the slab words it read. */
+int mpp_maaco_pheromone(const mpp_map_batch *maps, const mpp_colony *colony, uint32_t *slabs_dev, uint32_t *touched_dev,
+                        int n_ants_total, int tile_row0, int buf_tile_rows, double rho, int iteration, int clear_slabs,
+                        void *stream);
+
+/* one whole pass of a non-sharded colony: rank + tours + best + pheromone, enqueued on `stream` (asynchronous) */
+int mpp_maaco_pass(const mpp_map_batch *maps, const mpp_colony *colony, const mpp_maaco_params *p, int iteration,
+                   int n_ants, int ants_per_warp, void *stream);
+
+/* the same pass with HOST buffers -- what a caller holding NumPy arrays binds: copies the pheromone field in
+ * (tau_in_host: n_maps x rows*cols doubles, or NULL to keep the device field), runs the pass, copies out the updated
+ * field, the per-ant results (n_maps x n_ants), the colony state(s) and the best path(s) so far
+ * (n_maps x best_cells_capacity int32); any output pointer may be NULL.  SYNCHRONOUS: returns when the outputs are
+ * valid.  replaces one iteration of MAACO.solve_path_planning's loop, MAACO.py:336-359. */
+int mpp_maaco_pass_host(const mpp_map_batch *maps, const mpp_colony *colony, const mpp_maaco_params *p, int iteration,
+                        int n_ants, int ants_per_warp, const double *tau_in_host, double *tau_out_host,
+                        mpp_ant_result *result_out_host, mpp_maaco_state *state_out_host, int32_t *best_cells_out_host,
+                        int best_cells_capacity, void *stream);
 
 /* ---- sharded-colony exchange (no reference counterpart: the reference is single-process; these implement the
  * per-iteration exchange BASELINE's north star asks for, bit-exactly) ----------------------------------------
- * Tours travel between GPUs as 1-byte move codes (MAACO move order, MAACO.py:98).
- * mpp_maaco_move_offsets: from the all-gathered results ([n_seg*seg_ants], segment = source rank) compute each
- *   ant's byte offset inside its segment's packed buffer and the per-segment totals (n_cells-1 bytes per
- *   successful ant, 0 for failed ants).
- * mpp_maaco_pack_moves: encode this rank's paths (cells_dev, n_local x max_cells) at offsets_local_dev.
- *   status_dev[0] = 2 if a path was truncated at max_cells or does not fit `capacity`.
- * mpp_maaco_rebuild_visits: replay the codes of every ant (packed_all_dev = n_seg buffers of `capacity` bytes)
- *   and set the visited bits falling into words [word0, word0+n_words) of visit_seg_dev
- *   ([n_seg][n_words][seg_ants], zero on entry) -- the input layout of mpp_maaco_pheromone. */
-int mpp_maaco_move_offsets(const mpp_ant_result *result_dev, int n_seg, int seg_ants, int32_t *offsets_dev,
-                           int32_t *totals_dev, void *stream);
-int mpp_maaco_pack_moves(const mpp_map *map, const int32_t *cells_dev, int max_cells,
-                         const mpp_ant_result *result_local_dev, const int32_t *offsets_local_dev, int n_local,
-                         uint8_t *packed_dev, int capacity, int32_t *status_dev, void *stream);
-int mpp_maaco_rebuild_visits(const mpp_map *map, const uint8_t *packed_all_dev, int capacity,
-                             const int32_t *offsets_dev, const mpp_ant_result *result_dev, int n_seg, int seg_ants,
-                             int word0, int n_words, uint32_t *visit_seg_dev, void *stream);
+ * Rank g ships the results and the tours (1-byte move codes) of its n_local ants in ONE buffer per pass:
+ *   [n_local x mpp_ant_result][int32 total code bytes + 12 pad bytes][codes: `capacity` bytes]
+ * (mpp_maaco_xhdr_bytes(n_local) + capacity bytes; one all-gather moves it to every rank).
+ * mpp_maaco_xpack   fills this rank's buffer from colony->result / moves (offsets_local_dev: n_local int32 scratch).
+ * mpp_maaco_xunpack on the gathered buffers (n_seg = ranks, seg_ants = ants per rank): copies all results into
+ *   colony->result, computes per-ant code offsets (offsets_dev: n_seg*seg_ants int32), replays every ant's codes into
+ *   the receive slabs / touched of tile rows [tile_row0, tile_row0 + buf_tile_rows) -- the input of
+ *   mpp_maaco_pheromone (slabs_recv_dev must be zero on entry: the update clears what it read) -- and clears the
+ *   parity-(iteration+1) half of the rank's own touched_local_dev.  If a segment's codes exceed `capacity` or a tour
+ *   exceeds max_cells, *colony->latch is set to `iteration` (identically on every rank) and every later kernel is a
+ *   no-op until the host clears it and repeats the pass with more room. */
+long long mpp_maaco_xhdr_bytes(int n_local);
+int mpp_maaco_xpack(const mpp_map_batch *maps, const mpp_colony *colony, int ant_offset, int n_local, int n_ants_total,
+                    int32_t *offsets_local_dev, uint8_t *xbuf_local_dev, long long capacity, void *stream);
+int mpp_maaco_xunpack(const mpp_map_batch *maps, const mpp_colony *colony, const uint8_t *xbuf_all_dev, long long capacity,
+                      int n_seg, int seg_ants, int iteration, int32_t *offsets_dev, int tile_row0, int buf_tile_rows,
+                      uint32_t *slabs_recv_dev, uint32_t *touched_recv_dev, uint32_t *touched_local_dev, void *stream);
 
 /* ---- A* connectors, waypoint-chain fitness, path statistics (astar.py, MPA.py, helper.py, pso.py, ga_solver.py) ---- */
 typedef struct {

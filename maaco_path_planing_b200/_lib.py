@@ -31,6 +31,15 @@ class MaacoState(C.Structure):
                 ("iter_best_turns", C.c_int32), ("iter_best_ant", C.c_int32)]
 
 
+class Colony(C.Structure):
+    """mpp_colony (include/mpp.h): the caller-owned device buffers of a colony / of one colony per map of a batch."""
+    _fields_ = [("tau", c_void_p), ("tau_stride", C.c_longlong), ("E01", c_void_p), ("E01_stride", C.c_longlong),
+                ("rank", c_void_p), ("slabs", c_void_p), ("touched", c_void_p), ("moves", c_void_p),
+                ("max_cells", c_int), ("log_rows", c_int), ("result", c_void_p), ("deposit", c_void_p),
+                ("okbits", c_void_p), ("state", c_void_p), ("best_cells", c_void_p), ("log", c_void_p),
+                ("steps", c_void_p), ("seeds", c_void_p), ("latch", c_void_p)]
+
+
 class Policy(C.Structure):
     _fields_ = [("turn_penalty_factor", c_double), ("safety_penalty_factor", c_double),
                 ("min_safe_distance", c_double), ("diagonal_obstacle_penalty_value", c_double),
@@ -49,16 +58,31 @@ _SIGS = {
     "mpp_map_target": (c_int, [c_void_p]),
     "mpp_map_device": (c_int, [c_void_p]),
     "mpp_map_occ_bits": (c_void_p, [c_void_p, C.POINTER(c_int)]),
-    "mpp_maaco_tables": (c_int, [c_void_p, C.POINTER(MaacoParams), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mpp_map_batch_create": (c_int, [c_void_p, c_int, c_int, c_int, c_int, C.POINTER(c_void_p)]),
+    "mpp_map_batch_destroy": (None, [c_void_p]),
+    "mpp_map_batch_size": (c_int, [c_void_p]),
+    "mpp_map_batch_start": (c_int, [c_void_p, c_int]),
+    "mpp_map_batch_target": (c_int, [c_void_p, c_int]),
+    "mpp_map_as_batch": (c_void_p, [c_void_p]),
+    "mpp_maaco_tables": (c_int, [c_void_p, C.POINTER(MaacoParams), c_void_p, C.c_longlong, c_void_p, c_void_p, c_void_p]),
     "mpp_maaco_q0": (c_double, [c_int, c_int, c_double]),
-    "mpp_maaco_rank_words": (C.c_longlong, [c_void_p]),
-    "mpp_maaco_rank": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p]),
-    "mpp_maaco_tours": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_int, c_int,
-                                c_u64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
-    "mpp_maaco_best": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int, c_void_p,
-                               c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mpp_maaco_pheromone": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double,
-                                    c_void_p, c_int, c_void_p]),
+    "mpp_maaco_rank_words": (C.c_longlong, [c_int, c_int]),
+    "mpp_maaco_slab_words": (C.c_longlong, [c_int, c_int, c_int]),
+    "mpp_maaco_touched_words": (C.c_longlong, [c_int, c_int, c_int]),
+    "mpp_maaco_rank": (c_int, [c_void_p, C.POINTER(Colony), c_double, c_void_p]),
+    "mpp_maaco_tours": (c_int, [c_void_p, C.POINTER(Colony), c_int, c_double, c_double, c_int, c_int, c_int, c_int,
+                                c_void_p]),
+    "mpp_maaco_best": (c_int, [c_void_p, C.POINTER(Colony), c_int, c_int, c_int, c_double, c_int, c_void_p]),
+    "mpp_maaco_pheromone": (c_int, [c_void_p, C.POINTER(Colony), c_void_p, c_void_p, c_int, c_int, c_int, c_double,
+                                    c_int, c_int, c_void_p]),
+    "mpp_maaco_pass": (c_int, [c_void_p, C.POINTER(Colony), C.POINTER(MaacoParams), c_int, c_int, c_int, c_void_p]),
+    "mpp_maaco_pass_host": (c_int, [c_void_p, C.POINTER(Colony), C.POINTER(MaacoParams), c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "mpp_maaco_xhdr_bytes": (C.c_longlong, [c_int]),
+    "mpp_maaco_xpack": (c_int, [c_void_p, C.POINTER(Colony), c_int, c_int, c_int, c_void_p, c_void_p, C.c_longlong,
+                                c_void_p]),
+    "mpp_maaco_xunpack": (c_int, [c_void_p, C.POINTER(Colony), c_void_p, C.c_longlong, c_int, c_int, c_int, c_void_p,
+                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpp_map_safety_table": (c_int, [c_void_p, c_double, c_void_p]),
     "mpp_path_stats": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, C.POINTER(Policy), c_void_p, c_void_p]),
     "mpp_astar_scratch_bytes": (C.c_size_t, [c_void_p, c_int, c_int]),
@@ -77,11 +101,6 @@ _SIGS = {
                                   c_double, c_double, c_u64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, C.c_size_t, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p]),
-    "mpp_maaco_move_offsets": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "mpp_maaco_pack_moves": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
-                                     c_void_p]),
-    "mpp_maaco_rebuild_visits": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                         c_void_p, c_void_p]),
 }
 
 _lib = None

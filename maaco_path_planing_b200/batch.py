@@ -1,10 +1,22 @@
-"""Batched sweeps over independent maps (BASELINE config 5): maps are independent units, so they are
-sharded over the ranks with no data-path collective, and on each GPU several colonies run concurrently on
-separate CUDA streams (a 1024-ant colony fills ~1/9 of a B200; the colony pass is enqueued without host
-synchronisation, so interleaving the launches of a wave of solvers overlaps them)."""
+"""Batched sweeps over independent maps (BASELINE config 5: "10k independent 256x256 maps x population 1024,
+MPA+MAACO, maps sharded across 8 B200").  Maps are independent units, so they are sharded over the ranks with no
+data-path collective, and on each GPU a WAVE of same-shape maps is one mpp_map_batch: every colony pass of the
+whole wave is four kernel launches (ranking, tours, best tracking, pheromone update with grid.y = map), enqueued
+without host synchronisation.  Results are identical to solving each map alone with the same seed.
+
+The eta'**beta / dist-to-target tables depend only on (shape, start, target, parameters), so a wave shares ONE
+table computed on the host with libm (bit-identical to the reference), and tau0 of each map is that shared table
+with the map's obstacles masked on the device (mpp_maaco_tables)."""
 from __future__ import annotations
 
-from .dist import shard_range
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .gridmap import START_NODE_VAL, TARGET_NODE_VAL
+
+INF = float("inf")
 
 
 def shard_maps(n_maps, group=None):
@@ -17,41 +29,165 @@ def shard_maps(n_maps, group=None):
     return min(n_maps, rank * per), min(n_maps, (rank + 1) * per)
 
 
-def solve_maaco_batch(grids, num_ants, num_iterations, params, seeds=None, concurrent=12, group=None, device=None,
+class MAACOBatch:
+    """M same-shape maps that share start and target, one colony of `num_ants` ants per map, solved together.
+    Same parameters as MAACO (MAACO.py:11-14); `seeds` = one Philox seed per map."""
+
+    def __init__(self, grids, num_ants, num_iterations, alpha, beta, rho, Q, a_turn_coef, wh_max, wh_min, k_h_adaptive,
+                 q0_initial, C0_initial_pheromone=0.1, *, seeds=None, device=None, max_cells=None, ants_per_warp=0):
+        import torch
+        L = _lib.lib()
+        g = np.ascontiguousarray(np.asarray(grids, dtype=int))
+        if g.ndim != 3:
+            raise ValueError("grids must be [n_maps, rows, cols]")
+        self.n_maps, self.rows, self.cols = g.shape
+        for k in range(self.n_maps):
+            if not (g[k] == START_NODE_VAL).any():
+                raise ValueError("MAACO: Start node not found.")              # MAACO.py:35-36
+            if not (g[k] == TARGET_NODE_VAL).any():
+                raise ValueError("MAACO: Target node not found.")             # MAACO.py:37-38
+        _lib.require_device()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        g8 = np.ascontiguousarray(np.clip(g, 0, 255), dtype=np.uint8)
+        h = C.c_void_p()
+        _lib.check(L.mpp_map_batch_create(g8.ctypes.data_as(C.c_void_p), self.n_maps, self.rows, self.cols,
+                                          self.device_index, C.byref(h)), "mpp_map_batch_create")
+        self._maps = h
+        self.num_ants, self.num_iterations = int(num_ants), int(num_iterations)
+        self.alpha, self.rho, self.Q = alpha, rho, Q
+        self._params = _lib.MaacoParams(alpha, beta, rho, Q, a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
+                                        C0_initial_pheromone, num_iterations)
+        M, R, Cc, N = self.n_maps, self.rows, self.cols, self.num_ants
+        n = R * Cc
+        TR = (R + 31) // 32
+        if max_cells is None:
+            max_cells = min(n, max(1024, 8 * (R + Cc)))
+        self.max_cells = int(max_cells)
+        self._apw = int(ants_per_warp)
+        if seeds is None:
+            seeds = [int.from_bytes(np.random.bytes(8), "little") for _ in range(M)]
+        self.seeds = [int(s) & (2 ** 64 - 1) for s in seeds]
+        dev = self.device
+        f64, i32, i64, u8 = torch.float64, torch.int32, torch.int64, torch.uint8
+        self._tau = torch.zeros((M, n), dtype=f64, device=dev)
+        self._E01 = torch.empty(2 * n, dtype=f64, device=dev)                 # shared by the whole wave
+        self._dist_t = torch.empty(n, dtype=f64, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.mpp_maaco_tables(self._maps, C.byref(self._params), _lib.ptr(self._tau), n, _lib.ptr(self._E01),
+                                      _lib.ptr(self._dist_t), stream), "mpp_maaco_tables")
+        self._rank = torch.empty(M * L.mpp_maaco_rank_words(R, Cc), dtype=i32, device=dev)
+        self._slabs = torch.empty(M * L.mpp_maaco_slab_words(TR, Cc, N), dtype=i32, device=dev)
+        self._touched = torch.zeros(M * L.mpp_maaco_touched_words(TR, Cc, N), dtype=i32, device=dev)
+        self._moves = torch.zeros(M * N * self.max_cells, dtype=u8, device=dev)
+        self._result = torch.zeros((M, N, 2), dtype=i64, device=dev)
+        self._deposit = torch.zeros((M, N), dtype=f64, device=dev)
+        self._okbits = torch.zeros((M, (N + 31) // 32), dtype=i32, device=dev)
+        self._best_cells = torch.zeros((M, self.max_cells + 1), dtype=i32, device=dev)
+        self._steps = torch.zeros(1, dtype=i64, device=dev)
+        K = max(1, self.num_iterations)
+        self._log = torch.zeros((M, K, 4), dtype=f64, device=dev)
+        self._seeds = torch.from_numpy(np.array(self.seeds, np.uint64).view(np.int64)).to(dev)
+        st = bytes(_lib.MaacoState(INF, -1, 0, 0, -1, INF, -1, -1))
+        self._state = torch.frombuffer(bytearray(st * M), dtype=u8).to(dev)
+        self._colony = _lib.Colony(
+            self._tau.data_ptr(), n, self._E01.data_ptr(), 0, self._rank.data_ptr(), self._slabs.data_ptr(),
+            self._touched.data_ptr(), self._moves.data_ptr(), self.max_cells, K, self._result.data_ptr(),
+            self._deposit.data_ptr(), self._okbits.data_ptr(), self._state.data_ptr(), self._best_cells.data_ptr(),
+            self._log.data_ptr(), self._steps.data_ptr(), self._seeds.data_ptr(), None)
+        self._iter_done = 0
+        self.kernel_launches = 0
+
+    def close(self):
+        h, self._maps = getattr(self, "_maps", None), None
+        if h:
+            _lib.lib().mpp_map_batch_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_iteration(self, it):
+        """Enqueue one colony pass of every map of the wave (asynchronous)."""
+        import torch
+        if not 1 <= it <= max(1, self.num_iterations):
+            raise ValueError(f"iteration {it} outside 1..{self.num_iterations}")
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(_lib.lib().mpp_maaco_pass(self._maps, C.byref(self._colony), C.byref(self._params), it, self.num_ants,
+                                             self._apw, stream), "mpp_maaco_pass")
+        self.kernel_launches += 4
+        self._iter_done = max(self._iter_done, it)
+
+    def pheromone(self):
+        return self._tau.cpu().numpy().reshape(self.n_maps, self.rows, self.cols)
+
+    def last_results(self):
+        """(n_cells, length, turns), each [n_maps, num_ants], of the last pass."""
+        import torch
+        torch.cuda.synchronize(self.device)
+        rec = self._result.cpu().numpy().view(np.dtype([("length", "<f8"), ("n_cells", "<i4"), ("turns", "<i4")]))
+        rec = rec.reshape(self.n_maps, self.num_ants)
+        return rec["n_cells"].copy(), rec["length"].copy(), rec["turns"].copy()
+
+    def total_steps(self):
+        return int(self._steps.cpu().item())
+
+    def solve(self):
+        """Runs the remaining iterations; returns one (path, length, turns, convergence_curve) per map -- the values
+        MAACO.solve_path_planning (MAACO.py:334-371) returns / stores for that map."""
+        import torch
+        for it in range(self._iter_done + 1, self.num_iterations + 1):
+            self.run_iteration(it)
+        torch.cuda.synchronize(self.device)
+        M, K = self.n_maps, self.num_iterations
+        st = np.frombuffer(self._state.cpu().numpy().tobytes(), dtype=np.dtype(
+            [("best_len", "<f8"), ("best_turns", "<i4"), ("best_n_cells", "<i4"), ("best_iter", "<i4"), ("best_ant", "<i4"),
+             ("iter_best_len", "<f8"), ("iter_best_turns", "<i4"), ("iter_best_ant", "<i4")]))
+        if (st["best_n_cells"] - 1 > self.max_cells).any():
+            raise _lib.MppError(f"a best path outgrew max_cells={self.max_cells}; re-run with a larger max_cells")
+        best = self._best_cells.cpu().numpy()
+        log = self._log.cpu().numpy()[:, :K]
+        out = []
+        for k in range(M):
+            nb = int(st["best_n_cells"][k])
+            path = [(int(c) // self.cols, int(c) % self.cols) for c in best[k, :nb]]
+            turns = int(st["best_turns"][k]) if st["best_turns"][k] >= 0 else INF
+            curve = [float(v) if v != INF else None for v in log[k, :, 2]]
+            out.append((path, float(st["best_len"][k]), turns, curve))
+        return out
+
+
+def _waves(grids, lo, hi, wave):
+    """Group this rank's maps into waves of same shape / start / target (what one mpp_map_batch needs)."""
+    groups = {}
+    for i in range(lo, hi):
+        g = np.asarray(grids[i])
+        s, t = np.argwhere(g == START_NODE_VAL), np.argwhere(g == TARGET_NODE_VAL)
+        key = (g.shape, tuple(s[0]) if len(s) else None, tuple(t[0]) if len(t) else None)
+        groups.setdefault(key, []).append(i)
+    for idx in groups.values():
+        for w0 in range(0, len(idx), wave):
+            yield idx[w0:w0 + wave]
+
+
+def solve_maaco_batch(grids, num_ants, num_iterations, params, seeds=None, wave=256, group=None, device=None,
                       max_cells=None):
-    """Run MAACO on every grid of `grids` (this rank's shard when `group` is given).
+    """Run MAACO on every grid of `grids` (this rank's shard when `group` is given), `wave` maps per launch.
 
     Returns a list of (map_index, path, length, turns, convergence_curve) for the maps of this rank; results
     are identical to solving each map alone (same seeds => same Philox streams)."""
-    import torch
-    from .maaco import MAACO
     lo, hi = shard_maps(len(grids), group)
     out = []
-    # the overlapped colonies fill the GPU together: pack the ants as one colony of that total size would be packed
-    in_flight = max(1, min(concurrent, hi - lo)) * num_ants
-    apw = 2 if in_flight <= 4096 else (4 if in_flight <= 8192 else 8)
-    for w0 in range(lo, hi, concurrent):
-        idx = list(range(w0, min(hi, w0 + concurrent)))
-        solvers, streams = [], []
-        for i in idx:
-            g = grids[i]
-            mc = max_cells or min(g.shape[0] * g.shape[1], 16 * (g.shape[0] + g.shape[1]))
-            solvers.append(MAACO(g, num_ants, num_iterations, rng_seed=None if seeds is None else seeds[i],
-                                 device=device, verbose=False, max_cells=mc, ants_per_warp=apw, **params))
-            streams.append(torch.cuda.Stream(device=solvers[-1].device))
-        cur = torch.cuda.current_stream(solvers[0].device)
-        for st in streams:
-            st.wait_stream(cur)
-        for it in range(1, num_iterations + 1):                    # interleave the waves' launches
-            for s, st in zip(solvers, streams):
-                with torch.cuda.stream(st):
-                    s._enqueue_iteration(it)
-        for st in streams:
-            st.synchronize()
-        for i, s in zip(idx, solvers):
-            s._iter_done = num_iterations
-            path, length, turns = s.solve_path_planning()           # nothing left to enqueue: reads results back
-            out.append((i, path, length, turns, list(s.convergence_curve_data)))
+    for idx in _waves(grids, lo, hi, wave):
+        b = MAACOBatch(np.stack([np.asarray(grids[i]) for i in idx]), num_ants, num_iterations,
+                       seeds=None if seeds is None else [seeds[i] for i in idx], device=device, max_cells=max_cells,
+                       **params)
+        for i, (path, length, turns, curve) in zip(idx, b.solve()):
+            out.append((i, path, length, turns, curve))
+        b.close()
+    out.sort(key=lambda r: r[0])
     return out
 
 

@@ -33,6 +33,33 @@ void mpp_set_error(const char *fmt, ...);
         }                               \
     } while (0)
 
+// strategy-1 constants of one map (P1 = orientation start -> target, MAACO.py:146-165)
+struct MppS1 {
+    uint32_t P1;
+    int fast_ok;            // P1 has exactly three moves
+    int sm[3];              // those moves
+    int dpr[3], dc[3];      // window row pointer delta (bytes) and column delta of each
+    int so[3];              // ranking-word offset of (neighbour cell, context move+1)
+};
+struct MppMapMeta {         // per-map scalars the MAACO kernels read from device memory (one per map of a batch)
+    int start, target;
+    MppS1 s1;
+};
+MppMapMeta mpp_make_meta(int rows, int cols, int start, int target);
+
+// A batch of same-shape maps: what every MAACO launcher takes (grid.y / blockIdx.y = map).  A single mpp_map
+// owns a batch of one (`self_batch`) over its own buffers.
+struct mpp_map_batch {
+    int n_maps, rows, cols, device, sm_count;
+    int pitch_words, occ_words;
+    uint32_t *occ_dev;      // [n_maps][occ_words]
+    uint8_t *svalid_dev;    // [n_maps][rows*cols]
+    MppMapMeta *meta_dev;   // [n_maps]
+    MppMapMeta *meta_host;  // [n_maps]
+    uint8_t *grid_host;     // [n_maps][rows*cols] (host copy for host-side table builds), may be null for views
+    int owns;               // 1 = buffers are freed by mpp_map_batch_destroy
+};
+
 struct mpp_map {
     int rows, cols, device;
     int start, target;      // cell ids or -1
@@ -48,6 +75,7 @@ struct mpp_map {
     uint16_t *safety_d2_dev; // rows*cols
     double *safety_lut_dev; // safety_lut_n doubles: penalty contribution for class d^2
     int safety_lut_n;
+    mpp_map_batch self_batch; // this map as a batch of one (view; meta_dev / meta_host owned by the map)
 };
 
 int mpp_check_device(int device);

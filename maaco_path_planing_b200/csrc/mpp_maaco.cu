@@ -1,8 +1,18 @@
-// mpp_maaco.cu -- MAACO colony pass on B200: per-pass move ranking, tour construction (one thread per
-// ant by default; warp / 16- / 8-lane cooperative forms kept), order-dependent best tracking, and the
-// atomics-free ordered pheromone update.
+// mpp_maaco.cu -- MAACO colony pass on B200: per-pass move ranking, tour construction (one thread per ant),
+// order-dependent best tracking, and the atomics-free ordered pheromone update -- every kernel batched over
+// independent same-shape maps (blockIdx.y = map; a single map is a batch of one).
 // Reference semantics: MAACO.py:58-91 (tables), :100-181 (filter), :197-262 (selection),
 // :278-302 (tour), :304-332 (pheromone), :343-358 (best tracking).
+//
+// Data layout of one colony (n_ants ants on an R x C map; TR x TC tiles of 32 x 32 cells):
+//   slabs    [tile][ant][32] uint32   the visited bits of `ant` inside `tile`, one word per tile row -- written by the
+//                                     tour kernel as whole 128-byte lines when a tile leaves the ant's shared-memory
+//                                     window, read back (rarely) when the ant re-enters a tile, and streamed by the
+//                                     pheromone update, which only ever touches the (tile, ant) pairs that exist
+//   touched  [2][tile][ceil(n_ants/32)] uint32  bit = (tile, ant) has a slab this pass; double buffered by pass parity
+//                                     (the update of pass p clears the buffer pass p+1 will use)
+//   moves    [ant][max_cells] uint8   the tour as move codes (MAACO.py:98 order): the best path is decoded from them,
+//                                     and they are what a sharded colony exchanges
 #include <cmath>
 #include <cstdlib>
 #include <thread>
@@ -32,18 +42,13 @@ extern "C" double mpp_maaco_q0(int K, int k, double q0_initial) {  // MAACO.py:2
     return q0 < 0.99 ? q0 : 0.99;
 }
 
-extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, double *tau0_dev, double *E01_dev,
-                                double *dist_t_dev, void *stream) {
-    MPP_REQUIRE(map && p && tau0_dev && E01_dev, "mpp_maaco_tables: null argument");
-    MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_tables: map has no start/target");
-    const int R = map->rows, C = map->cols;
-    const size_t n = (size_t)R * C;
-    const int sr = map->start / C, sc = map->start % C, tr = map->target / C, tc = map->target % C;
+// tau0 (as if no cell were an obstacle), E01 and dist_to_target of an R x C map with the given start / target:
+// functions of (shape, start, target, parameters) only -- a batch of maps that share them shares the tables.
+static void host_tables(int R, int C, int start, int target, const mpp_maaco_params *p, double *tau0, double *E01,
+                        double *dt) {
+    const int sr = start / C, sc = start % C, tr = target / C, tc = target % C;
     double dsT = hdist(sr, sc, tr, tc);
     if (dsT < 1e-9) dsT = 1e-9;  // MAACO.py:43-45
-    std::vector<double> buf(4 * n);
-    double *tau0 = buf.data(), *E01 = tau0 + n, *dt = E01 + 2 * n;
-    const uint8_t *grid = map->grid_host;
     auto work = [&](int r_lo, int r_hi) {
         for (int r = r_lo; r < r_hi; ++r)
             for (int c = 0; c < C; ++c) {
@@ -51,17 +56,15 @@ extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, d
                 const double diT = hdist(r, c, tr, tc);
                 const double dsi = hdist(sr, sc, r, c);
                 dt[i] = diT;
-                if (grid[i] == 1) {
-                    tau0[i] = 1e-9;
-                } else {
-                    const double den = dsi + diT;
+                {
+                    const double den = dsi + diT;                // MAACO.py:58-84
                     double factor;
                     if (den < 1e-9) factor = (dsi < 1e-6 || diT < 1e-6) ? 1.0 : 0.1;
                     else factor = dsT / den;
                     const double v = factor * p->C0_initial_pheromone;
                     tau0[i] = v < 1e-9 ? 1e-9 : v;
                 }
-                double h;
+                double h;                                        // MAACO.py:197-210
                 if (dsT < 1e-9) h = p->wh_min;
                 else h = p->wh_max - (p->wh_max - p->wh_min) * std::exp(-p->k_h_adaptive * diT / dsT);
                 const double g = 1.0 - h;
@@ -75,7 +78,7 @@ extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, d
     };
     unsigned nt = std::thread::hardware_concurrency();
     if (nt > 16) nt = 16;
-    if (nt < 2 || n < 65536) {
+    if (nt < 2 || (size_t)R * C < 65536) {
         work(0, R);
     } else {
         std::vector<std::thread> th;
@@ -86,19 +89,52 @@ extern "C" int mpp_maaco_tables(const mpp_map *map, const mpp_maaco_params *p, d
         }
         for (auto &t : th) t.join();
     }
+}
+
+// tau0 of every map of the batch = the shared free-cell table with the map's obstacles at 1e-9 (MAACO.py:62-63)
+__global__ void mpp_maaco_tau0_kernel(const double *__restrict__ tau0_free, const uint32_t *__restrict__ occ, int occ_words,
+                                      int pitch, int R, int C, double *__restrict__ tau, long long tau_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * C) return;
+    occ += (size_t)blockIdx.y * occ_words;
+    const int r = i / C, pb = i % C + 1;
+    const bool obst = (occ[(r + 1) * pitch + (pb >> 5)] >> (pb & 31)) & 1u;
+    tau[(size_t)blockIdx.y * tau_stride + i] = obst ? 1e-9 : tau0_free[i];
+}
+
+extern "C" int mpp_maaco_tables(const mpp_map_batch *maps, const mpp_maaco_params *p, double *tau0_dev, long long tau_stride,
+                                double *E01_dev, double *dist_t_dev, void *stream) {
+    MPP_REQUIRE(maps && p && tau0_dev && E01_dev, "mpp_maaco_tables: null argument");
+    const int R = maps->rows, C = maps->cols;
+    const size_t n = (size_t)R * C;
+    MPP_REQUIRE(tau_stride >= (long long)n, "mpp_maaco_tables: tau_stride < rows*cols");
+    const MppMapMeta &M0 = maps->meta_host[0];
+    MPP_REQUIRE(M0.start >= 0 && M0.target >= 0, "mpp_maaco_tables: map has no start/target");
+    for (int k = 1; k < maps->n_maps; ++k)
+        MPP_REQUIRE(maps->meta_host[k].start == M0.start && maps->meta_host[k].target == M0.target,
+                    "mpp_maaco_tables: the maps of a batch must share start and target (map %d differs); group them", k);
+    std::vector<double> buf(4 * n);
+    double *tau0 = buf.data(), *E01 = tau0 + n, *dt = E01 + 2 * n;
+    host_tables(R, C, M0.start, M0.target, p, tau0, E01, dt);
     cudaStream_t s = (cudaStream_t)stream;
-    MPP_CUDA(cudaSetDevice(map->device));
-    MPP_CUDA(cudaMemcpyAsync(tau0_dev, tau0, n * 8, cudaMemcpyHostToDevice, s));
+    MPP_CUDA(cudaSetDevice(maps->device));
+    double *tau0_free = nullptr;
+    MPP_CUDA(cudaMalloc(&tau0_free, n * 8));
+    MPP_CUDA(cudaMemcpyAsync(tau0_free, tau0, n * 8, cudaMemcpyHostToDevice, s));
     MPP_CUDA(cudaMemcpyAsync(E01_dev, E01, 2 * n * 8, cudaMemcpyHostToDevice, s));
     if (dist_t_dev) MPP_CUDA(cudaMemcpyAsync(dist_t_dev, dt, n * 8, cudaMemcpyHostToDevice, s));
-    MPP_CUDA(cudaStreamSynchronize(s));  // buf is freed on return
+    mpp_maaco_tau0_kernel<<<dim3(((int)n + 255) / 256, maps->n_maps), 256, 0, s>>>(
+        tau0_free, maps->occ_dev, maps->occ_words, maps->pitch_words, R, C, tau0_dev, tau_stride);
+    MPP_CUDA(cudaGetLastError());
+    MPP_CUDA(cudaStreamSynchronize(s));  // buf / tau0_free are released on return
+    MPP_CUDA(cudaFree(tau0_free));
     return MPP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: tour construction
+// sizes
 // ---------------------------------------------------------------------------------------------
-// Buffer layout (uint32 words): [margin | 9*R*C strategy-1 words | margin | pad to even] [9*R*C full entries (2 words)].
+// Ranking buffer layout (uint32 words): [margin | 9*R*C strategy-1 words | margin | pad to even] [9*R*C full entries (2 words)].
 // The margins let the tour kernel read the word of a neighbour cell without bounds checks.
 struct RankLayout { size_t margin, fast_words, total_words; };
 static RankLayout rank_layout(int R, int C) {
@@ -108,265 +144,19 @@ static RankLayout rank_layout(int R, int C) {
     L.total_words = L.fast_words + (size_t)18 * R * C;
     return L;
 }
-static uint32_t host_orient_mask(int dR, int dC) {                // MAACO.py:146-157
-    uint32_t k = 0xffu;
-    if (dC > 0) k &= ~0x29u;
-    if (dC < 0) k &= ~0x94u;
-    if (dR > 0) k &= ~0x07u;
-    if (dR < 0) k &= ~0xE0u;
-    return k;
+static inline int tiles_r(int R) { return (R + 31) >> 5; }
+static inline int tiles_c(int C) { return (C + 31) >> 5; }
+
+extern "C" long long mpp_maaco_rank_words(int rows, int cols) { return (long long)rank_layout(rows, cols).total_words; }
+extern "C" long long mpp_maaco_slab_words(int tile_rows, int cols, int n_ants) {
+    return (long long)tile_rows * tiles_c(cols) * (long long)n_ants * 32;
 }
-
-struct TourS1 {              // strategy-1 constants (P1 = orientation start -> target, MAACO.py:146-165)
-    uint32_t P1;
-    int fast_ok;            // P1 has exactly three moves
-    int sm[3];              // those moves
-    int dpr[3], dc[3];      // window row pointer delta (bytes) and column delta of each
-    int so[3];              // ranking-word offset of (neighbour cell, context move+1)
-};
-
-struct TourArgs {
-    TourS1 s1;
-    const uint8_t *svalid;  // per-cell static move mask (MAACO move order)
-    const uint32_t *rank;   // ranking buffer (mpp_maaco_rank) or null; layout: rank_layout()
-    const uint32_t *rank_fast;   // word (cell*9 + ctx) of the strategy-1 table (margins on both sides)
-    const uint2 *rank_slow;      // entry (cell*9 + ctx) of the full ranking
-    int R, C, start, target;
-    const double *tau, *E01;
-    uint32_t it;
-    double q0, alpha;
-    int n_ants, ant_offset;
-    uint32_t k0, k1;
-    uint32_t *visitT;
-    int32_t *cells;
-    int max_cells;
-    mpp_ant_result *result;
-    unsigned long long *steps;
-};
-
-#ifndef MPP_TOUR_THREADS
-#define MPP_TOUR_THREADS 256
-#endif
-#ifndef MPP_TOUR_MIN_BLOCKS
-#define MPP_TOUR_MIN_BLOCKS 4
-#endif
-#define MPP_SQRT2 1.4142135623730951  // sqrt(2.0) correctly rounded == math.sqrt(2)
-
-
-// Full roulette branch MAACO.py:255-262 (rare; kept out of line so it does not cost registers
-// in the step loop).  Returns the rank (among candidates, in move order) of the selected move.
-__device__ __noinline__ int roulette_rank(double attr, uint32_t cand, uint32_t gmask, int gshift, double S, double u1) {
-    double at[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) at[i] = __shfl_sync(gmask, attr, gshift + i);
-    const int n = __popc(cand);
-    double pr[8], ps = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        pr[i] = at[i] / S;                                            // :255
-        if ((cand >> i) & 1u) ps += pr[i];
-    }
-    if (fabs(ps - 1.0) > 1e-6) {                                      // :257-258
-        const double ps0 = ps;
-        ps = 0.0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            pr[i] = pr[i] / ps0;
-            if ((cand >> i) & 1u) ps += pr[i];
-        }
-    }
-    int k;
-    if (!(fabs(ps - 1.0) <= 1.4901161193847656e-08)) {                // np.random.choice ValueError -> :262
-        k = (int)(u1 * (double)n);
-    } else {
-        // RandomState.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, side='right')
-        double acc = 0.0, cdf[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if ((cand >> i) & 1u) acc += pr[i];
-            cdf[i] = acc;
-        }
-        k = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (((cand >> i) & 1u) && (cdf[i] / acc <= u1)) ++k;
-    }
-    return k < n ? k : n - 1;
-}
-
-__device__ __noinline__ double pow_slow(double x, double y) { return pow(x, y); }
-
-// Philox block `blk` of stream (seed, TOUR, it, ant) -> the two uniforms of ant step `blk` (out of line:
-// runs once per LPA steps, keeps the ten rounds out of the step loop's register budget)
-__device__ __noinline__ void tour_uniforms(uint32_t blk, uint32_t ant, uint32_t it, uint32_t k0, uint32_t k1,
-                                           double &u0, double &u1) {
-    const mpp_u4 rb = mpp_philox(blk, ant, it, MPP_CLS_MAACO_TOUR, k0, k1);
-    u0 = mpp_u53(rb.x, rb.y);
-    u1 = mpp_u53(rb.z, rb.w);
-}
-
-template <int LPA>
-__device__ __forceinline__ uint32_t group_ballot(uint32_t gmask, int gshift, bool pred) {
-    uint32_t b = __ballot_sync(gmask, pred);
-    return (LPA == 32) ? (b & 0xffu) : ((b >> gshift) & 0xffu);  // only lanes m < 8 can vote true
-}
-
-// Per step each group (LPA lanes; lane m < 8 owns move m) does ONE round of loads -- the cell's static
-// move mask (bounds + obstacles + crossing prohibition, precomputed per map), and per move the visited
-// word, tau and E -- then one ballot, a REDUX max and the literal selection rules.  Philox blocks are
-// generated LPA steps at a time (lane m computes the block of step base+m): two double shuffles per step.
-template <int LPA>
-__global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_BLOCKS : 2) mpp_maaco_tour_kernel(const TourArgs A) {
-    const int lane = threadIdx.x & 31;
-    const int m = lane % LPA;                      // move index handled by this lane (m < 8 active)
-    const int gshift = (LPA == 32) ? 0 : (lane / LPA) * LPA;
-    const uint32_t gmask = (LPA == 32) ? 0xffffffffu : (((1u << LPA) - 1u) << gshift);
-    const int a = (blockIdx.x * MPP_TOUR_THREADS + threadIdx.x) / LPA;
-    if (a >= A.n_ants) return;
-    // move order MAACO.py:98: (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1); (delta+1) packed 2 bits/move
-    const int C = A.C, RC = A.R * A.C;
-    const int mm = m & 7;
-    const int delta = ((int)((0xA940u >> (2 * mm)) & 3u) - 1) * C + ((int)((0x9224u >> (2 * mm)) & 3u) - 1);
-    const int target = A.target;
-    const int tr = target / C, tc = target % C;
-    int cur = A.start;
-    // orientation masks MAACO.py:146-157
-    auto orient_mask = [](int dR, int dC) -> uint32_t {
-        uint32_t k = 0xffu;
-        if (dC > 0) k &= ~0x29u;  // moves with dc<0: m0,m3,m5
-        if (dC < 0) k &= ~0x94u;  // dc>0: m2,m4,m7
-        if (dR > 0) k &= ~0x07u;  // dr<0: m0,m1,m2
-        if (dR < 0) k &= ~0xE0u;  // dr>0: m5,m6,m7
-        return k;
-    };
-    const uint32_t P1 = orient_mask(tr - cur / C, tc - cur % C);
-    const uint32_t ant_global = (uint32_t)(A.ant_offset + a);
-    const size_t n_ants = (size_t)A.n_ants;
-    uint32_t *const visit_a = A.visitT + a;                      // word w of this ant at visit_a[w * n_ants]
-    int32_t *const cells_a = A.cells + (size_t)a * A.max_cells;
-    const double *const __restrict__ tau = A.tau;
-    const double *const __restrict__ E01 = A.E01;                // interleaved: E[2*cell + turn]
-    const uint8_t *const __restrict__ svalid = A.svalid;
-    const uint32_t *const __restrict__ rank = A.rank;
-    int n_path = 1, prev_m = -1, turns = 0;                       // steps taken == n_path - 1
-    double len = 0.0;
-    const int max_path = 2 * RC + 1;                              // step cap 2*R*C (MAACO.py:283); R*C < 2^30
-    bool failed = false;
-    double u0_l = 0.0, u1_l = 0.0;
-    if (m == 0) {
-        visit_a[(size_t)(cur >> 5) * n_ants] = 1u << (cur & 31);
-        cells_a[0] = cur;
-    }
-    __syncwarp(gmask);
-    int32_t *cell_out = cells_a + 1;                              // next path slot
-    while (cur != target && n_path < max_path) {
-        // ---- one round of loads: the cell's ranking word (or static mask) and this lane's visited word ----
-        // ranking word (mpp_maaco_rank): [31:24] static move mask, [23:0] rank position of each move by
-        // attractiveness (3 bits/move) for this (cell, previous move); 0xFFFFFF = "not small, use the full rule"
-        const uint32_t ctx = (n_path >= 2) ? (uint32_t)(prev_m + 1) : 0u;
-        const uint32_t rw = rank ? A.rank_slow[(size_t)cur * 9 + ctx].y : (((uint32_t)svalid[cur] << 24) | 0xFFFFFFu);
-        const uint32_t sv = rw >> 24;                                 // bounds / obstacle / corner-cut (:93-120)
-        int j = cur + delta;
-        j = j < 0 ? 0 : (j >= RC ? RC - 1 : j);                       // clamp: lanes outside the mask are ignored
-        const uint32_t tw = visit_a[(size_t)(j >> 5) * n_ants];
-        // uniforms: draws 2s (q-test) and 2s+1 (selection) of stream (seed, TOUR, it, ant); block s
-        const uint32_t step = (uint32_t)(n_path - 1), sub = step & (uint32_t)(LPA - 1);
-        if (sub == 0) tour_uniforms(step + (uint32_t)m, ant_global, A.it, A.k0, A.k1, u0_l, u1_l);
-        const double u0 = __shfl_sync(gmask, u0_l, gshift + (int)sub);
-        const double u1 = __shfl_sync(gmask, u1_l, gshift + (int)sub);
-        const bool free_lane = (m < 8) && ((sv >> m) & 1u) && !((tw >> (j & 31)) & 1u);   // + tabu :93-95
-        const uint32_t valid = group_ballot<LPA>(gmask, gshift, free_lane);
-        uint32_t cand = valid & P1;                                   // strategy 1 :165
-        if (!cand) cand = valid & orient_mask(tr - cur / C, tc - cur % C);   // strategy 2 :169
-        if (!cand) cand = valid;                                      // strategy 3 :172-180
-        if (!cand) { failed = true; break; }                          // :287-288
-        const bool in_c = (cand >> m) & 1u;                           // cand has 8 bits -> false for m >= 8
-        uint32_t pool;   // the set the final uniform index is taken from
-        int k = -1;      // >= 0: rank already decided by the roulette
-        if ((rw & 0xFFFFFFu) != 0xFFFFFFu) {
-            // every attractiveness around this cell is < 1e-10 (mpp_maaco_rank), hence:
-            //  greedy  :241-250 -> |attr_i - max| < 1e-9 for all i: pool = first arg-max + every later candidate;
-            //  roulette:251-254 -> sum < 1e-9: uniform over all candidates.
-            // Only the ORDER of the attractiveness values matters, and that was ranked once per cell.
-            if (u0 <= A.q0) {
-                const uint32_t key = in_c ? ((((rw >> (3 * m)) & 7u) << 3) | (uint32_t)m) : 0xFFu;
-                const int r = (int)(__reduce_min_sync(gmask, key) & 7u);   // best-ranked candidate == first arg-max
-                pool = cand & ~((1u << r) - 1u);
-            } else {
-                pool = cand;
-            }
-        } else {
-        const bool turn = (n_path >= 2) && (m != prev_m);             // MAACO.py:184-195
-        const double tv = tau[j];
-        const double ev = E01[2 * (size_t)j + (turn ? 1 : 0)];
-        const double ta = (A.alpha == 1.0) ? tv : pow_slow(tv, A.alpha);   // tau**alpha (x**1.0 == x exactly)
-        const double attr = ta * ev;                                  // :238
-        // group max of attr over the candidates (attr >= 0: IEEE order == unsigned bit order)
-        const unsigned long long key = in_c ? (unsigned long long)__double_as_longlong(attr) : 0ull;
-        const uint32_t hi = (uint32_t)(key >> 32);
-        const uint32_t mhi = __reduce_max_sync(gmask, hi);
-        const uint32_t lo = (in_c && hi == mhi) ? (uint32_t)key : 0u;
-        const uint32_t mlo = __reduce_max_sync(gmask, lo);
-        const double mx = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-        if (u0 <= A.q0) {
-            // greedy :241-250.  Sequential rule == {first arg-max r} U {i>r : |attr_i - max| < 1e-9}
-            const uint32_t eq = group_ballot<LPA>(gmask, gshift, in_c && attr == mx);
-            const int r = __ffs(eq) - 1;
-            if (mx < 1e-9) {
-                // every candidate lies in [0, max] with max < 1e-9, so |attr_i - max| < 1e-9 holds for all of
-                // them: the pool is the first arg-max and every later candidate
-                pool = cand & ~((1u << r) - 1u);
-            } else {
-                pool = group_ballot<LPA>(gmask, gshift, in_c && (m == r || (m > r && fabs(attr - mx) < 1e-9)));
-            }
-        } else {
-            pool = cand;
-            // :251-262.  sum() over np.float64 items == plain left-to-right.  n <= 8 terms <= mx, so
-            // 8*mx < 0.9e-9 already implies S < 1e-9
-            if (!(mx * 8.0 < 0.9e-9)) {
-                double S = 0.0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const double v = __shfl_sync(gmask, attr, gshift + i);
-                    if ((cand >> i) & 1u) S += v;
-                }
-                if (!(S < 1e-9)) k = roulette_rank(attr, cand, gmask, gshift, S, u1);  // rare: near T only
-            }
-        }
-        }
-        if (k < 0) {                                                  // random.choice(pool) -> pool[floor(u*n)]
-            const int n = __popc(pool);
-            k = (int)(u1 * (double)n);
-            k = k < n ? k : n - 1;
-        }
-        const uint32_t sel = group_ballot<LPA>(gmask, gshift, ((pool >> m) & 1u) && __popc(pool & ((1u << m) - 1u)) == k);
-        const int pick = __ffs(sel) - 1;
-        // ---- advance :293-297 ----
-        len += ((0xA5u >> pick) & 1u) ? MPP_SQRT2 : 1.0;              // diagonal moves m0,m2,m5,m7
-        if (n_path >= 2 && pick != prev_m) ++turns;                   // :264-276 counted on the fly
-        prev_m = pick;
-        if (m == pick) {
-            visit_a[(size_t)(j >> 5) * n_ants] = tw | (1u << (j & 31));
-            if (n_path < A.max_cells) *cell_out = j;
-        }
-        cur = __shfl_sync(gmask, j, gshift + pick);
-        ++n_path;
-        ++cell_out;
-        __syncwarp(gmask);
-    }
-    if (m == 0) {
-        const bool ok = !failed && cur == target;
-        mpp_ant_result res;
-        res.length = ok ? len : __longlong_as_double(0x7ff0000000000000ll);
-        res.n_cells = ok ? n_path : 0;
-        res.turns = ok ? turns : -1;
-        A.result[a] = res;
-        if (A.steps) atomicAdd(A.steps, (unsigned long long)(n_path - 1));
-    }
+extern "C" long long mpp_maaco_touched_words(int tile_rows, int cols, int n_ants) {
+    return 2ll * tile_rows * tiles_c(cols) * ((n_ants + 31) / 32);
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2, thread-per-ant form (default).  One ant step is a serial chain (position -> tabu bits -> candidate
+// K2: tour construction, one thread per ant.  One ant step is a serial chain (position -> tabu bits -> candidate
 // set -> selection -> position) and a colony pass lasts as long as its longest tour times the latency of that
 // chain, so the chain stays inside ONE thread (no shuffles / votes / warp reductions on it) and touches only
 // shared memory; a lone warp issues about one instruction per 5 cycles here, so what counts is the number of
@@ -375,9 +165,9 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
 //     words; the ant stays at least U cells inside it).  A global store to a line evicts it from L1 (measured:
 //     tools/ubench/l1_store.cu, 123 -> 432 cycles per dependent load), so re-reading a bitmap the ant itself
 //     keeps writing costs an L2 round trip per step wherever it lives in global memory.  When the ant reaches
-//     the window's edge the window slides by one 32-cell tile: the warp writes the leaving tile to the
-//     word-major visitT (what the pheromone update streams) and reloads the entering one from there; the four
-//     tiles still in the window are written at the end of the tour;
+//     the window's edge the window slides by one 32-cell tile: the warp writes the two leaving tiles to the ant's
+//     slabs (one coalesced 128-byte store each, skipped when the tile is empty) and reloads the entering ones if
+//     the ant has been there before (`touched` bit); the four tiles still in the window are written at the end;
 //   * strategy 1 (:165, almost every step): the strategy-1 word of (cell, previous move) from mpp_maaco_rank
 //     -- static move mask + what greedy selection keeps of every subset of P1's three moves -- plus the
 //     precomputed greedy flag / floor(u1*n) of the step index one shared-memory table row that yields the move
@@ -387,7 +177,31 @@ __global__ void __launch_bounds__(MPP_TOUR_THREADS, (LPA == 32) ? MPP_TOUR_MIN_B
 //   * the warp's lanes generate Philox blocks together: lane L makes the block of ant L%apw, step s+L/apw.
 // `apw` lanes of each warp own an ant: fewer ants per warp = more warps to spread over the SMs.
 // ---------------------------------------------------------------------------------------------
+struct TourArgs {
+    const MppMapMeta *meta;      // [n_maps]
+    const uint32_t *rank;        // [n_maps][rank_stride] ranking buffers (mpp_maaco_rank), layout: rank_layout()
+    size_t rank_stride, rank_margin, rank_fast_words;
+    int R, C;
+    const double *tau, *E01;
+    size_t tau_stride, E01_stride;
+    uint32_t it;
+    double q0, alpha;
+    int n_ants, ant_offset;
+    const uint64_t *seeds;       // [n_maps]
+    uint32_t *slabs, *touched;   // this pass's buffers
+    size_t slab_stride, touched_stride;
+    uint8_t *moves;
+    int max_cells;
+    mpp_ant_result *result;
+    size_t result_stride;        // results of one map (>= ant_offset + n_ants)
+    unsigned long long *steps;
+    const int32_t *latch;        // non-zero = a sharded colony's exchange overflowed: every kernel is a no-op until the host rewinds
+};
+
+#define MPP_SQRT2 1.4142135623730951  // sqrt(2.0) correctly rounded == math.sqrt(2)
 #define MPP_TOUR1_THREADS 128
+
+__device__ __noinline__ double pow_slow(double x, double y) { return pow(x, y); }
 
 // literal selection rules MAACO.py:228-262 for one ant; cand = candidate move mask (move order :98).
 __device__ __noinline__ int tour_select_slow(uint32_t cand, int cr, int cc, int C, bool have_prev, int prev_m,
@@ -448,27 +262,28 @@ __device__ __noinline__ int tour_select_slow(uint32_t cand, int cr, int cc, int 
     return mv[k];
 }
 
-// visited bits of cells (r, 32*tcx .. 32*tcx+31) from the word-major bitmap (flat cell index, 32 per word)
-__device__ __forceinline__ uint32_t tour_tile_word(const uint32_t *visit_a, size_t n_ants, int n_words, int r, int tcx,
-                                                   int R, int C, int TC) {
-    if (r < 0 || r >= R || tcx < 0 || tcx >= TC) return 0u;
-    const int f = r * C + (tcx << 5), w = f >> 5, sh = f & 31;
-    const uint32_t lo = __ldcg(visit_a + (size_t)w * n_ants);
-    if (sh == 0) return lo;
-    const uint32_t hi = (w + 1 < n_words) ? __ldcg(visit_a + (size_t)(w + 1) * n_ants) : 0u;
-    return __funnelshift_r(lo, hi, sh);
+// One 32x32-cell tile of ant `a`'s visited set, lane = tile row.  Warp-level: all 32 lanes call these together.
+struct TourSlabs {
+    uint32_t *slabs, *touched;   // of this map
+    size_t n_ants;
+    int NW, TR, TC;
+};
+__device__ __forceinline__ uint32_t tour_tile_load(const TourSlabs &V, int a, int trow, int tcx, int lane) {
+    if (trow < 0 || trow >= V.TR || tcx < 0 || tcx >= V.TC) return 0u;
+    const int tile = trow * V.TC + tcx;
+    // the bit was set (if at all) by lane 0 of this warp: lane 0 reads it back, program order on one address
+    uint32_t tw = 0u;
+    if (lane == 0) tw = __ldcg(V.touched + (size_t)tile * V.NW + (a >> 5));
+    tw = __shfl_sync(0xffffffffu, tw, 0);
+    if (!((tw >> (a & 31)) & 1u)) return 0u;
+    return __ldcg(V.slabs + ((size_t)tile * V.n_ants + a) * 32 + lane);      // row `lane` was stored by this lane
 }
-
-// the reverse: merge a window word into the word-major bitmap.  Rows are always handled by lane (r & 31), so a later
-// tour_tile_word of the same row is ordered after this by program order.  With C % 32 == 0 the window word IS the
-// bitmap word (and holds everything the bitmap held: it was loaded from there), so a plain store does.
-__device__ __forceinline__ void tour_tile_store(uint32_t *visit_a, size_t n_ants, int n_words, int r, int tcx, int R, int C,
-                                                int TC, uint32_t v) {
-    if (v == 0u || r < 0 || r >= R || tcx < 0 || tcx >= TC) return;
-    const int f = r * C + (tcx << 5), w = f >> 5, sh = f & 31;
-    if ((C & 31) == 0) { visit_a[(size_t)w * n_ants] = v; return; }
-    atomicOr(visit_a + (size_t)w * n_ants, v << sh);
-    if (sh != 0 && w + 1 < n_words && (v >> (32 - sh)) != 0u) atomicOr(visit_a + (size_t)(w + 1) * n_ants, v >> (32 - sh));
+__device__ __forceinline__ void tour_tile_store(const TourSlabs &V, int a, int trow, int tcx, int lane, uint32_t v) {
+    if (trow < 0 || trow >= V.TR || tcx < 0 || tcx >= V.TC) return;
+    if (!__any_sync(0xffffffffu, v != 0u)) return;                           // nothing visited in this tile
+    const int tile = trow * V.TC + tcx;
+    V.slabs[((size_t)tile * V.n_ants + a) * 32 + lane] = v;                  // one 128-byte line
+    if (lane == 0) atomicOr(V.touched + (size_t)tile * V.NW + (a >> 5), 1u << (a & 31));
 }
 
 // a load the compiler may not sink to its use (it would turn "select among three loaded entries" into "one load
@@ -505,7 +320,7 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 
-// shared-memory tables of the thread-per-ant kernel (per block)
+// shared-memory tables of the tour kernel (per block)
 struct Tour1Move {          // one per move (order MAACO.py:98)
     int dcur;               // flat cell delta  dr*C + dc
     int dprow;              // byte delta of the window row pointer  dr*8
@@ -520,10 +335,14 @@ struct Tour1Move {          // one per move (order MAACO.py:98)
 #define T1_RNG_OFF (4096 + 256 + 512)       // per warp: double2 u[32] (512 B) + uint32 pack[32] (128 B)
 #define T1_WIN_OFF (T1_RNG_OFF + (MPP_TOUR1_THREADS / 32) * 640)
 
-__global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(const TourArgs A, const int apw) {
+__global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(const TourArgs A, const int apw) {
     extern __shared__ __align__(16) uint8_t t1_smem[];
+    if (A.latch && *A.latch) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int R = A.R, C = A.C, TC = (C + 31) >> 5;
+    const int map = blockIdx.y;
+    const MppMapMeta &MM = A.meta[map];
+    const MppS1 s1 = MM.s1;
     {   // ---- tables ----
         uint8_t *const kth = t1_smem + T1_KTH_OFF;
         uint2 *const spread = (uint2 *)(t1_smem + T1_SPREAD_OFF);
@@ -548,7 +367,7 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
         }
         if (threadIdx.x < 32) {                                    // (k, subset of P1's three moves) -> k-th member
             const int k = threadIdx.x >> 3, p3 = threadIdx.x & 7;
-            const uint32_t P1t = A.s1.P1;
+            const uint32_t P1t = s1.P1;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (__popc(P1t) == 3) {
                 const int s[3] = {__ffs(P1t) - 1, __ffs(P1t & (P1t - 1)) - 1, 31 - __clz(P1t)};
@@ -565,16 +384,15 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
     double2 *const rngu = (double2 *)(t1_smem + T1_RNG_OFF + wib * 640);
     uint32_t *const rngp = (uint32_t *)(t1_smem + T1_RNG_OFF + wib * 640 + 512);
     uint2 *const win_w = (uint2 *)(t1_smem + T1_WIN_OFF) + (size_t)wib * apw * 64;   // the warp's windows: 64 rows x uint2 each
-    for (int i = lane; i < apw * 64; i += 32) win_w[i] = make_uint2(0u, 0u);          // visitT is zero on entry, so is the window
+    for (int i = lane; i < apw * 64; i += 32) win_w[i] = make_uint2(0u, 0u);          // a tour starts with nothing visited
     __syncthreads();
     const int warp = (blockIdx.x * MPP_TOUR1_THREADS + threadIdx.x) >> 5;
     const int a0 = warp * apw;                                     // first ant of this warp
     if (a0 >= A.n_ants) return;                                    // whole warp
     const int a = a0 + lane;
     bool active = lane < apw && a < A.n_ants;
-    const int n_words = (R * C + 31) >> 5;
-    const int target = A.target;
-    int cur = A.start;
+    const int target = MM.target;
+    int cur = MM.start;
     auto orient_mask = [](int dR, int dC) -> uint32_t {           // MAACO.py:146-157
         uint32_t k = 0xffu;
         if (dC > 0) k &= ~0x29u;
@@ -584,34 +402,37 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
         return k;
     };
     const int tr = target / C, tc = target % C;
-    const uint32_t P1 = A.s1.P1;                                  // the same for every ant: start and target are the map's
+    const uint32_t P1 = s1.P1;                                     // the same for every ant of a map
     // the ranking entry of the next cell is fetched before the move is chosen: one load per strategy-1 move (the
     // first three of P1; P1 has 3 moves unless start and target share a row or column)
-    // strategy 1 usually leaves three moves (a quadrant); then each step works on those three only
-    const bool fast_ok = A.s1.fast_ok;
-    const int sm0 = A.s1.sm[0], sm1 = A.s1.sm[1], sm2 = A.s1.sm[2];
-    const int dpr0 = A.s1.dpr[0], dpr1 = A.s1.dpr[1], dpr2 = A.s1.dpr[2];
-    const int dc0 = A.s1.dc[0], dc1 = A.s1.dc[1], dc2 = A.s1.dc[2];
-    const int so0 = A.s1.so[0], so1 = A.s1.so[1], so2 = A.s1.so[2];
-    // (kept in registers: re-reading kernel parameters inside the step costs a constant-bank round trip each time)
-#define T1_KEEP(x) x = __shfl_sync(0xffffffffu, x, 0)   /* a value ptxas cannot re-derive from the parameter bank */
-    int k_sm0 = sm0, k_sm1 = sm1, k_sm2 = sm2, k_dpr0 = dpr0, k_dpr1 = dpr1, k_dpr2 = dpr2;
-    int k_dc0 = dc0, k_dc1 = dc1, k_dc2 = dc2, k_so0 = so0, k_so1 = so1, k_so2 = so2;
+    const bool fast_ok = s1.fast_ok;
+    // (kept in registers: re-reading them inside the step costs a memory round trip each time)
+#define T1_KEEP(x) x = __shfl_sync(0xffffffffu, x, 0)   /* a value ptxas cannot re-derive from its source */
+    int k_sm0 = s1.sm[0], k_sm1 = s1.sm[1], k_sm2 = s1.sm[2], k_dpr0 = s1.dpr[0], k_dpr1 = s1.dpr[1], k_dpr2 = s1.dpr[2];
+    int k_dc0 = s1.dc[0], k_dc1 = s1.dc[1], k_dc2 = s1.dc[2], k_so0 = s1.so[0], k_so1 = s1.so[1], k_so2 = s1.so[2];
     T1_KEEP(k_sm0); T1_KEEP(k_sm1); T1_KEEP(k_sm2); T1_KEEP(k_dpr0); T1_KEEP(k_dpr1); T1_KEEP(k_dpr2);
     T1_KEEP(k_dc0); T1_KEEP(k_dc1); T1_KEEP(k_dc2); T1_KEEP(k_so0); T1_KEEP(k_so1); T1_KEEP(k_so2);
-    const size_t n_ants = (size_t)A.n_ants;
-    int32_t *const cells_a = A.cells + (size_t)(active ? a : a0) * A.max_cells;
-    const uint32_t *__restrict__ rank_fast = A.rank_fast;
+    TourSlabs V;
+    V.slabs = A.slabs + (size_t)map * A.slab_stride;
+    V.touched = A.touched + (size_t)map * A.touched_stride;
+    V.n_ants = (size_t)A.n_ants; V.NW = (A.n_ants + 31) >> 5; V.TR = (R + 31) >> 5; V.TC = TC;
+    uint8_t *const moves_a = A.moves + ((size_t)map * A.n_ants + (active ? a : a0)) * A.max_cells;
+    const double *const tau_m = A.tau + (size_t)map * A.tau_stride;
+    const double *const E01_m = A.E01 + (size_t)map * A.E01_stride;
+    const uint32_t *__restrict__ rank_fast = A.rank + (size_t)map * A.rank_stride + A.rank_margin;
+    const uint2 *const rank_slow = (const uint2 *)(A.rank + (size_t)map * A.rank_stride + A.rank_fast_words);
     {
         unsigned long long rf = (unsigned long long)rank_fast;
         rf = __shfl_sync(0xffffffffu, rf, 0);
         rank_fast = (const uint32_t *)rf;
     }
-    int k_target = A.target, k_max_cells = A.max_cells;
+    int k_target = target, k_max_cells = A.max_cells;
     T1_KEEP(k_target); T1_KEEP(k_max_cells);
+    const uint64_t seed = A.seeds[map];
+    const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     int n_path = 1, prev_m = -1, turns = 0;
     double len = 0.0;
-    const int max_path = 2 * R * C + 1;
+    const int max_path = 2 * R * C + 1;                            // step cap 2*R*C (MAACO.py:283); R*C < 2^30
     bool failed = false;
     // window = tile rows {wr, wr+1} x tile cols {wc, wc+1} (64 x 64 cells); row lrow of it is the uint2 at prow,
     // bit lcol of that 64-bit row is the cell; the ant stays in [1, 62] x [1, 62]
@@ -632,14 +453,13 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
     uint32_t pf0 = 0u, pf1 = 0u, pf2 = 0u;                        // ... of the three strategy-1 neighbours, prefetched
     if (active) {
         asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(prow_s + 4u * ((uint32_t)lcol >> 5)), "r"(1u << (lcol & 31)) : "memory");
-        cells_a[0] = cur;
         fw = rank_fast[(size_t)cur * 9];                          // context 0: no previous move
         // (read it here: a first use inside the loop would make every step wait on this load's scoreboard, which the
         // loop's own prefetches share.)  Field 0 is 0 or 7, so the test is never true.
         if (cur == target || (fw & 7u) == 3u) active = false;
         if (fast_ok) {
             const uint32_t *const rk = rank_fast + (size_t)cur * 9;
-            pf0 = ldg32_pinned(rk + so0); pf1 = ldg32_pinned(rk + so1); pf2 = ldg32_pinned(rk + so2);
+            pf0 = ldg32_pinned(rk + k_so0); pf1 = ldg32_pinned(rk + k_so1); pf2 = ldg32_pinned(rk + k_so2);
         }
     }
     __syncwarp();
@@ -659,7 +479,7 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                 // every pool size n = 1..8 (random.choice on n items).
                 const int la = lane & (apw - 1);
                 const mpp_u4 rb = mpp_philox(step + (uint32_t)(lane / apw), (uint32_t)(A.ant_offset + a0 + la), A.it,
-                                             MPP_CLS_MAACO_TOUR, A.k0, A.k1);
+                                             MPP_CLS_MAACO_TOUR, key0, key1);
                 const double u0 = mpp_u53(rb.x, rb.y), u1 = mpp_u53(rb.z, rb.w);
                 uint32_t pack = (u0 <= A.q0) ? (1u << 24) : 0u;
 #pragma unroll
@@ -679,31 +499,30 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                 const int src = __ffs(need) - 1;
                 const int s_lrow = __shfl_sync(0xffffffffu, lrow, src), s_lcol = __shfl_sync(0xffffffffu, lcol, src);
                 const int s_wr = __shfl_sync(0xffffffffu, wr, src), s_wc = __shfl_sync(0xffffffffu, wc, src);
-                uint32_t *const v_s = A.visitT + (a0 + src);
+                const int a_s = a0 + src;
                 uint2 *const w_s = win_w + src * 64;
                 int d_wr = 0, d_wc = 0;
-                if ((unsigned)s_lrow - edge_lo > edge_span) {      // vertical: rows move by 32, one tile row leaves, one enters
+                if ((unsigned)s_lrow - edge_lo > edge_span) {      // vertical: one tile row leaves, one enters
                     const bool up = s_lrow < U;
                     d_wr = up ? -1 : 1;
-                    const int r_out = ((up ? s_wr + 1 : s_wr) << 5) + lane, r_in = ((up ? s_wr - 1 : s_wr + 2) << 5) + lane;
+                    const int t_out = up ? s_wr + 1 : s_wr, t_in = up ? s_wr - 1 : s_wr + 2;
                     const uint2 keep = w_s[up ? lane : lane + 32], out = w_s[up ? lane + 32 : lane];
-                    tour_tile_store(v_s, n_ants, n_words, r_out, s_wc, R, C, TC, out.x);
-                    tour_tile_store(v_s, n_ants, n_words, r_out, s_wc + 1, R, C, TC, out.y);
+                    tour_tile_store(V, a_s, t_out, s_wc, lane, out.x);
+                    tour_tile_store(V, a_s, t_out, s_wc + 1, lane, out.y);
                     uint2 nw;
-                    nw.x = tour_tile_word(v_s, n_ants, n_words, r_in, s_wc, R, C, TC);
-                    nw.y = tour_tile_word(v_s, n_ants, n_words, r_in, s_wc + 1, R, C, TC);
+                    nw.x = tour_tile_load(V, a_s, t_in, s_wc, lane);
+                    nw.y = tour_tile_load(V, a_s, t_in, s_wc + 1, lane);
                     w_s[up ? lane + 32 : lane] = keep;
                     w_s[up ? lane : lane + 32] = nw;
                 } else {                                           // horizontal: the two words of each row shift
                     const bool left = s_lcol < U;
                     d_wc = left ? -1 : 1;
                     const int t_out = left ? s_wc + 1 : s_wc, t_in = left ? s_wc - 1 : s_wc + 2;
-                    const int r = (s_wr << 5) + lane;
                     const uint2 o0 = w_s[lane], o1 = w_s[lane + 32];
-                    tour_tile_store(v_s, n_ants, n_words, r, t_out, R, C, TC, left ? o0.y : o0.x);
-                    tour_tile_store(v_s, n_ants, n_words, r + 32, t_out, R, C, TC, left ? o1.y : o1.x);
-                    const uint32_t x0 = tour_tile_word(v_s, n_ants, n_words, r, t_in, R, C, TC);
-                    const uint32_t x1 = tour_tile_word(v_s, n_ants, n_words, r + 32, t_in, R, C, TC);
+                    tour_tile_store(V, a_s, s_wr, t_out, lane, left ? o0.y : o0.x);
+                    tour_tile_store(V, a_s, s_wr + 1, t_out, lane, left ? o1.y : o1.x);
+                    const uint32_t x0 = tour_tile_load(V, a_s, s_wr, t_in, lane);
+                    const uint32_t x1 = tour_tile_load(V, a_s, s_wr + 1, t_in, lane);
                     w_s[lane] = left ? make_uint2(x0, o0.x) : make_uint2(o0.y, x0);
                     w_s[lane + 32] = left ? make_uint2(x1, o1.x) : make_uint2(o1.y, x1);
                 }
@@ -769,13 +588,13 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                         m = __ffs(cand) - 1;                          // one candidate: every rule picks it
                     } else if ((fw & 7u) != 0u) {                     // some attractiveness >= 1e-10: literal rules
                         const double2 uu = rngu[(su & gmask) * apw + lane];
-                        m = tour_select_slow(cand, cur / C, cur % C, C, n_path >= 2, prev_m, A.tau, A.E01, A.alpha, A.q0, uu.x, uu.y);
+                        m = tour_select_slow(cand, cur / C, cur % C, C, n_path >= 2, prev_m, tau_m, E01_m, A.alpha, A.q0, uu.x, uu.y);
                     } else {
                         uint32_t pool = cand;                         // roulette over tiny values: uniform (:253-254)
                         if (pack & (1u << 24)) {
                             // greedy: first arg-max = best-ranked candidate (full entry: permute the candidate flags
                             // into rank order, take the first) and every later candidate
-                            const uint2 rws = A.rank_slow[(size_t)cur * 9 + (n_path >= 2 ? prev_m + 1 : 0)];
+                            const uint2 rws = rank_slow[(size_t)cur * 9 + (n_path >= 2 ? prev_m + 1 : 0)];
                             const uint2 sp = lds_u2(sbase_k + T1_SPREAD_OFF + 8u * cand);
                             const uint32_t f0 = __byte_perm(sp.x, sp.y, rws.x & 0xFFFFu), f1 = __byte_perm(sp.x, sp.y, rws.x >> 16);
                             const uint32_t ff = f0 ? f0 : f1;
@@ -815,7 +634,7 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
                 lrow += dpr >> 3;
                 lcol += dcc;
                 asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(prow_s + 4u * ((uint32_t)lcol >> 5)), "r"(1u << (lcol & 31)) : "memory");
-                if (n_path < k_max_cells) cells_a[n_path] = cur;
+                if (n_path <= k_max_cells) moves_a[n_path - 1] = (uint8_t)m;   // move code of step n_path-1
                 len += lds_f64(sbase_k + T1_DLEN_OFF + 8u * (uint32_t)m);
                 if (n_path >= 2 && m != prev_m) ++turns;              // :264-276 counted on the fly
                 prev_m = m;
@@ -824,16 +643,14 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
             }
         }
     }
-    // ---- the windows still hold the marks of their four tiles: merge them into visitT ----
+    // ---- the windows still hold the marks of their four tiles: write them to the ants' slabs ----
     for (int src = 0; src < apw && a0 + src < A.n_ants; ++src) {
         const int s_wr = __shfl_sync(0xffffffffu, wr, src), s_wc = __shfl_sync(0xffffffffu, wc, src);
-        uint32_t *const v_s = A.visitT + (a0 + src);
         const uint2 o0 = win_w[src * 64 + lane], o1 = win_w[src * 64 + lane + 32];
-        const int r = (s_wr << 5) + lane;
-        tour_tile_store(v_s, n_ants, n_words, r, s_wc, R, C, TC, o0.x);
-        tour_tile_store(v_s, n_ants, n_words, r, s_wc + 1, R, C, TC, o0.y);
-        tour_tile_store(v_s, n_ants, n_words, r + 32, s_wc, R, C, TC, o1.x);
-        tour_tile_store(v_s, n_ants, n_words, r + 32, s_wc + 1, R, C, TC, o1.y);
+        tour_tile_store(V, a0 + src, s_wr, s_wc, lane, o0.x);
+        tour_tile_store(V, a0 + src, s_wr, s_wc + 1, lane, o0.y);
+        tour_tile_store(V, a0 + src, s_wr + 1, s_wc, lane, o1.x);
+        tour_tile_store(V, a0 + src, s_wr + 1, s_wc + 1, lane, o1.y);
     }
     if (lane < apw && a < A.n_ants) {
         const bool ok = !failed && cur == target;
@@ -841,83 +658,65 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS) mpp_maaco_tour1_kernel(cons
         res.length = ok ? len : __longlong_as_double(0x7ff0000000000000ll);
         res.n_cells = ok ? n_path : 0;
         res.turns = ok ? turns : -1;
-        A.result[a] = res;
+        A.result[(size_t)map * A.result_stride + A.ant_offset + a] = res;
         if (A.steps) atomicAdd(A.steps, (unsigned long long)(n_path - 1));
     }
 }
 
-extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const double *E01_dev,
-                               const uint32_t *rank_dev, int iteration, double q0, double alpha, int n_ants, int ant_offset, uint64_t seed,
-                               uint32_t *visitT_dev, int32_t *cells_dev, int max_cells, mpp_ant_result *result_dev,
-                               unsigned long long *steps_dev, int lanes_per_ant, void *stream) {
-    MPP_REQUIRE(map && tau_dev && E01_dev && visitT_dev && cells_dev && result_dev, "mpp_maaco_tours: null argument");
-    MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_tours: map has no start/target");
-    MPP_REQUIRE(n_ants > 0 && max_cells > 0, "mpp_maaco_tours: n_ants=%d max_cells=%d", n_ants, max_cells);
-    int apw_hint = 0;                                             // lanes_per_ant = -k: thread per ant, k ants per warp
-    if (lanes_per_ant < 0) { apw_hint = -lanes_per_ant; lanes_per_ant = 1; }
-    if (lanes_per_ant == 0) {
-        const char *e = getenv("MPP_TOUR_LPA");
-        lanes_per_ant = e ? atoi(e) : 1;   // measured on B200: thread-per-ant beats the cooperative forms from 256 to 16k ants
-    }
-    MPP_REQUIRE(lanes_per_ant == 1 || lanes_per_ant == 8 || lanes_per_ant == 16 || lanes_per_ant == 32,
-                "mpp_maaco_tours: lanes_per_ant must be 1, 8, 16 or 32");
-    MPP_CUDA(cudaSetDevice(map->device));
+static int colony_check(const mpp_map_batch *maps, const mpp_colony *c, const char *who) {
+    MPP_REQUIRE(maps && c, "%s: null argument", who);
+    MPP_REQUIRE(c->tau && c->E01 && c->rank && c->slabs && c->touched && c->moves && c->result && c->deposit && c->okbits &&
+                    c->state && c->best_cells && c->seeds, "%s: null colony buffer", who);
+    MPP_REQUIRE(c->max_cells > 0 && c->tau_stride >= (long long)maps->rows * maps->cols, "%s: bad max_cells / tau_stride", who);
+    for (int k = 0; k < maps->n_maps; ++k)
+        MPP_REQUIRE(maps->meta_host[k].start >= 0 && maps->meta_host[k].target >= 0, "%s: map %d has no start/target", who, k);
+    return MPP_OK;
+}
+
+extern "C" int mpp_maaco_tours(const mpp_map_batch *maps, const mpp_colony *c, int iteration, double q0, double alpha,
+                               int n_ants, int ant_offset, int n_ants_total, int ants_per_warp, void *stream) {
+    int rc = colony_check(maps, c, "mpp_maaco_tours");
+    if (rc) return rc;
+    MPP_REQUIRE(n_ants > 0 && ant_offset >= 0 && ant_offset + n_ants <= n_ants_total, "mpp_maaco_tours: bad ant range");
+    MPP_CUDA(cudaSetDevice(maps->device));
+    const RankLayout L = rank_layout(maps->rows, maps->cols);
+    const int TR = tiles_r(maps->rows);
     TourArgs A;
-    A.svalid = map->svalid_dev;
-    A.rank = rank_dev;
-    {
-        TourS1 &S = A.s1;
-        S.P1 = host_orient_mask(map->target / map->cols - map->start / map->cols, map->target % map->cols - map->start % map->cols);
-        S.fast_ok = __builtin_popcount(S.P1) == 3;
-        uint32_t rest = S.P1;
-        for (int i = 0; i < 3; ++i) {
-            const int m = S.fast_ok ? __builtin_ctz(rest) : __builtin_ctz(S.P1);
-            rest &= rest - 1;
-            const int dr = (int)((0xA940u >> (2 * m)) & 3u) - 1, dc = (int)((0x9224u >> (2 * m)) & 3u) - 1;
-            S.sm[i] = m; S.dpr[i] = dr * 8; S.dc[i] = dc; S.so[i] = (dr * map->cols + dc) * 9 + m + 1;
-        }
-    }
-    {
-        const RankLayout L = rank_layout(map->rows, map->cols);
-        A.rank_fast = rank_dev ? rank_dev + L.margin : nullptr;
-        A.rank_slow = rank_dev ? (const uint2 *)(rank_dev + L.fast_words) : nullptr;
-    }
-    A.R = map->rows; A.C = map->cols; A.start = map->start; A.target = map->target;
-    A.tau = tau_dev; A.E01 = E01_dev;
+    A.meta = maps->meta_dev;
+    A.rank = c->rank; A.rank_stride = L.total_words; A.rank_margin = L.margin; A.rank_fast_words = L.fast_words;
+    A.R = maps->rows; A.C = maps->cols;
+    A.tau = c->tau; A.tau_stride = (size_t)c->tau_stride; A.E01 = c->E01; A.E01_stride = (size_t)c->E01_stride;
     A.it = (uint32_t)iteration; A.q0 = q0; A.alpha = alpha;
     A.n_ants = n_ants; A.ant_offset = ant_offset;
-    A.k0 = (uint32_t)seed; A.k1 = (uint32_t)(seed >> 32);
-    A.visitT = visitT_dev; A.cells = cells_dev; A.max_cells = max_cells;
-    A.result = result_dev; A.steps = steps_dev;
-    if (lanes_per_ant == 1 && !rank_dev) lanes_per_ant = 32;      // the thread-per-ant kernel needs the ranking table
-    if (lanes_per_ant == 1) {
-        // ants per warp: enough warps for every SM sub-partition first, full warps only for big colonies
-        int apw = 32;
-        const char *e = getenv("MPP_TOUR_APW");
-        if (e) apw = atoi(e);
-        else if (apw_hint) apw = apw_hint;
-        else while (apw > 2 && (n_ants + apw - 1) / apw < 12 * map->sm_count) apw >>= 1;   // measured: 2 ants/warp at 4096 ants
-        MPP_REQUIRE(apw == 1 || apw == 2 || apw == 4 || apw == 8 || apw == 16 || apw == 32, "ants per warp (MPP_TOUR_APW / -lanes_per_ant) must be a power of two <= 32");
-        const int warps = (n_ants + apw - 1) / apw, wpb = MPP_TOUR1_THREADS / 32;
-        const size_t smem = T1_WIN_OFF + (size_t)wpb * apw * 512;   // tables + per-warp RNG + 512-byte windows
-        {   // raise the kernel's dynamic shared-memory limit only when it grows (the call is slow; devices tracked apart)
-            static size_t smem_set[64] = {0};
-            const int dv = map->device & 63;
-            if (smem > smem_set[dv]) {
-                MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                smem_set[dv] = smem;
-            }
-        }
-        mpp_maaco_tour1_kernel<<<(warps + wpb - 1) / wpb, MPP_TOUR1_THREADS, smem, (cudaStream_t)stream>>>(A, apw);
-        MPP_CUDA(cudaGetLastError());
-        return MPP_OK;
+    A.seeds = c->seeds;
+    const size_t tw = (size_t)mpp_maaco_touched_words(TR, maps->cols, n_ants) / 2;   // one parity, one map
+    A.slabs = c->slabs; A.slab_stride = (size_t)mpp_maaco_slab_words(TR, maps->cols, n_ants);
+    A.touched = c->touched + (size_t)(iteration & 1) * tw * maps->n_maps; A.touched_stride = tw;
+    A.moves = c->moves; A.max_cells = c->max_cells;
+    A.result = c->result; A.result_stride = (size_t)n_ants_total;
+    A.steps = c->steps; A.latch = c->latch;
+    // ants per warp: enough warps for every SM sub-partition first, full warps only for big colonies
+    int apw = 32;
+    const char *e = getenv("MPP_TOUR_APW");
+    if (e) apw = atoi(e);
+    else if (ants_per_warp) apw = ants_per_warp;
+    else {
+        const long long total = (long long)n_ants * maps->n_maps;
+        while (apw > 2 && (total + apw - 1) / apw < 12ll * maps->sm_count) apw >>= 1;   // measured: 2 ants/warp at 4096 ants
     }
-    const int ants_per_block = MPP_TOUR_THREADS / lanes_per_ant;
-    const int blocks = (n_ants + ants_per_block - 1) / ants_per_block;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (lanes_per_ant == 32) mpp_maaco_tour_kernel<32><<<blocks, MPP_TOUR_THREADS, 0, s>>>(A);
-    else if (lanes_per_ant == 16) mpp_maaco_tour_kernel<16><<<blocks, MPP_TOUR_THREADS, 0, s>>>(A);
-    else mpp_maaco_tour_kernel<8><<<blocks, MPP_TOUR_THREADS, 0, s>>>(A);
+    MPP_REQUIRE(apw == 1 || apw == 2 || apw == 4 || apw == 8 || apw == 16 || apw == 32,
+                "ants per warp (MPP_TOUR_APW / ants_per_warp) must be a power of two <= 32");
+    const int warps = (n_ants + apw - 1) / apw, wpb = MPP_TOUR1_THREADS / 32;
+    const size_t smem = T1_WIN_OFF + (size_t)wpb * apw * 512;   // tables + per-warp RNG + 512-byte windows
+    {   // raise the kernel's dynamic shared-memory limit only when it grows (the call is slow; devices tracked apart)
+        static size_t smem_set[64] = {0};
+        const int dv = maps->device & 63;
+        if (smem > smem_set[dv]) {
+            MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set[dv] = smem;
+        }
+    }
+    mpp_maaco_tour1_kernel<<<dim3((warps + wpb - 1) / wpb, maps->n_maps), MPP_TOUR1_THREADS, smem, (cudaStream_t)stream>>>(A, apw);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
@@ -925,34 +724,38 @@ extern "C" int mpp_maaco_tours(const mpp_map *map, const double *tau_dev, const 
 // ---------------------------------------------------------------------------------------------
 // K2a: per (cell, turn context) ranking of the 8 moves by attractiveness tau**alpha * eta'**beta (MAACO.py:238).
 // With beta = 7 the values are ~1e-8..1e-20, so the selection rules (:241-262) only depend on their ORDER
-// (|attr_i - max| < 1e-9 and sum < 1e-9 always hold); the tour kernels then need one or two words per step
+// (|attr_i - max| < 1e-9 and sum < 1e-9 always hold); the tour kernel then needs one word per step
 // instead of 16 fp64 loads.  Context 0 = no previous move (turn flag 0 for every candidate, :185-186),
 // context p+1 = previous move p (turn flag = (m != p)).  Entry = two words.  Word 1: [31:24] static move mask,
 // [23:0] rank position of each move (0 = largest attractiveness, ties -> lower move index, exactly the order the
-// sequential scan sees), or 0xFFFFFF when some attractiveness is >= 1e-10 (the tour kernels then apply the full
+// sequential scan sees), or 0xFFFFFF when some attractiveness is >= 1e-10 (the tour kernel then applies the full
 // rule).  Word 0: the inverse permutation, nibble p = move at rank position p (a PRMT selector).
-// ---------------------------------------------------------------------------------------------
-
-extern "C" long long mpp_maaco_rank_words(const mpp_map *map) {
-    if (!map) return 0;
-    return (long long)rank_layout(map->rows, map->cols).total_words;
-}
-
+//
 // Strategy-1 word (one per (cell, context)): [31:24] static move mask; field c (3 bits at 3c, c = 1..7 = a subset of
 // P1's three moves in move order) = what greedy selection (:241-250) keeps of candidate set c, as a subset again;
 // field 0 = 0 when the ranking applies (all attractiveness < 1e-10), 7 when it does not; fields 1..7 are only
 // filled when P1 has exactly three moves.
-__global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__restrict__ svalid,
-                                                             const double *__restrict__ tau,
-                                                             const double *__restrict__ E01, double alpha, int R, int C,
-                                                             uint32_t P1, uint32_t *__restrict__ rank_fast,
-                                                             uint2 *__restrict__ rank_slow) {
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__restrict__ svalid_all,
+                                                             const double *__restrict__ tau_all, size_t tau_stride,
+                                                             const double *__restrict__ E01_all, size_t E01_stride,
+                                                             double alpha, int R, int C,
+                                                             const MppMapMeta *__restrict__ meta, uint32_t *__restrict__ rank_all,
+                                                             size_t rank_stride, size_t rank_margin, size_t rank_fast_words,
+                                                             const int32_t *__restrict__ latch) {
     // one thread per cell: the eight neighbours' tau / eta' are read once and serve all nine contexts
     const int cell = blockIdx.x * 128 + threadIdx.x;
     if (cell >= R * C) return;
+    if (latch && *latch) return;
+    const int map = blockIdx.y;
+    const uint8_t *svalid = svalid_all + (size_t)map * R * C;
+    const double *tau = tau_all + (size_t)map * tau_stride;
+    const double *E01 = E01_all + (size_t)map * E01_stride;
+    uint32_t *rank_fast = rank_all + (size_t)map * rank_stride + rank_margin;
+    uint2 *rank_slow = (uint2 *)(rank_all + (size_t)map * rank_stride + rank_fast_words);
+    const uint32_t P1 = meta[map].s1.P1;
     const uint32_t sv = svalid[cell];
     double a0[8], a1[8];                                          // attractiveness without / with the turn factor (:238)
-    double mx = 0.0;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
         a0[m] = a1[m] = -1.0;
@@ -963,7 +766,6 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
             const double2 e = *(const double2 *)(E01 + 2 * (size_t)j);
             a0[m] = ta * e.x;
             a1[m] = ta * e.y;
-            mx = fmax(mx, fmax(a0[m], a1[m]));
         }
     }
     const bool p1_three = __popc(P1) == 3;
@@ -1005,53 +807,68 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
         rank_fast[t] = fast | (sv << 24);
         rank_slow[t] = make_uint2(perm, word | (sv << 24));
     }
-    (void)mx;
 }
 
-extern "C" int mpp_maaco_rank(const mpp_map *map, const double *tau_dev, const double *E01_dev, double alpha,
-                              uint32_t *rank_dev, void *stream) {
-    MPP_REQUIRE(map && tau_dev && E01_dev && rank_dev, "mpp_maaco_rank: null argument");
-    MPP_REQUIRE(map->start >= 0 && map->target >= 0, "mpp_maaco_rank: map has no start/target");
-    MPP_CUDA(cudaSetDevice(map->device));
-    const int total = map->rows * map->cols;
-    const RankLayout L = rank_layout(map->rows, map->cols);
-    const uint32_t P1 = host_orient_mask(map->target / map->cols - map->start / map->cols,
-                                         map->target % map->cols - map->start % map->cols);
-    mpp_maaco_rank_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        map->svalid_dev, tau_dev, E01_dev, alpha, map->rows, map->cols, P1, rank_dev + L.margin,
-        (uint2 *)(rank_dev + L.fast_words));
+extern "C" int mpp_maaco_rank(const mpp_map_batch *maps, const mpp_colony *c, double alpha, void *stream) {
+    int rc = colony_check(maps, c, "mpp_maaco_rank");
+    if (rc) return rc;
+    MPP_CUDA(cudaSetDevice(maps->device));
+    const int total = maps->rows * maps->cols;
+    const RankLayout L = rank_layout(maps->rows, maps->cols);
+    mpp_maaco_rank_kernel<<<dim3((total + 127) / 128, maps->n_maps), 128, 0, (cudaStream_t)stream>>>(
+        maps->svalid_dev, c->tau, (size_t)c->tau_stride, c->E01, (size_t)c->E01_stride, alpha, maps->rows, maps->cols,
+        maps->meta_dev, c->rank, L.total_words, L.margin, L.fast_words, c->latch);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4: iteration-best / overall-best (MAACO.py:343-358) + deposits (:307-308)
+// K4: iteration-best / overall-best (MAACO.py:343-358) + deposits (:307-308) + the "deposits at all" bitmap the
+// pheromone update filters its ant lists with; one block per map
 // ---------------------------------------------------------------------------------------------
 #define MPP_BEST_THREADS 1024
 __device__ __forceinline__ bool lt_len_idx(double la, int ia, double lb, int ib) {
     return la < lb || (la == lb && ia < ib);
 }
+__device__ __forceinline__ int move_delta(uint32_t m, int C) {
+    return ((int)((0xA940u >> (2 * m)) & 3u) - 1) * C + ((int)((0x9224u >> (2 * m)) & 3u) - 1);
+}
 
 __global__ void __launch_bounds__(MPP_BEST_THREADS)
-mpp_maaco_best_kernel(const mpp_ant_result *__restrict__ res, const int32_t *__restrict__ cells, int max_cells,
-                      int cells_ant_offset, int cells_n_ants, int n, double Q, int iteration, mpp_maaco_state *state,
-                      int32_t *best_cells, double *deposit, double *log) {
+mpp_maaco_best_kernel(const mpp_ant_result *__restrict__ res_all, const uint8_t *__restrict__ moves_all, int max_cells,
+                      int moves_ant_offset, int moves_n_ants, int n, double Q, int iteration, int C,
+                      const MppMapMeta *__restrict__ meta, mpp_maaco_state *state_all, int32_t *best_cells_all,
+                      double *deposit_all, uint32_t *okbits_all, double *log_all, int log_rows,
+                      const int32_t *__restrict__ latch) {
     __shared__ double s_len[32];
     __shared__ int s_idx[32];
     __shared__ int s_t[32];
     __shared__ double b_len;
-    __shared__ int b_r, b_ant, b_turns, b_copy;
+    __shared__ int b_r, b_ant, b_turns, b_copy, s_base;
+    if (latch && *latch) return;
+    const int map = blockIdx.x;
+    const mpp_ant_result *res = res_all + (size_t)map * n;
+    double *deposit = deposit_all + (size_t)map * n;
+    uint32_t *okbits = okbits_all + (size_t)map * ((n + 31) >> 5);
+    mpp_maaco_state *state = state_all + map;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double INF = __longlong_as_double(0x7ff0000000000000ll);
     // phase 1: global min length and its first index r (the last strict record of the scan)
     double ml = INF;
     int mi = 0x7fffffff;
-    for (int i = tid; i < n; i += MPP_BEST_THREADS) {
-        const mpp_ant_result ri = res[i];
-        const double l = ri.length;
-        if (lt_len_idx(l, i, ml, mi)) { ml = l; mi = i; }
-        // deposit amount MAACO.py:307-308 (0.0 == "does not deposit"; x + 0.0 is exact anyway)
-        deposit[i] = (l != INF && ri.n_cells > 0 && l > 1e-6) ? Q / l : 0.0;
+    for (int i0 = 0; i0 < n; i0 += MPP_BEST_THREADS) {               // whole warps stay together for the ballot
+        const int i = i0 + tid;
+        bool dep = false;
+        if (i < n) {
+            const mpp_ant_result ri = res[i];
+            const double l = ri.length;
+            if (lt_len_idx(l, i, ml, mi)) { ml = l; mi = i; }
+            // deposit amount MAACO.py:307-308 (0.0 == "does not deposit"; x + 0.0 is exact anyway)
+            dep = (l != INF && ri.n_cells > 0 && l > 1e-6);
+            deposit[i] = dep ? Q / l : 0.0;
+        }
+        const uint32_t ok = __ballot_sync(0xffffffffu, dep);
+        if (lane == 0 && i < n) okbits[i >> 5] = ok;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -1119,47 +936,75 @@ mpp_maaco_best_kernel(const mpp_ant_result *__restrict__ res, const int32_t *__r
             st.iter_best_len = L; st.iter_best_turns = b_turns; st.iter_best_ant = b_ant;
             *state = st;
             b_copy = copy;
-            if (log) {
-                double *lg = log + 4 * (size_t)(iteration - 1);
+            if (log_all && iteration >= 1 && iteration <= log_rows) {
+                double *lg = log_all + ((size_t)map * log_rows + (size_t)(iteration - 1)) * 4;
                 lg[0] = L; lg[1] = (double)b_turns; lg[2] = st.best_len; lg[3] = (double)st.best_turns;
             }
         }
     }
     __syncthreads();
-    // the path is copied only by the rank that owns the ant (sharded colony: cells holds ants
-    // [cells_ant_offset, cells_ant_offset + cells_n_ants)); the owner broadcasts it after the solve
-    if (b_copy && b_ant >= cells_ant_offset && b_ant < cells_ant_offset + cells_n_ants) {
-        const int a = b_ant - cells_ant_offset;
-        int nc = res[b_ant].n_cells;
-        if (nc > max_cells) nc = max_cells;
-        const int32_t *src = cells + (size_t)a * max_cells;
-        for (int k = tid; k < nc; k += MPP_BEST_THREADS) best_cells[k] = src[k];
+    // the path is decoded only by the rank that owns the ant (sharded colony: moves holds ants
+    // [moves_ant_offset, moves_ant_offset + moves_n_ants)); the owner broadcasts it after the solve
+    if (b_copy && b_ant >= moves_ant_offset && b_ant < moves_ant_offset + moves_n_ants) {
+        const int a = b_ant - moves_ant_offset;
+        int nm = res[b_ant].n_cells - 1;                             // moves of the path
+        if (nm > max_cells) nm = max_cells;
+        const uint8_t *mv = moves_all + ((size_t)map * moves_n_ants + a) * max_cells;
+        int32_t *out = best_cells_all + (size_t)map * (max_cells + 1);
+        if (tid == 0) { out[0] = meta[map].start; s_base = meta[map].start; }
+        __syncthreads();
+        for (int k0 = 0; k0 < nm; k0 += MPP_BEST_THREADS) {          // block-wide inclusive scan of the cell deltas
+            const int k = k0 + tid;
+            int x = (k < nm) ? move_delta(mv[k], C) : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) s_idx[wid] = x;
+            __syncthreads();
+            if (wid == 0) {
+                int w = s_idx[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+                s_idx[lane] = w;
+            }
+            __syncthreads();
+            const int cell = s_base + (wid ? s_idx[wid - 1] : 0) + x;
+            if (k < nm) out[k + 1] = cell;
+            __syncthreads();
+            if (tid == MPP_BEST_THREADS - 1) s_base = cell;
+            __syncthreads();
+        }
     }
 }
 
-extern "C" int mpp_maaco_best(const mpp_ant_result *result_dev, const int32_t *cells_dev, int max_cells,
-                              int cells_ant_offset, int cells_n_ants, int n_ants, double Q, int iteration,
-                              mpp_maaco_state *state_dev, int32_t *best_cells_dev, double *deposit_dev,
-                              double *log_dev, void *stream) {
-    MPP_REQUIRE(result_dev && cells_dev && state_dev && best_cells_dev && deposit_dev, "mpp_maaco_best: null argument");
-    MPP_REQUIRE(n_ants > 0 && iteration >= 1, "mpp_maaco_best: n_ants=%d iteration=%d", n_ants, iteration);
-    mpp_maaco_best_kernel<<<1, MPP_BEST_THREADS, 0, (cudaStream_t)stream>>>(
-        result_dev, cells_dev, max_cells, cells_ant_offset, cells_n_ants, n_ants, Q, iteration, state_dev,
-        best_cells_dev, deposit_dev, log_dev);
+extern "C" int mpp_maaco_best(const mpp_map_batch *maps, const mpp_colony *c, int moves_ant_offset, int moves_n_ants,
+                              int n_ants_total, double Q, int iteration, void *stream) {
+    int rc = colony_check(maps, c, "mpp_maaco_best");
+    if (rc) return rc;
+    MPP_REQUIRE(n_ants_total > 0 && iteration >= 1, "mpp_maaco_best: n_ants=%d iteration=%d", n_ants_total, iteration);
+    MPP_CUDA(cudaSetDevice(maps->device));
+    mpp_maaco_best_kernel<<<maps->n_maps, MPP_BEST_THREADS, 0, (cudaStream_t)stream>>>(
+        c->result, c->moves, c->max_cells, moves_ant_offset, moves_n_ants, n_ants_total, Q, iteration, maps->cols,
+        maps->meta_dev, c->state, c->best_cells, c->deposit, c->okbits, c->log, c->log_rows, c->latch);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: pheromone evaporate + ordered deposit + MMAS clip (MAACO.py:304-332)
-// One warp owns 32 consecutive cells (one bitmap word); it streams that word of every ant
-// (word-major layout => 128-B coalesced loads of 32 ants) and adds deposits in ant order.
+// K3: pheromone evaporate + ordered deposit + MMAS clip (MAACO.py:304-332).
+// One CTA per (map, tile, group of 8 tile rows); warp = one row of 32 cells, lane = cell.  The deposit of a cell
+// is a sequential fp64 sum over the ants that visited it, in ant order (:306-311), so each warp walks the ants that
+// (a) have a slab for this tile (`touched`) and (b) deposit at all (`okbits`, from mpp_maaco_best) in index order:
+// 32 ants per round -- lane L loads the row word of ant L's slab -- the non-empty words are compacted with their
+// deposits into a per-warp shared-memory list, and the fold over that list is a bare DADD chain (the operand is
+// selected, t + 0.0 == t exactly).  Only slabs that exist are ever read: the traffic is 128 B per (ant, tile) pair
+// + tau, not a dense bitmap.
 // ---------------------------------------------------------------------------------------------
 #define MPP_PHER_THREADS 256
+#define MPP_PHER_CHUNK 2048                   // ants per list-building round (64 bitmap words)
 struct __align__(16) PherEntry { double d; uint32_t w; uint32_t pad; };
 
 // MMAS clip + obstacle reset (MAACO.py:312-332) for one cell
-__device__ __forceinline__ double pher_finalize(double t, int cell, const uint32_t *occ, int pitch, int R, int C,
+__device__ __forceinline__ double pher_finalize(double t, int r, int c, const uint32_t *occ, int pitch, int R, int C,
                                                 double rho, const mpp_maaco_state *state) {
     double b = state->best_len;                                               // :312-316
     if (b == __longlong_as_double(0x7ff0000000000000ll)) b = (double)(R + C);
@@ -1168,158 +1013,174 @@ __device__ __forceinline__ double pher_finalize(double t, int cell, const uint32
     int mx = C > R ? C : R;
     if (mx < 1) mx = 1;
     const double tmin = tmax / (2.0 * (double)mx);                            // :323
-    const int r = cell / C, c = cell % C, pb = c + 1;
+    const int pb = c + 1;
     const bool obst = (occ[(r + 1) * pitch + (pb >> 5)] >> (pb & 31)) & 1u;
     if (obst) return 1e-9;                                                    // :332
     t = t > tmin ? t : tmin;                                                  // :327-331 np.clip
     return t < tmax ? t : tmax;
 }
 
-// One CTA per bitmap word.  A block issues the loads of 4096 ants
-// (16 words per lane) at once, so a word costs ONE round trip.  The hits -- typically a few dozen per word -- are
-// compacted in ant order into a small list (warp-count prefix over shared memory) that warp 0 folds; words with more
-// hits than the list holds (around the start cell) fall back to one warp's 512 ants at a time.
-#define MPP_PHER_SR 4096
-#define MPP_PHER_SRU (MPP_PHER_SR / 8 / 32)   // loads per lane per super-round (8 warps)
-#define MPP_PHER_CAP 512                     // list entries per buffer (>= ants per warp per super-round)
+struct PherArgs {
+    const uint32_t *occ; int occ_words, pitch, R, C;
+    double *tau; size_t tau_stride;
+    uint32_t *slabs; size_t slab_stride;        // [n_maps][buf tiles][n_ants][32]
+    uint32_t *touched, *touched_next;           // this pass's bitmaps (read) / next pass's (cleared); [n_maps][buf tiles][NW]
+    size_t touched_stride;
+    const double *deposit; const uint32_t *okbits;
+    int n_ants;                                 // all ants of the colony, global order
+    int tile_row0;                              // first tile row of the buffers (a sharded colony updates a slice)
+    double rho;
+    const mpp_maaco_state *state;
+    int clear_slabs;                            // zero the slab words that were read (sharded colony: rebuilt by OR next pass)
+    const int32_t *latch;
+};
 
-__device__ __forceinline__ double pher_fold_list(const PherEntry *lst, int n, int lane, double t) {
-    int i = 0;
-    for (; i + 4 <= n; i += 4) {
-        // select the operand, not the sum: the loop-carried chain is a bare DADD (t + 0.0 == t exactly)
-        const PherEntry x0 = lst[i], x1 = lst[i + 1], x2 = lst[i + 2], x3 = lst[i + 3];
-        const double a0 = ((x0.w >> lane) & 1u) ? x0.d : 0.0, a1 = ((x1.w >> lane) & 1u) ? x1.d : 0.0;
-        const double a2 = ((x2.w >> lane) & 1u) ? x2.d : 0.0, a3 = ((x3.w >> lane) & 1u) ? x3.d : 0.0;
-        t += a0;                                                             // :311
-        t += a1;
-        t += a2;
-        t += a3;
-    }
-    for (; i < n; ++i) {
-        const PherEntry x = lst[i];
-        t += ((x.w >> lane) & 1u) ? x.d : 0.0;
-    }
-    return t;
-}
-
-__global__ void __launch_bounds__(MPP_PHER_THREADS, 3)
-mpp_maaco_pheromone_sr_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, double *__restrict__ tau,
-                              uint32_t *__restrict__ visitT, const double *__restrict__ deposit, int n_seg,
-                              int seg_ants, int word0, int n_words, double rho,
-                              const mpp_maaco_state *__restrict__ state, int clear_visit) {
-    __shared__ PherEntry s_list[2][MPP_PHER_CAP];
-    __shared__ int s_cnt[2][8];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int wl = blockIdx.x;                               // one bitmap word (32 cells) per block
-    const int cell = (word0 + wl) * 32 + lane;
-    const bool live = cell < R * C;
+__global__ void __launch_bounds__(MPP_PHER_THREADS) mpp_maaco_pheromone_kernel(const PherArgs A) {
+    __shared__ int s_list[MPP_PHER_CHUNK];
+    __shared__ PherEntry s_buf[MPP_PHER_THREADS / 32][32];
+    __shared__ int s_wcnt[2];
+    if (A.latch && *A.latch) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, map = blockIdx.y;
+    const int TC = (A.C + 31) >> 5;
+    const int tile_l = blockIdx.x >> 2, rg = blockIdx.x & 3;          // tile index inside the buffers, row group
+    const int trow = A.tile_row0 + tile_l / TC, tcx = tile_l % TC;
+    const int row_in_tile = rg * 8 + wid;
+    const int r = (trow << 5) + row_in_tile, c = (tcx << 5) + lane;
+    const bool live = r < A.R && c < A.C;
+    double *tau = A.tau + (size_t)map * A.tau_stride;
+    const int NW = (A.n_ants + 31) >> 5;
+    const uint32_t *tb = A.touched + (size_t)map * A.touched_stride + (size_t)tile_l * NW;
+    const uint32_t *ok = A.okbits + (size_t)map * NW;
+    uint32_t *slab_t = A.slabs + (size_t)map * A.slab_stride + (size_t)tile_l * A.n_ants * 32 + row_in_tile;
+    const double *dep = A.deposit + (size_t)map * A.n_ants;
     double t = 0.0;
-    if (wid == 0 && live) t = tau[cell] * (1.0 - rho);       // :305
-    const int sr_per_seg = (seg_ants + MPP_PHER_SR - 1) / MPP_PHER_SR;
-    const int n_sr = n_seg * sr_per_seg;
+    if (live) t = tau[(size_t)r * A.C + c] * (1.0 - A.rho);            // :305
+    PherEntry *sb = s_buf[wid];
     const uint32_t lt = (1u << lane) - 1u;
-    for (int sr = 0; sr < n_sr; ++sr) {
-        const int buf = sr & 1;
-        const int seg = sr / sr_per_seg, a_base = (sr % sr_per_seg) * MPP_PHER_SR + wid * (MPP_PHER_SR / 8);
-        uint32_t *const row = visitT + ((size_t)seg * n_words + wl) * seg_ants;
-        const double *const dep = deposit + (size_t)seg * seg_ants;
-        uint32_t wd[MPP_PHER_SRU];
-#pragma unroll
-        for (int u = 0; u < MPP_PHER_SRU; ++u) {
-            const int a = a_base + u * 32 + lane;
-            wd[u] = (a < seg_ants) ? row[a] : 0u;
-        }
+    for (int w0 = 0; w0 < NW; w0 += MPP_PHER_CHUNK / 32) {
+        // ---- the ants of this chunk that have a slab here and deposit, in index order ----
         int cnt = 0;
+        uint32_t bits = 0u;
+        if (wid < 2) {
+            const int w = w0 + wid * 32 + lane;
+            if (w < NW) bits = tb[w] & ok[w];
+            cnt = __popc(bits);
+            int x = cnt;
 #pragma unroll
-        for (int u = 0; u < MPP_PHER_SRU; ++u) cnt += __popc(__ballot_sync(0xffffffffu, wd[u] != 0u));
-        if (lane == 0) s_cnt[buf][wid] = cnt;
-        double dv[MPP_PHER_SRU];                             // deposits of the hits: all loads in flight before the barrier
-#pragma unroll
-        for (int u = 0; u < MPP_PHER_SRU; ++u) {
-            dv[u] = 0.0;
-            if (wd[u] != 0u) {
-                const int a = a_base + u * 32 + lane;
-                dv[u] = dep[a];
-                if (clear_visit) row[a] = 0u;
-            }
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) s_wcnt[wid] = x;
+            cnt = x - cnt;                                             // exclusive prefix inside the warp
         }
         __syncthreads();
-        int off = 0, total = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = s_cnt[buf][k];
-            if (k < wid) off += c;
-            total += c;
+        const int k = s_wcnt[0] + s_wcnt[1];
+        if (wid < 2) {
+            int o = cnt + (wid ? s_wcnt[0] : 0);
+            const int abase = (w0 + wid * 32 + lane) << 5;
+            while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; s_list[o++] = abase + b; }
         }
-        if (total <= MPP_PHER_CAP) {
-            int o = off;
-#pragma unroll
-            for (int u = 0; u < MPP_PHER_SRU; ++u) {
-                const uint32_t nz = __ballot_sync(0xffffffffu, wd[u] != 0u);
-                if (wd[u] != 0u) {
-                    PherEntry e; e.d = dv[u]; e.w = wd[u]; e.pad = 0u;
-                    s_list[buf][o + __popc(nz & lt)] = e;
-                }
-                o += __popc(nz);
+        __syncthreads();
+        // ---- this warp's row: words of those ants, 32 per round, the next round in flight during the fold ----
+        int a_n = (lane < k) ? s_list[lane] : 0;
+        uint32_t w_n = (lane < k) ? __ldcg(slab_t + (size_t)a_n * 32) : 0u;
+        double d_n = (lane < k) ? dep[a_n] : 0.0;
+        for (int base = 0; base < k; base += 32) {
+            const uint32_t word = w_n;
+            const double d = d_n;
+            const int a_c = a_n;
+            const int i = base + 32 + lane;
+            if (i < k) {
+                a_n = s_list[i];
+                w_n = __ldcg(slab_t + (size_t)a_n * 32);
+                d_n = dep[a_n];
+            } else {
+                w_n = 0u;
             }
-            __syncthreads();
-            if (wid == 0) t = pher_fold_list(s_list[buf], total, lane, t);   // ants in index order :306
-        } else {
-            // crowded word: one warp's ants (<= 512 hits) at a time through the same list
-            for (int c = 0; c < 8; ++c) {
-                if (wid == c) {
-                    int o = 0;
-#pragma unroll
-                    for (int u = 0; u < MPP_PHER_SRU; ++u) {
-                        const uint32_t nz = __ballot_sync(0xffffffffu, wd[u] != 0u);
-                        if (wd[u] != 0u) {
-                            PherEntry e; e.d = dv[u]; e.w = wd[u]; e.pad = 0u;
-                            s_list[buf][o + __popc(nz & lt)] = e;
-                        }
-                        o += __popc(nz);
-                    }
-                }
-                __syncthreads();
-                if (wid == 0) t = pher_fold_list(s_list[buf], s_cnt[buf][c], lane, t);
-                __syncthreads();
+            const uint32_t nz = __ballot_sync(0xffffffffu, word != 0u);
+            if (!nz) continue;
+            if (word != 0u) {
+                PherEntry e; e.d = d; e.w = word; e.pad = 0u;
+                sb[__popc(nz & lt)] = e;
+                if (A.clear_slabs) slab_t[(size_t)a_c * 32] = 0u;
             }
+            __syncwarp();
+            const int n = __popc(nz);
+            int q = 0;
+            for (; q + 4 <= n; q += 4) {
+                // select the operand, not the sum: the loop-carried chain is a bare DADD (t + 0.0 == t exactly)
+                const PherEntry x0 = sb[q], x1 = sb[q + 1], x2 = sb[q + 2], x3 = sb[q + 3];
+                const double a0 = ((x0.w >> lane) & 1u) ? x0.d : 0.0, a1 = ((x1.w >> lane) & 1u) ? x1.d : 0.0;
+                const double a2 = ((x2.w >> lane) & 1u) ? x2.d : 0.0, a3 = ((x3.w >> lane) & 1u) ? x3.d : 0.0;
+                t += a0;                                                     // :311, ants in index order :306
+                t += a1;
+                t += a2;
+                t += a3;
+            }
+            for (; q < n; ++q) {
+                const PherEntry x = sb[q];
+                t += ((x.w >> lane) & 1u) ? x.d : 0.0;
+            }
+            __syncwarp();
         }
+        __syncthreads();                                               // s_list is rebuilt by the next chunk
     }
-    if (wid == 0 && live) tau[cell] = pher_finalize(t, cell, occ, pitch, R, C, rho, state);
+    if (live) tau[(size_t)r * A.C + c] = pher_finalize(t, r, c, A.occ + (size_t)map * A.occ_words, A.pitch, A.R, A.C, A.rho,
+                                                      A.state + map);
+    // the bitmaps the NEXT pass will fill are the ones the previous pass consumed: clear this tile's share
+    {
+        uint32_t *tn = A.touched_next + (size_t)map * A.touched_stride + (size_t)tile_l * NW;
+        for (int w = rg * MPP_PHER_THREADS + threadIdx.x; w < NW; w += 4 * MPP_PHER_THREADS) tn[w] = 0u;
+    }
 }
 
-extern "C" int mpp_maaco_pheromone(const mpp_map *map, double *tau_dev, uint32_t *visitT_dev,
-                                   const double *deposit_dev, int n_seg, int seg_ants, int word0, int n_words,
-                                   double rho, const mpp_maaco_state *state_dev, int clear_visit, void *stream) {
-    MPP_REQUIRE(map && tau_dev && visitT_dev && deposit_dev && state_dev, "mpp_maaco_pheromone: null argument");
-    MPP_REQUIRE(n_seg > 0 && seg_ants > 0 && word0 >= 0 && n_words > 0, "mpp_maaco_pheromone: bad shape");
-    MPP_CUDA(cudaSetDevice(map->device));
-    mpp_maaco_pheromone_sr_kernel<<<n_words, MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(
-        map->occ_dev, map->pitch_words, map->rows, map->cols, tau_dev, visitT_dev, deposit_dev, n_seg, seg_ants,
-        word0, n_words, rho, state_dev, clear_visit);
+extern "C" int mpp_maaco_pheromone(const mpp_map_batch *maps, const mpp_colony *c, uint32_t *slabs_dev, uint32_t *touched_dev,
+                                   int n_ants_total, int tile_row0, int buf_tile_rows, double rho, int iteration,
+                                   int clear_slabs, void *stream) {
+    int rc = colony_check(maps, c, "mpp_maaco_pheromone");
+    if (rc) return rc;
+    const int TR = tiles_r(maps->rows), TC = tiles_c(maps->cols);
+    MPP_REQUIRE(slabs_dev && touched_dev && n_ants_total > 0, "mpp_maaco_pheromone: null argument");
+    MPP_REQUIRE(tile_row0 >= 0 && buf_tile_rows > 0, "mpp_maaco_pheromone: bad tile-row range");
+    MPP_CUDA(cudaSetDevice(maps->device));
+    int n_tile_rows = buf_tile_rows;                                  // rows of the buffers that lie inside the map
+    if (tile_row0 + n_tile_rows > TR) n_tile_rows = TR - tile_row0;
+    if (n_tile_rows <= 0) return MPP_OK;                              // a padded slice beyond the map
+    const int NW = (n_ants_total + 31) / 32;
+    PherArgs A;
+    A.occ = maps->occ_dev; A.occ_words = maps->occ_words; A.pitch = maps->pitch_words; A.R = maps->rows; A.C = maps->cols;
+    A.tau = c->tau; A.tau_stride = (size_t)c->tau_stride;
+    A.slabs = slabs_dev;
+    A.slab_stride = (size_t)buf_tile_rows * TC * (size_t)n_ants_total * 32;
+    A.touched_stride = (size_t)buf_tile_rows * TC * (size_t)NW;
+    const size_t par = A.touched_stride * maps->n_maps;
+    A.touched = touched_dev + (size_t)(iteration & 1) * par;
+    A.touched_next = touched_dev + (size_t)((iteration + 1) & 1) * par;
+    A.deposit = c->deposit; A.okbits = c->okbits; A.n_ants = n_ants_total;
+    A.tile_row0 = tile_row0; A.rho = rho; A.state = c->state; A.clear_slabs = clear_slabs;
+    A.latch = c->latch;
+    mpp_maaco_pheromone_kernel<<<dim3(n_tile_rows * TC * 4, maps->n_maps), MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(A);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sharded-colony exchange: tours travel between GPUs as 1-byte move codes (MAACO move order), ~10x
-// smaller than dense visited bitmaps and 4x smaller than int32 cell lists; every rank replays the codes of
-// all ants into the visited words of ITS slice of the map.
+// Sharded-colony exchange.  Rank g constructs its ants and ships (a) their 16-byte results and (b) their tours as
+// 1-byte move codes in ONE buffer per pass (one all-gather); every rank then replays the codes of all ants into
+// slabs of ITS slice of tile rows and updates the pheromone of that slice with all ants in global order.
+//   exchange buffer of one rank: [n_local x mpp_ant_result][int32 total code bytes, 3 x int32 pad][codes ...]
 // ---------------------------------------------------------------------------------------------
-// offsets[i] = byte offset of ant i's codes inside its segment's packed buffer; totals[seg] = bytes of
-// segment seg.  One block per segment (exclusive scan over the segment's ants of n_cells-1, 0 for failed ants).
-__global__ void __launch_bounds__(1024) mpp_maaco_move_offsets_kernel(const mpp_ant_result *__restrict__ res,
-                                                                      int seg_ants, int32_t *__restrict__ offsets,
-                                                                      int32_t *__restrict__ totals) {
-    __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_carry = 0;
+#define MPP_XHDR(n_local) ((size_t)16 * (size_t)(n_local) + 16)
+
+// exclusive scan of (n_cells - 1, 0 for failed ants) over one segment's results; one block of 1024 threads.
+// offsets[a] = byte offset of ant a's codes; returns the total through *total_out.
+__device__ __forceinline__ void xscan_segment(const mpp_ant_result *__restrict__ res, int seg_ants, int32_t *__restrict__ offsets,
+                                              int *s_warp, int *s_carry, int *total_out) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) *s_carry = 0;
     __syncthreads();
     for (int base = 0; base < seg_ants; base += 1024) {
         const int a = base + tid;
         int len = 0;
-        if (a < seg_ants) { const int n = res[(size_t)seg * seg_ants + a].n_cells; len = n > 0 ? n - 1 : 0; }
+        if (a < seg_ants) { const int n = res[a].n_cells; len = n > 0 ? n - 1 : 0; }
         int x = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -1332,105 +1193,211 @@ __global__ void __launch_bounds__(1024) mpp_maaco_move_offsets_kernel(const mpp_
             s_warp[lane] = w;
         }
         __syncthreads();
-        const int excl = s_carry + (wid ? s_warp[wid - 1] : 0) + x - len;
-        if (a < seg_ants) offsets[(size_t)seg * seg_ants + a] = excl;
+        const int excl = *s_carry + (wid ? s_warp[wid - 1] : 0) + x - len;
+        if (a < seg_ants) offsets[a] = excl;
         __syncthreads();
-        if (tid == 1023) s_carry += s_warp[31];
+        if (tid == 1023) *s_carry += s_warp[31];
         __syncthreads();
     }
-    if (tid == 0) totals[seg] = s_carry;
+    *total_out = *s_carry;
 }
 
-// one warp per local ant: cells -> move codes at packed[offsets[a] ...]
-__global__ void __launch_bounds__(256) mpp_maaco_pack_moves_kernel(const int32_t *__restrict__ cells, int max_cells,
+// step 1 on the sending rank: header (results + total) and the offsets of the local ants
+__global__ void __launch_bounds__(1024) mpp_maaco_xpack_scan_kernel(const mpp_ant_result *__restrict__ res_local, int n_local,
+                                                                    int32_t *__restrict__ offsets_local, uint8_t *__restrict__ xbuf,
+                                                                    const int32_t *__restrict__ latch) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (latch && *latch) return;
+    int total;
+    xscan_segment(res_local, n_local, offsets_local, s_warp, &s_carry, &total);
+    mpp_ant_result *hdr = (mpp_ant_result *)xbuf;
+    for (int a = threadIdx.x; a < n_local; a += 1024) hdr[a] = res_local[a];
+    if (threadIdx.x == 0) {
+        int32_t *tail = (int32_t *)(xbuf + (size_t)16 * n_local);
+        tail[0] = total; tail[1] = 0; tail[2] = 0; tail[3] = 0;
+    }
+}
+
+// step 2: one warp per local ant copies its move codes behind the header (nothing is written past `cap`; the
+// receivers see total > cap in the header and raise the latch)
+__global__ void __launch_bounds__(256) mpp_maaco_xpack_copy_kernel(const uint8_t *__restrict__ moves, int max_cells,
                                                                    const mpp_ant_result *__restrict__ res_local,
                                                                    const int32_t *__restrict__ offsets_local, int n_local,
-                                                                   int C, uint8_t *__restrict__ packed, int cap,
-                                                                   int32_t *__restrict__ status) {
+                                                                   uint8_t *__restrict__ xbuf, long long cap,
+                                                                   const int32_t *__restrict__ latch) {
+    if (latch && *latch) return;
     const int a = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (a >= n_local) return;
     const int n = res_local[a].n_cells;
     if (n <= 1) return;
-    if (n > max_cells || offsets_local[a] + (n - 1) > cap) { if (lane == 0) atomicMax(status, 2); return; }
-    const int32_t *p = cells + (size_t)a * max_cells;
-    uint8_t *out = packed + offsets_local[a];
-    for (int i = lane; i + 1 < n; i += 32) {
-        const int d = p[i + 1] - p[i];                     // -C-1,-C,-C+1,-1,+1,C-1,C,C+1 -> move 0..7
-        const int dr = (d + C + 1) / C - 1 + ((d + C + 1) < 0 ? -1 : 0);  // rows: d in [-C-1,-C+1] -> -1, [-1,1] -> 0, [C-1,C+1] -> 1
-        const int dc = d - dr * C;
-        const int i9 = (dr + 1) * 3 + (dc + 1);
-        out[i] = (uint8_t)(i9 - (i9 > 4));
-    }
+    const long long off = offsets_local[a];
+    if (n - 1 > max_cells || off + (n - 1) > cap) return;
+    const uint8_t *src = moves + (size_t)a * max_cells;
+    uint8_t *dst = xbuf + MPP_XHDR(n_local) + off;
+    for (int i = lane; i < n - 1; i += 32) dst[i] = src[i];
 }
 
-// one warp per global ant: replay its moves 32 at a time (warp prefix sum of the cell deltas) and set the
-// visited bits that fall into words [word0, word0 + n_words); visit_seg is [n_seg][n_words][seg_ants] and
-// must be zero on entry.  Bits are set with fire-and-forget RED.OR (a column belongs to one ant).
-__global__ void __launch_bounds__(256) mpp_maaco_rebuild_visits_kernel(const uint8_t *__restrict__ packed_all, int cap,
-                                                                       const int32_t *__restrict__ offsets,
-                                                                       const mpp_ant_result *__restrict__ res, int n_seg,
-                                                                       int seg_ants, int start, int C, int word0,
-                                                                       int n_words, uint32_t *__restrict__ visit_seg) {
+// step 3 on every rank after the all-gather: results of all segments into the contiguous table, per-ant code offsets,
+// overflow check (a tour longer than max_cells or a segment larger than `cap` raises the latch = this iteration),
+// and the clearing of the local `touched` bitmaps of the NEXT pass (nobody consumes a sharded rank's own slabs)
+__global__ void __launch_bounds__(1024) mpp_maaco_xunpack_kernel(const uint8_t *__restrict__ xbuf_all, size_t seg_stride,
+                                                                 int seg_ants, long long cap, int max_cells,
+                                                                 mpp_ant_result *__restrict__ result,
+                                                                 int32_t *__restrict__ offsets, int32_t *latch, int iteration,
+                                                                 uint32_t *__restrict__ clear_ptr, size_t clear_words) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    __shared__ int s_long;
+    if (*latch) return;
+    const int seg = blockIdx.x;
+    const uint8_t *xb = xbuf_all + (size_t)seg * seg_stride;
+    const mpp_ant_result *hdr = (const mpp_ant_result *)xb;
+    if (threadIdx.x == 0) s_long = 0;
+    int total;
+    xscan_segment(hdr, seg_ants, offsets + (size_t)seg * seg_ants, s_warp, &s_carry, &total);
+    for (int a = threadIdx.x; a < seg_ants; a += 1024) {
+        const mpp_ant_result r = hdr[a];
+        result[(size_t)seg * seg_ants + a] = r;
+        if (r.n_cells - 1 > max_cells) s_long = 1;
+    }
+    for (size_t w = (size_t)seg * 1024 + threadIdx.x; w < clear_words; w += (size_t)gridDim.x * 1024) clear_ptr[w] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0 && (total > cap || s_long)) atomicMax(latch, iteration);
+}
+
+// step 4: one warp per global ant replays its moves 32 at a time (warp prefix sum of the cell deltas) and sets the
+// visited bits that fall into tile rows [tile_row0, tile_row0 + buf_tile_rows) of the receive slabs
+// ([tile][all ants][32], zero on entry: the update clears what it reads) and the (tile, ant) bits of `touched`.
+__global__ void __launch_bounds__(256) mpp_maaco_rebuild_kernel(const uint8_t *__restrict__ xbuf_all, size_t seg_stride,
+                                                                const int32_t *__restrict__ offsets,
+                                                                const mpp_ant_result *__restrict__ res, int n_seg,
+                                                                int seg_ants, int start, int C, int TC, int tile_row0,
+                                                                int buf_tile_rows, uint32_t *__restrict__ slabs,
+                                                                uint32_t *__restrict__ touched,
+                                                                const int32_t *__restrict__ latch) {
+    if (*latch) return;
     const int g = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (g >= n_seg * seg_ants) return;
+    const int n_total = n_seg * seg_ants;
+    if (g >= n_total) return;
     const int n = res[g].n_cells;
     if (n <= 0) return;                                      // failed ants deposit nothing (MAACO.py:307)
-    const int seg = g / seg_ants, a = g - seg * seg_ants;
-    const uint8_t *codes = packed_all + (size_t)seg * cap + offsets[g];
-    uint32_t *col = visit_seg + (size_t)seg * n_words * seg_ants + a;     // word w of this ant at col[w * seg_ants]
+    const int seg = g / seg_ants;
+    const uint8_t *codes = xbuf_all + (size_t)seg * seg_stride + MPP_XHDR(seg_ants) + offsets[g];
+    const int NW = (n_total + 31) >> 5;
+    auto mark = [&](int cell, bool first_of_tile) {
+        const int r = cell / C, c = cell - r * C;
+        const int trl = (r >> 5) - tile_row0;
+        if (trl < 0 || trl >= buf_tile_rows) return;
+        const int tile_l = trl * TC + (c >> 5);
+        atomicOr(slabs + ((size_t)tile_l * n_total + g) * 32 + (r & 31), 1u << (c & 31));
+        if (first_of_tile) atomicOr(touched + (size_t)tile_l * NW + (g >> 5), 1u << (g & 31));
+    };
     int base_cell = start;                                   // cell before the first move of the current chunk
-    if (lane == 0) {
-        const int w = (start >> 5) - word0;
-        if (w >= 0 && w < n_words) atomicOr(&col[(size_t)w * seg_ants], 1u << (start & 31));
-    }
+    if (lane == 0) mark(start, true);
     for (int i0 = 0; i0 < n - 1; i0 += 32) {
         const int i = i0 + lane;
         int d = 0;
-        if (i < n - 1) {
-            const int m = codes[i];
-            d = ((int)((0xA940u >> (2 * m)) & 3u) - 1) * C + ((int)((0x9224u >> (2 * m)) & 3u) - 1);
-        }
+        if (i < n - 1) d = move_delta(codes[i], C);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, d, o); if (lane >= o) d += y; }
         const int cell = base_cell + d;                      // cell reached after move i
-        if (i < n - 1) {
-            const int w = (cell >> 5) - word0;
-            if (w >= 0 && w < n_words) atomicOr(&col[(size_t)w * seg_ants], 1u << (cell & 31));
-        }
+        // (tile, ant) bit: once per run of cells inside one tile (the lane before is in another tile, or lane 0)
+        const int tkey = ((cell / C) >> 5) * TC + ((cell % C) >> 5);
+        const int tprev = __shfl_up_sync(0xffffffffu, tkey, 1);
+        if (i < n - 1) mark(cell, lane == 0 || tprev != tkey);
         base_cell = __shfl_sync(0xffffffffu, cell, 31);
     }
 }
 
-extern "C" int mpp_maaco_move_offsets(const mpp_ant_result *result_dev, int n_seg, int seg_ants, int32_t *offsets_dev,
-                                      int32_t *totals_dev, void *stream) {
-    MPP_REQUIRE(result_dev && offsets_dev && totals_dev && n_seg > 0 && seg_ants > 0, "mpp_maaco_move_offsets: bad argument");
-    mpp_maaco_move_offsets_kernel<<<n_seg, 1024, 0, (cudaStream_t)stream>>>(result_dev, seg_ants, offsets_dev, totals_dev);
+extern "C" long long mpp_maaco_xhdr_bytes(int n_local) { return (long long)MPP_XHDR(n_local); }
+
+extern "C" int mpp_maaco_xpack(const mpp_map_batch *maps, const mpp_colony *c, int ant_offset, int n_local, int n_ants_total,
+                               int32_t *offsets_local_dev, uint8_t *xbuf_local_dev, long long capacity, void *stream) {
+    int rc = colony_check(maps, c, "mpp_maaco_xpack");
+    if (rc) return rc;
+    MPP_REQUIRE(maps->n_maps == 1, "mpp_maaco_xpack: a sharded colony is one map");
+    MPP_REQUIRE(offsets_local_dev && xbuf_local_dev && n_local > 0 && capacity >= 0 && ant_offset + n_local <= n_ants_total,
+                "mpp_maaco_xpack: bad argument");
+    MPP_CUDA(cudaSetDevice(maps->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    mpp_maaco_xpack_scan_kernel<<<1, 1024, 0, s>>>(c->result + ant_offset, n_local, offsets_local_dev, xbuf_local_dev, c->latch);
+    mpp_maaco_xpack_copy_kernel<<<(n_local + 7) / 8, 256, 0, s>>>(c->moves, c->max_cells, c->result + ant_offset,
+                                                                  offsets_local_dev, n_local, xbuf_local_dev, capacity, c->latch);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
 
-extern "C" int mpp_maaco_pack_moves(const mpp_map *map, const int32_t *cells_dev, int max_cells,
-                                    const mpp_ant_result *result_local_dev, const int32_t *offsets_local_dev, int n_local,
-                                    uint8_t *packed_dev, int capacity, int32_t *status_dev, void *stream) {
-    MPP_REQUIRE(map && cells_dev && result_local_dev && offsets_local_dev && packed_dev && status_dev && n_local > 0,
-                "mpp_maaco_pack_moves: bad argument");
-    MPP_CUDA(cudaSetDevice(map->device));
-    mpp_maaco_pack_moves_kernel<<<(n_local + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        cells_dev, max_cells, result_local_dev, offsets_local_dev, n_local, map->cols, packed_dev, capacity, status_dev);
+extern "C" int mpp_maaco_xunpack(const mpp_map_batch *maps, const mpp_colony *c, const uint8_t *xbuf_all_dev, long long capacity,
+                                 int n_seg, int seg_ants, int iteration, int32_t *offsets_dev, int tile_row0, int buf_tile_rows,
+                                 uint32_t *slabs_recv_dev, uint32_t *touched_recv_dev, uint32_t *touched_local_dev,
+                                 void *stream) {
+    int rc = colony_check(maps, c, "mpp_maaco_xunpack");
+    if (rc) return rc;
+    MPP_REQUIRE(maps->n_maps == 1, "mpp_maaco_xunpack: a sharded colony is one map");
+    MPP_REQUIRE(xbuf_all_dev && offsets_dev && slabs_recv_dev && touched_recv_dev && touched_local_dev && c->latch &&
+                    n_seg > 0 && seg_ants > 0 && capacity >= 0, "mpp_maaco_xunpack: bad argument");
+    MPP_CUDA(cudaSetDevice(maps->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int TR = tiles_r(maps->rows), TC = tiles_c(maps->cols);
+    const size_t seg_stride = MPP_XHDR(seg_ants) + (size_t)capacity;
+    const int n_total = n_seg * seg_ants;
+    // the local tour buffers of the next pass: parity (iteration + 1)
+    const size_t tw_local = (size_t)mpp_maaco_touched_words(TR, maps->cols, seg_ants) / 2;
+    uint32_t *clear_ptr = touched_local_dev + (size_t)((iteration + 1) & 1) * tw_local;
+    mpp_maaco_xunpack_kernel<<<n_seg, 1024, 0, s>>>(xbuf_all_dev, seg_stride, seg_ants, capacity, c->max_cells, c->result,
+                                                    offsets_dev, (int32_t *)c->latch, iteration, clear_ptr, tw_local);
+    const size_t tw_recv = (size_t)mpp_maaco_touched_words(buf_tile_rows, maps->cols, n_total) / 2;
+    mpp_maaco_rebuild_kernel<<<(n_total + 7) / 8, 256, 0, s>>>(
+        xbuf_all_dev, seg_stride, offsets_dev, c->result, n_seg, seg_ants, maps->meta_host[0].start, maps->cols, TC,
+        tile_row0, buf_tile_rows, slabs_recv_dev, touched_recv_dev + (size_t)(iteration & 1) * tw_recv, c->latch);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
 
-extern "C" int mpp_maaco_rebuild_visits(const mpp_map *map, const uint8_t *packed_all_dev, int capacity,
-                                        const int32_t *offsets_dev, const mpp_ant_result *result_dev, int n_seg,
-                                        int seg_ants, int word0, int n_words, uint32_t *visit_seg_dev, void *stream) {
-    MPP_REQUIRE(map && packed_all_dev && offsets_dev && result_dev && visit_seg_dev && n_seg > 0 && seg_ants > 0,
-                "mpp_maaco_rebuild_visits: bad argument");
-    MPP_CUDA(cudaSetDevice(map->device));
-    const int total = n_seg * seg_ants;
-    mpp_maaco_rebuild_visits_kernel<<<(total + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        packed_all_dev, capacity, offsets_dev, result_dev, n_seg, seg_ants, map->start, map->cols, word0, n_words,
-        visit_seg_dev);
-    MPP_CUDA(cudaGetLastError());
+// ---------------------------------------------------------------------------------------------
+// One whole colony pass of a non-sharded colony (ranking, tours, best tracking, pheromone update), and the same
+// pass driven with HOST buffers: the pheromone field goes in, the per-ant results, the colony state, the best path
+// and the updated field come out, all inside the call (the reference-facing, synchronous form of the hot path).
+// ---------------------------------------------------------------------------------------------
+extern "C" int mpp_maaco_pass(const mpp_map_batch *maps, const mpp_colony *c, const mpp_maaco_params *p, int iteration,
+                              int n_ants, int ants_per_warp, void *stream) {
+    MPP_REQUIRE(p, "mpp_maaco_pass: null params");
+    int rc = mpp_maaco_rank(maps, c, p->alpha, stream);
+    if (rc) return rc;
+    rc = mpp_maaco_tours(maps, c, iteration, mpp_maaco_q0(p->num_iterations, iteration, p->q0_initial), p->alpha, n_ants, 0,
+                         n_ants, ants_per_warp, stream);
+    if (rc) return rc;
+    rc = mpp_maaco_best(maps, c, 0, n_ants, n_ants, p->Q, iteration, stream);
+    if (rc) return rc;
+    return mpp_maaco_pheromone(maps, c, c->slabs, c->touched, n_ants, 0, tiles_r(maps->rows), p->rho, iteration, 0, stream);
+}
+
+extern "C" int mpp_maaco_pass_host(const mpp_map_batch *maps, const mpp_colony *c, const mpp_maaco_params *p, int iteration,
+                                   int n_ants, int ants_per_warp, const double *tau_in_host, double *tau_out_host,
+                                   mpp_ant_result *result_out_host, mpp_maaco_state *state_out_host,
+                                   int32_t *best_cells_out_host, int best_cells_capacity, void *stream) {
+    int rc = colony_check(maps, c, "mpp_maaco_pass_host");
+    if (rc) return rc;
+    MPP_CUDA(cudaSetDevice(maps->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)maps->rows * maps->cols;
+    const int M = maps->n_maps;
+    if (tau_in_host)
+        MPP_CUDA(cudaMemcpy2DAsync(c->tau, (size_t)c->tau_stride * 8, tau_in_host, n * 8, n * 8, M, cudaMemcpyHostToDevice, s));
+    rc = mpp_maaco_pass(maps, c, p, iteration, n_ants, ants_per_warp, stream);
+    if (rc) return rc;
+    if (tau_out_host)
+        MPP_CUDA(cudaMemcpy2DAsync(tau_out_host, n * 8, c->tau, (size_t)c->tau_stride * 8, n * 8, M, cudaMemcpyDeviceToHost, s));
+    if (result_out_host)
+        MPP_CUDA(cudaMemcpyAsync(result_out_host, c->result, sizeof(mpp_ant_result) * (size_t)n_ants * M, cudaMemcpyDeviceToHost, s));
+    if (state_out_host)
+        MPP_CUDA(cudaMemcpyAsync(state_out_host, c->state, sizeof(mpp_maaco_state) * M, cudaMemcpyDeviceToHost, s));
+    if (best_cells_out_host) {
+        int cap = best_cells_capacity < c->max_cells + 1 ? best_cells_capacity : c->max_cells + 1;
+        MPP_CUDA(cudaMemcpy2DAsync(best_cells_out_host, (size_t)best_cells_capacity * 4, c->best_cells, (size_t)(c->max_cells + 1) * 4,
+                                   (size_t)cap * 4, M, cudaMemcpyDeviceToHost, s));
+    }
+    MPP_CUDA(cudaStreamSynchronize(s));
     return MPP_OK;
 }

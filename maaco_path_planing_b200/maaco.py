@@ -6,13 +6,10 @@ arguments select the RNG stream seed, the device and the (optional) ``torch.dist
 over which the colony is sharded.  No CPU fallback: without libmpp_b200.so or a B200 this raises.
 
 Keyword-only additions (none changes a result; every combination is bit-identical, see tests/test_maaco_gpu.py):
-  rng_seed        seed of the Philox streams; None = from os.urandom
+  rng_seed        seed of the Philox streams; None = from os.urandom (or $MPP_RNG_SEED)
   device, group   CUDA device index; torch.distributed group to shard the colony over
-  exchange        "moves" (default) or "dense": how a sharded colony ships its tours between ranks
-  use_rank        per-pass move-ranking tables (mpp_maaco_rank); False = literal selection rules at every step
-  lanes_per_ant   tour kernel form: 0 = library default (one thread per ant), 8 / 16 / 32 = cooperative lanes
-  ants_per_warp   packing hint for the thread-per-ant kernel when several colonies share the GPU (batch.py)
-  max_cells       capacity of the per-ant path buffers (default 8*(rows+cols); the solve repeats itself with rows*cols
+  ants_per_warp   form of the tour kernel (one thread per ant): 0 = chosen from the colony size, or 1, 2, 4, ..., 32
+  max_cells       capacity of the per-ant tour buffers (default 8*(rows+cols); the solve repeats itself with rows*cols
                   if the best path did not fit)
 """
 from __future__ import annotations
@@ -25,10 +22,18 @@ import numpy as np
 
 from . import _lib
 from . import dist as dist_mod
-from .dist import padded_words
+from .dist import padded_tile_rows
 from .gridmap import GridMap, START_NODE_VAL, TARGET_NODE_VAL
 
 INF = float("inf")
+
+
+class _PathOverflow(Exception):
+    """a tour did not fit max_cells (internal: solve_path_planning repeats the solve with full capacity)"""
+
+
+def _round64k(x):
+    return ((int(x) + 65535) // 65536) * 65536
 
 
 def _fresh_seed():
@@ -45,15 +50,12 @@ class MAACO:
                  alpha, beta, rho, Q,
                  a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
                  C0_initial_pheromone=0.1, *,
-                 rng_seed=None, device=None, max_cells=None, lanes_per_ant=0, ants_per_warp=0, group=None,
-                 exchange="moves",
-                 use_rank=True, verbose=True):
+                 rng_seed=None, device=None, max_cells=None, ants_per_warp=0, group=None, verbose=True):
         import torch
         self._ctor = dict(grid=grid, num_ants=num_ants, num_iterations=num_iterations, alpha=alpha, beta=beta, rho=rho,
                           Q=Q, a_turn_coef=a_turn_coef, wh_max=wh_max, wh_min=wh_min, k_h_adaptive=k_h_adaptive,
                           q0_initial=q0_initial, C0_initial_pheromone=C0_initial_pheromone, rng_seed=rng_seed,
-                          device=device, lanes_per_ant=lanes_per_ant, ants_per_warp=ants_per_warp, group=group,
-                          exchange=exchange, use_rank=use_rank, verbose=verbose)
+                          device=device, ants_per_warp=ants_per_warp, group=group, verbose=verbose)
         self.grid = np.array(grid, dtype=int)                       # MAACO.py:15
         self.rows, self.cols = self.grid.shape
         self.num_ants = num_ants
@@ -76,11 +78,9 @@ class MAACO:
         self.rng_seed = _fresh_seed() if rng_seed is None else int(rng_seed)
         self._ctor["rng_seed"] = self.rng_seed
         self.verbose = verbose
-        # ants_per_warp: hint for the thread-per-ant kernel when several colonies share the GPU (batch.py)
-        self.lanes_per_ant = -int(ants_per_warp) if ants_per_warp and lanes_per_ant in (0, 1) else lanes_per_ant
-        if exchange not in ("moves", "dense"):
-            raise ValueError("exchange must be 'moves' or 'dense'")
-        self.exchange = exchange
+        if ants_per_warp not in (0, 1, 2, 4, 8, 16, 32):
+            raise ValueError("ants_per_warp must be 0 (automatic) or a power of two <= 32")
+        self._apw = int(ants_per_warp)
 
         # ---- sharding of the colony over the process group (ants are independent given tau) ----
         self.group = group
@@ -96,54 +96,72 @@ class MAACO:
 
         L = _lib.lib()
         self.map = GridMap(self.grid, device=device)
+        self._maps = C.c_void_p(L.mpp_map_as_batch(self.map.handle))
         self.device = torch.device("cuda", self.map.device)
         n = self.rows * self.cols
-        self.n_words = padded_words(n, self.world)                  # bitmap words per ant (padded to split evenly)
-        self.words_per_rank = self.n_words // self.world
+        R, Cc = self.rows, self.cols
+        self.tile_rows, self.tile_cols = (R + 31) // 32, (Cc + 31) // 32
+        # a sharded colony updates tau by slices of whole tile rows (32 cell rows), padded to split evenly
+        self.tile_rows_per_rank = padded_tile_rows(self.tile_rows, self.world) // self.world
+        npad = self.tile_rows_per_rank * self.world * 32 * Cc
         # per-ant path capacity: tours are a few (R+C) cells long (no backtracking, MAACO.py:278-302); a tour that
-        # outgrows the buffer is still constructed and counted exactly -- only its cell list is truncated -- and
+        # outgrows the buffer is still constructed and counted exactly -- only its move list is truncated -- and
         # solve_path_planning() re-runs the (deterministic) solve with full capacity if the best path was cut
         self._auto_cells = max_cells is None
         if max_cells is None:
-            max_cells = min(n, max(1024, 8 * (self.rows + self.cols)))
+            max_cells = min(n, max(1024, 8 * (R + Cc)))
         self.max_cells = int(max_cells)
         dev = self.device
-        f64, i32, i64 = torch.float64, torch.int32, torch.int64
-        npad = self.n_words * 32
+        f64, i32, i64, u8 = torch.float64, torch.int32, torch.int64, torch.uint8
+        nl = self.n_local
         self._tau = torch.zeros(npad, dtype=f64, device=dev)        # padded so tau slices all-gather evenly
         self._E01 = torch.empty(2 * n, dtype=f64, device=dev)       # eta'**beta, interleaved by turn flag
         self._dist_t = torch.empty(n, dtype=f64, device=dev)
-        self.use_rank = use_rank
-        self._rank = (torch.empty(_lib.lib().mpp_maaco_rank_words(self.map.handle), dtype=i32, device=dev)
-                      if use_rank else None)
+        self._rank = torch.empty(L.mpp_maaco_rank_words(R, Cc), dtype=i32, device=dev)
         self._params = _lib.MaacoParams(alpha, beta, rho, Q, a_turn_coef, wh_max, wh_min, k_h_adaptive, q0_initial,
                                         C0_initial_pheromone, num_iterations)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(L.mpp_maaco_tables(self.map.handle, C.byref(self._params), _lib.ptr(self._tau), _lib.ptr(self._E01),
-                                      _lib.ptr(self._dist_t), C.c_void_p(stream)),
-                   "mpp_maaco_tables")
-        # word-major visited bitmaps of the local ants: [n_words][n_local]
-        self._visit_local = torch.zeros(self.n_words * self.n_local, dtype=i32, device=dev)
-        if self.world > 1:
-            self._visit_recv = torch.empty(self.n_words * self.n_local, dtype=i32, device=dev)  # [G][Wn][n_local]
-            self._side = torch.cuda.Stream(device=dev)
-            if self.exchange == "moves":
-                if self.cols < 3:
-                    raise ValueError("the move-code exchange needs at least 3 columns")
-                self._visit_recv.zero_()                              # rebuilt per pass, cleared by the update
-                self._offsets = torch.zeros(num_ants, dtype=i32, device=dev)
-                self._totals = torch.zeros(self.world, dtype=i32, device=dev)
-                self._totals_host = torch.zeros(self.world, dtype=i32).pin_memory()
-                self._xstatus = torch.zeros(1, dtype=i32, device=dev)
-                self._packed_cap = 0
-        self._cells = torch.zeros(self.n_local * self.max_cells, dtype=i32, device=dev)
+        _lib.check(L.mpp_maaco_tables(self._maps, C.byref(self._params), _lib.ptr(self._tau), npad, _lib.ptr(self._E01),
+                                      _lib.ptr(self._dist_t), C.c_void_p(stream)), "mpp_maaco_tables")
+        # visited sets of the local ants as per-tile slabs + the (tile, ant) bitmaps (csrc/mpp_maaco.cu, header comment)
+        self._slabs = torch.empty(L.mpp_maaco_slab_words(self.tile_rows, Cc, nl), dtype=i32, device=dev)
+        self._touched = torch.zeros(L.mpp_maaco_touched_words(self.tile_rows, Cc, nl), dtype=i32, device=dev)
+        self._moves = torch.zeros(nl * self.max_cells, dtype=u8, device=dev)
         self._result = torch.zeros((num_ants, 2), dtype=i64, device=dev)   # mpp_ant_result per global ant
         self._deposit = torch.zeros(num_ants, dtype=f64, device=dev)
-        self._best_cells = torch.zeros(self.max_cells, dtype=i32, device=dev)
+        self._okbits = torch.zeros((num_ants + 31) // 32, dtype=i32, device=dev)
+        self._best_cells = torch.zeros(self.max_cells + 1, dtype=i32, device=dev)
         self._steps = torch.zeros(1, dtype=i64, device=dev)
         self._log = torch.zeros(max(1, num_iterations) * 4, dtype=f64, device=dev)
+        self._seeds = torch.from_numpy(np.array([self.rng_seed & (2 ** 64 - 1)], np.uint64).view(np.int64)).to(dev)
         st = _lib.MaacoState(INF, -1, 0, 0, -1, INF, -1, -1)
         self._state = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(dev)
+        self._latch = None
+        if self.world > 1:
+            tr = self.tile_rows_per_rank
+            self._slabs_recv = torch.zeros(L.mpp_maaco_slab_words(tr, Cc, num_ants), dtype=i32, device=dev)
+            self._touched_recv = torch.zeros(L.mpp_maaco_touched_words(tr, Cc, num_ants), dtype=i32, device=dev)
+            self._latch = torch.zeros(1, dtype=i32, device=dev)
+            self._offsets_local = torch.zeros(nl, dtype=i32, device=dev)
+            self._offsets = torch.zeros(num_ants, dtype=i32, device=dev)
+            self._xhdr = int(L.mpp_maaco_xhdr_bytes(nl))
+            # capacity of the move-code area of one rank's exchange buffer: generous for the first two passes, then
+            # 1.5 x the largest segment seen two passes earlier (identical on every rank: the totals travel in the
+            # headers); an overflow raises the device latch and the pass is repeated with more room
+            self._cap_max = _round64k(nl * min(self.max_cells, max(64, 2 * (R + Cc))))
+            self._cap = self._cap_max
+            self._xbuf_local = torch.zeros(self._xhdr + self._cap_max, dtype=u8, device=dev)
+            self._xbuf_all = torch.zeros(self.world * (self._xhdr + self._cap_max), dtype=u8, device=dev)
+            self._ring = [torch.zeros(self.world + 1, dtype=i32).pin_memory() for _ in range(4)]
+            self._ring_ev = [None] * 4
+            self._ring_cap = [0] * 4
+            self._enqueued = []                                  # (iteration, cap) of passes not yet confirmed
+        self._colony = _lib.Colony(
+            self._tau.data_ptr(), npad, self._E01.data_ptr(), 0, self._rank.data_ptr(), self._slabs.data_ptr(),
+            self._touched.data_ptr(), self._moves.data_ptr(), self.max_cells, max(1, num_iterations),
+            self._result.data_ptr(), self._deposit.data_ptr(), self._okbits.data_ptr(), self._state.data_ptr(),
+            self._best_cells.data_ptr(), self._log.data_ptr(), self._steps.data_ptr(), self._seeds.data_ptr(),
+            self._latch.data_ptr() if self._latch is not None else None)
 
         self.best_path_overall = []
         self.best_path_length_overall = INF
@@ -155,6 +173,7 @@ class MAACO:
     # ---- reference attributes materialised from device state ------------------------------
     @property
     def pheromone_matrix(self):
+        self._settle()
         n = self.rows * self.cols
         return self._tau[:n].cpu().numpy().reshape(self.rows, self.cols)
 
@@ -166,39 +185,6 @@ class MAACO:
         return _lib.lib().mpp_maaco_q0(self.num_iterations, int(current_iteration_num), self.q0_initial)
 
     # ---- one colony pass (MAACO.py:336-359), fully asynchronous ----------------------------
-    def _enqueue_tours(self, it, stream, mid_event=None):
-        nl, off = self.n_local, self.ant_offset
-        if self.use_rank:                                            # move ranking for the current tau
-            _lib.check(_lib.lib().mpp_maaco_rank(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E01), self.alpha,
-                                                 _lib.ptr(self._rank), stream), "mpp_maaco_rank")
-        if mid_event is not None:
-            mid_event.record()
-        _lib.check(_lib.lib().mpp_maaco_tours(
-            self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._E01), _lib.ptr(self._rank) if self.use_rank else None, it,
-            self._calculate_adaptive_q0(it), self.alpha, nl, off, C.c_uint64(self.rng_seed),
-            _lib.ptr(self._visit_local), _lib.ptr(self._cells), self.max_cells,
-            C.c_void_p(self._result.data_ptr() + 16 * off), _lib.ptr(self._steps), self.lanes_per_ant, stream),
-            "mpp_maaco_tours")
-
-    def _enqueue_best(self, it, stream):
-        _lib.check(_lib.lib().mpp_maaco_best(
-            _lib.ptr(self._result), _lib.ptr(self._cells), self.max_cells, self.ant_offset, self.n_local,
-            self.num_ants, self.Q, it, _lib.ptr(self._state), _lib.ptr(self._best_cells), _lib.ptr(self._deposit),
-            _lib.ptr(self._log), stream), "mpp_maaco_best")
-
-    def _enqueue_pheromone(self, stream):
-        L = _lib.lib()
-        if self.world == 1:
-            _lib.check(L.mpp_maaco_pheromone(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._visit_local),
-                                             _lib.ptr(self._deposit), 1, self.num_ants, 0, self.n_words, self.rho,
-                                             _lib.ptr(self._state), 1, stream), "mpp_maaco_pheromone")
-        else:
-            wn = self.words_per_rank
-            _lib.check(L.mpp_maaco_pheromone(self.map.handle, _lib.ptr(self._tau), _lib.ptr(self._visit_recv),
-                                             _lib.ptr(self._deposit), self.world, self.n_local, self.rank * wn, wn,
-                                             self.rho, _lib.ptr(self._state), 1 if self.exchange == "moves" else 0,
-                                             stream), "mpp_maaco_pheromone")
-
     def _enqueue_iteration(self, it, events=None):
         """One colony pass.  `events`: optional CUDA events recorded at (start, after tours, before the
         pheromone update, end[, after the ranking kernel]) on the launching stream -- used by bench.py for
@@ -206,58 +192,108 @@ class MAACO:
         import torch
         if not 1 <= it <= max(1, self.num_iterations):               # the per-iteration log has num_iterations rows
             raise ValueError(f"iteration {it} outside 1..{self.num_iterations}")
+        if self.world > 1:
+            self._confirm(upto=it - 2)                                # lagged, deterministic sizing of the exchange
+        self._enqueue_pass(it, events)
+
+    def _enqueue_pass(self, it, events=None):
+        import torch
+        L = _lib.lib()
         cur = torch.cuda.current_stream(self.device)
         stream = C.c_void_p(cur.cuda_stream)
+        col = C.byref(self._colony)
+        nl, off, N = self.n_local, self.ant_offset, self.num_ants
         if events:
             events[0].record(cur)
-        self._enqueue_tours(it, stream, events[4] if events and len(events) > 4 else None)
+        _lib.check(L.mpp_maaco_rank(self._maps, col, self.alpha, stream), "mpp_maaco_rank")
+        if events and len(events) > 4:
+            events[4].record(cur)
+        _lib.check(L.mpp_maaco_tours(self._maps, col, it, self._calculate_adaptive_q0(it), self.alpha, nl, off, N,
+                                     self._apw, stream), "mpp_maaco_tours")
         if events:
             events[1].record(cur)
-        if self.world > 1:
-            nl, off = self.n_local, self.ant_offset
-            L = _lib.lib()
-            # in-place all-gather: this rank's slice of the result table is already in position
-            dist_mod.exchange_results(self._result, self._result[off:off + nl], self.group)
-            if self.exchange == "dense":
-                dist_mod.exchange_visit_slices(self._visit_recv, self._visit_local, self.group)
-            else:
-                _lib.check(L.mpp_maaco_move_offsets(_lib.ptr(self._result), self.world, nl, _lib.ptr(self._offsets),
-                                                    _lib.ptr(self._totals), stream), "mpp_maaco_move_offsets")
-                self._totals_host.copy_(self._totals, non_blocking=True)
-                cur.synchronize()                                      # the all-gather below is sized on the host
-                cap = ((int(self._totals_host.max()) + 65535) // 65536) * 65536
-                if cap > self._packed_cap:
-                    self._packed_cap = cap
-                    self._packed_local = torch.empty(cap, dtype=torch.uint8, device=self.device)
-                    self._packed_all = torch.empty(cap * self.world, dtype=torch.uint8, device=self.device)
-                cap = self._packed_cap
-                _lib.check(L.mpp_maaco_pack_moves(self.map.handle, _lib.ptr(self._cells), self.max_cells,
-                                                  C.c_void_p(self._result.data_ptr() + 16 * off),
-                                                  C.c_void_p(self._offsets.data_ptr() + 4 * off), nl,
-                                                  _lib.ptr(self._packed_local), cap, _lib.ptr(self._xstatus), stream),
-                           "mpp_maaco_pack_moves")
-                dist_mod.exchange_moves(self._packed_all, self._packed_local, self.group)
-                wn = self.words_per_rank
-                _lib.check(L.mpp_maaco_rebuild_visits(self.map.handle, _lib.ptr(self._packed_all), cap,
-                                                      _lib.ptr(self._offsets), _lib.ptr(self._result), self.world, nl,
-                                                      self.rank * wn, wn, _lib.ptr(self._visit_recv), stream),
-                           "mpp_maaco_rebuild_visits")
-                self.kernel_launches += 3
-            # the local bitmaps are free again: clear them off the critical path
-            self._side.wait_stream(cur)
-            with torch.cuda.stream(self._side):
-                self._visit_local.zero_()
-        self._enqueue_best(it, stream)
-        if events:
-            events[2].record(cur)
-        self._enqueue_pheromone(stream)
-        if self.world > 1:
-            wn32 = self.words_per_rank * 32
-            dist_mod.gather_tau(self._tau, self._tau[self.rank * wn32:(self.rank + 1) * wn32], self.group)
-            cur.wait_stream(self._side)                                # next pass's tours need the cleared bitmaps
+        if self.world == 1:
+            _lib.check(L.mpp_maaco_best(self._maps, col, 0, nl, N, self.Q, it, stream), "mpp_maaco_best")
+            if events:
+                events[2].record(cur)
+            _lib.check(L.mpp_maaco_pheromone(self._maps, col, _lib.ptr(self._slabs), _lib.ptr(self._touched), N, 0,
+                                             self.tile_rows, self.rho, it, 0, stream), "mpp_maaco_pheromone")
+            self.kernel_launches += 4
+        else:
+            cap = self._cap
+            seg = self._xhdr + cap
+            _lib.check(L.mpp_maaco_xpack(self._maps, col, off, nl, N, _lib.ptr(self._offsets_local),
+                                         _lib.ptr(self._xbuf_local), cap, stream), "mpp_maaco_xpack")
+            # ONE all-gather per pass carries the results and the tours (move codes) of every rank
+            dist_mod.exchange_buffers(self._xbuf_all[:self.world * seg], self._xbuf_local[:seg], self.group)
+            tr = self.tile_rows_per_rank
+            _lib.check(L.mpp_maaco_xunpack(self._maps, col, _lib.ptr(self._xbuf_all), cap, self.world, nl, it,
+                                           _lib.ptr(self._offsets), self.rank * tr, tr, _lib.ptr(self._slabs_recv),
+                                           _lib.ptr(self._touched_recv), _lib.ptr(self._touched), stream),
+                       "mpp_maaco_xunpack")
+            _lib.check(L.mpp_maaco_best(self._maps, col, off, nl, N, self.Q, it, stream), "mpp_maaco_best")
+            if events:
+                events[2].record(cur)
+            _lib.check(L.mpp_maaco_pheromone(self._maps, col, _lib.ptr(self._slabs_recv), _lib.ptr(self._touched_recv),
+                                             N, self.rank * tr, tr, self.rho, it, 1, stream), "mpp_maaco_pheromone")
+            sl = tr * 32 * self.cols
+            dist_mod.gather_tau(self._tau, self._tau[self.rank * sl:(self.rank + 1) * sl], self.group)
+            # what the host needs two passes later: every segment's code total (from the gathered headers) + the latch
+            slot = it & 3
+            hdr_tot = self._xbuf_all.view(torch.int32).as_strided((self.world,), (seg // 4,), (16 * nl) // 4)
+            self._ring[slot][:self.world].copy_(hdr_tot, non_blocking=True)
+            self._ring[slot][self.world:].copy_(self._latch, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._ring_ev[slot] = ev
+            self._enqueued.append((it, cap))
+            self.kernel_launches += 8
         if events:
             events[3].record(cur)
-        self.kernel_launches += 4 if self.use_rank else 3
+
+    def _confirm(self, upto):
+        """Sharded colony: wait for the (tiny, asynchronous) header copies of every enqueued pass <= `upto`, size the
+        next exchange from them and repeat passes from the first one whose exchange overflowed."""
+        while self._enqueued and self._enqueued[0][0] <= upto:
+            it, cap = self._enqueued[0]
+            slot = it & 3
+            self._ring_ev[slot].synchronize()
+            vals = self._ring[slot].tolist()
+            totals, latch = vals[:self.world], vals[self.world]
+            if latch != 0:
+                self._rewind(latch)
+                continue
+            self._enqueued.pop(0)
+            self._cap = min(self._cap_max, _round64k(int(1.5 * max(totals)) + 4096))
+
+    def _rewind(self, first_bad):
+        """The exchange of pass `first_bad` did not fit: since then every kernel was a no-op (device latch), so the colony
+        is exactly as pass first_bad - 1 left it.  Make room and enqueue those passes again."""
+        import torch
+        torch.cuda.synchronize(self.device)
+        redo = [it for it, _ in self._enqueued if it >= first_bad]
+        cap_bad = dict(self._enqueued)[first_bad]
+        seg = self._xhdr + cap_bad
+        totals = self._xbuf_all.view(torch.int32).as_strided((self.world,), (seg // 4,), (16 * self.n_local) // 4).tolist()
+        if max(totals) <= cap_bad:                                   # not the capacity: a tour outgrew max_cells
+            raise _PathOverflow()
+        self._cap_max = max(self._cap_max, _round64k(2 * max(totals)))
+        self._cap = self._cap_max
+        if self._xbuf_local.numel() < self._xhdr + self._cap_max:
+            self._xbuf_local = torch.zeros(self._xhdr + self._cap_max, dtype=torch.uint8, device=self.device)
+            self._xbuf_all = torch.zeros(self.world * (self._xhdr + self._cap_max), dtype=torch.uint8, device=self.device)
+        self._latch.zero_()
+        self._enqueued = [e for e in self._enqueued if e[0] < first_bad]
+        self.exchange_rewinds = getattr(self, "exchange_rewinds", 0) + 1
+        for it in redo:
+            self._enqueue_pass(it)
+
+    def _settle(self):
+        """Block until everything enqueued has really happened (a sharded colony may have to repeat passes)."""
+        import torch
+        if self.world > 1:
+            self._confirm(upto=1 << 30)
+        torch.cuda.synchronize(self.device)
 
     def _read_state(self):
         st = _lib.MaacoState.from_buffer_copy(self._state.cpu().numpy().tobytes())
@@ -266,19 +302,16 @@ class MAACO:
     def solve_path_planning(self):
         import torch
         K = self.num_iterations
-        for it in range(self._iter_done + 1, K + 1):
-            self._enqueue_iteration(it)
-        torch.cuda.synchronize(self.device)
+        overflow = False
+        try:
+            for it in range(self._iter_done + 1, K + 1):
+                self._enqueue_iteration(it)
+            self._settle()
+        except _PathOverflow:
+            overflow = True
         self._iter_done = K
         st = self._read_state()
-        overflow = st.best_n_cells > self.max_cells
-        if self.world > 1:
-            import torch.distributed as dist
-            # every rank must take the same decision: the flag of the move-code exchange is rank-local
-            flag = torch.tensor([int(overflow) | (int(self._xstatus.item()) if self.exchange == "moves" else 0)],
-                                dtype=torch.int32, device=self.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
-            overflow = bool(flag.item())
+        overflow = overflow or st.best_n_cells - 1 > self.max_cells
         if overflow:
             if not self._auto_cells or self.max_cells >= self.rows * self.cols:
                 raise _lib.MppError(f"a tour outgrew max_cells={self.max_cells} (best path: {st.best_n_cells} cells); "
@@ -320,24 +353,63 @@ class MAACO:
         self._enqueue_iteration(it)
         self._iter_done = max(self._iter_done, it)
 
+    def run_iteration_host(self, it, tau_in=None, tau_out=None, result_out=None, best_out=None):
+        """One colony pass with HOST buffers through the C ABI's mpp_maaco_pass_host (synchronous): `tau_in`
+        (rows*cols float64, or None to keep the device field) is copied in, the pass runs, and the updated field, the
+        per-ant records (num_ants x {f8 length, i4 n_cells, i4 turns} = 16 bytes each) and the best path so far are
+        copied into `tau_out` / `result_out` / `best_out` (NumPy arrays or pinned torch tensors; any may be None).
+        Returns the colony state (best length / turns / n_cells ...).  Non-sharded colonies only."""
+        import torch
+        if self.world != 1:
+            raise _lib.MppError("run_iteration_host: a sharded colony exchanges device buffers; use run_iteration")
+        if not 1 <= it <= max(1, self.num_iterations):
+            raise ValueError(f"iteration {it} outside 1..{self.num_iterations}")
+
+        def hp(x, nbytes):
+            if x is None:
+                return None
+            if isinstance(x, torch.Tensor):
+                assert not x.is_cuda and x.is_contiguous() and x.numel() * x.element_size() >= nbytes
+                return C.c_void_p(x.data_ptr())
+            assert x.flags["C_CONTIGUOUS"] and x.nbytes >= nbytes
+            return C.c_void_p(x.ctypes.data)
+        n = self.rows * self.cols
+        st = _lib.MaacoState()
+        cap = 0 if best_out is None else (best_out.numel() if isinstance(best_out, torch.Tensor) else best_out.size)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(_lib.lib().mpp_maaco_pass_host(
+            self._maps, C.byref(self._colony), C.byref(self._params), it, self.num_ants, self._apw, hp(tau_in, n * 8),
+            hp(tau_out, n * 8), hp(result_out, self.num_ants * 16), C.byref(st), hp(best_out, 4), cap, stream),
+            "mpp_maaco_pass_host")
+        self._iter_done = max(self._iter_done, it)
+        self.kernel_launches += 4
+        return st
+
     def last_results(self):
         """(n_cells, length, turns) of every ant of the colony in the last pass (numpy)."""
-        import torch
-        torch.cuda.synchronize(self.device)
+        self._settle()
         raw = self._result.cpu().numpy()
         rec = raw.view(np.dtype([("length", "<f8"), ("n_cells", "<i4"), ("turns", "<i4")])).reshape(-1)
         return rec["n_cells"].copy(), rec["length"].copy(), rec["turns"].copy()
 
     def last_tours(self):
-        """(n_cells, length, turns, cells[n_local, <= max_cells]) of this rank's ants in the last pass (only the
-        columns some tour reached are copied to the host)."""
+        """(n_cells, length, turns, cells[n_local, <= max_cells + 1]) of this rank's ants in the last pass; the tours
+        are decoded from their move codes (only the columns some tour reached are copied to the host)."""
         nc, ln, tn = self.last_results()
         sl = slice(self.ant_offset, self.ant_offset + self.n_local)
-        used = int(min(self.max_cells, max(1, nc[sl].max(initial=1))))
-        cells = self._cells.view(self.n_local, self.max_cells)[:, :used].cpu().numpy()
-        return nc[sl], ln[sl], tn[sl], cells
+        used = int(min(self.max_cells, max(1, nc[sl].max(initial=1) - 1)))
+        mv = self._moves.view(self.n_local, self.max_cells)[:, :used].cpu().numpy()
+        dr = np.array([-1, -1, -1, 0, 0, 1, 1, 1])                     # move order MAACO.py:98
+        dc = np.array([-1, 0, 1, -1, 1, -1, 0, 1])
+        delta = (dr * self.cols + dc).astype(np.int64)[mv & 7]
+        cells = np.empty((self.n_local, used + 1), np.int64)
+        cells[:, 0] = self.start_node[0] * self.cols + self.start_node[1]
+        np.cumsum(delta, axis=1, out=cells[:, 1:])
+        cells[:, 1:] += cells[:, :1]
+        return nc[sl], ln[sl], tn[sl], cells.astype(np.int32)
 
     def total_steps(self):
+        self._settle()
         return int(self._steps.cpu().item())
 
     # ---- plotting hooks of the reference (MAACO.py:373-377): out of scope, forwarded if possible --

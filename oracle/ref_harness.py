@@ -163,10 +163,13 @@ class _NpProxy:
 # Loading the reference
 # ----------------------------------------------------------------------------
 def ref_dir():
-    d = os.environ.get("MAACO_REF_DIR", "/root/reference")
-    if not os.path.isfile(os.path.join(d, "MAACO.py")):
-        raise FileNotFoundError(f"reference tree not found at {d}")
-    return d
+    """$MAACO_REF_DIR -> /root/reference (the authoring container) -> <repo>/baseline/_ref (the git-ignored copy that
+    __graft_entry__.build() makes and that travels to the GPU box)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d in (os.environ.get("MAACO_REF_DIR"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if d and os.path.isfile(os.path.join(d, "MAACO.py")):
+            return d
+    raise FileNotFoundError("reference tree not found ($MAACO_REF_DIR, /root/reference, baseline/_ref)")
 
 
 def _install_matplotlib_stub():

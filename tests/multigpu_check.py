@@ -25,7 +25,7 @@ def main():
                   q0_initial=0.5, C0_initial_pheromone=0.1)
     g = blocks_map(96, 0.2, seed=11)
     N, K, seed = 64 * world, 6, 9
-    dev = MAACO(g, N, K, rng_seed=seed, device=local, group=dist.group.WORLD, verbose=False, exchange=os.environ.get("MPP_EXCHANGE", "moves"), **params)
+    dev = MAACO(g, N, K, rng_seed=seed, device=local, group=dist.group.WORLD, verbose=False, **params)
     orc = O.MaacoOracle(g, N, K, seed=seed, **params)
     for it in range(1, K + 1):
         dev.run_iteration(it)
@@ -38,6 +38,15 @@ def main():
     orc2 = O.MaacoOracle(g, N, K, seed=seed, **params)
     opath, olen, oturns = orc2.solve()
     assert [r * 96 + c for r, c in path] == list(opath) and length == olen and turns == oturns, f"rank {rank} solve"
+    # an exchange buffer that is far too small: the device latch stops the colony, the host makes room and repeats
+    dev3 = MAACO(g, N, K, rng_seed=seed, device=local, group=dist.group.WORLD, verbose=False, **params)
+    dev3._cap = dev3._cap_max = 0
+    orc3 = O.MaacoOracle(g, N, K, seed=seed, **params)
+    for it in range(1, K + 1):
+        dev3.run_iteration(it)
+        orc3.iterate(it)
+    assert np.array_equal(dev3.pheromone_matrix.ravel(), orc3.tau), f"rank {rank} tau after rewind"
+    assert getattr(dev3, "exchange_rewinds", 0) >= 1, "the tiny exchange buffer should have overflowed"
     dist.barrier()
     if rank == 0:
         print(f"multigpu_check ok: world={world}, {N} ants, {K} passes bit-exact vs oracle")

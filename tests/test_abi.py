@@ -51,7 +51,7 @@ def test_ctypes_signatures_match_header_arity():
 def test_abi_version_and_error_string():
     from maaco_path_planing_b200 import _lib
     L = _lib.lib()
-    assert L.mpp_abi_version() == 1
+    assert L.mpp_abi_version() == 2
     assert isinstance(L.mpp_last_error(), bytes)
 
 

@@ -1,8 +1,9 @@
 """The N>1 path on CPU: two gloo ranks shard a colony exactly the way the NCCL ranks do
-(maaco_path_planing_b200/dist.py): all-gather of per-ant results, all-to-all of visited-bitmap word
-slices, slice-wise ordered deposit, all-gather of tau slices.  The tours and the arithmetic come from
-the oracle (there is no GPU here); what is under test is the sharding / exchange layout and that the
-ordered merge reproduces the single-colony pheromone field bit-for-bit."""
+(maaco_path_planing_b200/dist.py + the exchange protocol of csrc/mpp_maaco.cu): ONE all-gather of per-rank buffers
+holding the per-ant results and the tours as move codes, replay of every ant into this rank's slice of tile rows,
+slice-wise ordered deposit, all-gather of tau slices.  The tours and the arithmetic come from the oracle (there is no
+GPU here); what is under test is the sharding / buffer layout / host-side sizing and that the ordered merge
+reproduces the single-colony pheromone field bit-for-bit."""
 import os
 import sys
 
@@ -14,6 +15,59 @@ import torch.multiprocessing as mp
 
 from conftest import MAACO_DEFAULT, ROOT
 
+REC = np.dtype([("length", "<f8"), ("n_cells", "<i4"), ("turns", "<i4")])
+DR = np.array([-1, -1, -1, 0, 0, 1, 1, 1])                                # move order MAACO.py:98
+DC = np.array([-1, 0, 1, -1, 1, -1, 0, 1])
+
+
+def pack_buffer(cells, ncell, length, turns, C, cap):
+    """numpy statement of mpp_maaco_xpack: [n_local x mpp_ant_result][int32 total + 12 pad][codes]."""
+    nl = len(ncell)
+    hdr = 16 * nl + 16
+    buf = np.zeros(hdr + cap, np.uint8)
+    rec = np.zeros(nl, REC)
+    rec["length"], rec["n_cells"], rec["turns"] = length, ncell, turns
+    buf[:16 * nl] = rec.view(np.uint8)
+    off = 0
+    for a in range(nl):
+        n = int(ncell[a])
+        if n > 1:
+            d = np.diff(cells[a, :n].astype(np.int64))
+            dr = np.round(d / C).astype(int)
+            dc = d - dr * C
+            code = (dr + 1) * 3 + (dc + 1)
+            code = code - (code > 4)
+            if off + n - 1 <= cap:
+                buf[hdr + off:hdr + off + n - 1] = code
+            off += n - 1
+    buf[16 * nl:16 * nl + 4] = np.array([off], np.int32).view(np.uint8)
+    return buf
+
+
+def unpack_visits(buf_all, world, nl, cap, start, R, C, row0, rows):
+    """numpy statement of mpp_maaco_xunpack: records of all ants + the visited cells of every ant that fall into cell
+    rows [row0, row0 + rows)."""
+    hdr = 16 * nl + 16
+    seg = hdr + cap
+    recs, visits = [], []
+    for s in range(world):
+        b = buf_all[s * seg:(s + 1) * seg]
+        rec = b[:16 * nl].view(REC)
+        total = int(b[16 * nl:16 * nl + 4].view(np.int32)[0])
+        assert total <= cap, "exchange buffer overflow"
+        recs.append(rec)
+        off = 0
+        for a in range(nl):
+            n = int(rec["n_cells"][a])
+            mine = []
+            if n > 0:
+                codes = b[hdr + off:hdr + off + n - 1].astype(int)
+                cell = start + np.concatenate([[0], np.cumsum(DR[codes] * C + DC[codes])])
+                mine = [int(x) for x in cell if row0 <= x // C < row0 + rows]
+                off += n - 1
+            visits.append(mine)
+    return np.concatenate(recs), visits
+
 
 def _worker(rank, world, port, ret):
     sys.path.insert(0, ROOT)
@@ -24,31 +78,31 @@ def _worker(rank, world, port, ret):
         import pyoracle as O
         from maaco_path_planing_b200 import dist as dm
         from maaco_path_planing_b200.gridmap import blocks_map
-        g = blocks_map(40, 0.2, seed=3)
+        g = blocks_map(0, 0.2, seed=3, rows=70, cols=40)                   # 3 tile rows over 2 ranks: a padded slice
+        R, C = g.shape
         N, K, seed = 48, 3, 17
         n = g.size
         lo, hi = dm.shard_range(N, world, rank)
         nl = hi - lo
-        W = dm.padded_words(n, world)
-        wn = W // world
+        TR = (R + 31) // 32
+        per = dm.padded_tile_rows(TR, world) // world                     # tile rows per rank
+        npad = per * world * 32 * C
         full = O.MaacoOracle(g, N, K, seed=seed, **MAACO_DEFAULT)          # single-colony truth
         mine = O.MaacoOracle(g, N, K, seed=seed, **MAACO_DEFAULT)          # this rank's replica of tau
         grid = g.ravel()
+        (sr, sc), _ = O.find_start_target(g)
+        cap = 65536
         for it in range(1, K + 1):
             full.iterate(it)
             cells, ncell, length, turns, tabu = mine.tours(it, ant0=lo, n_ants=nl)     # only my ants
-            # per-ant results, packed like mpp_ant_result (length f64, n_cells i32, turns i32)
-            rec = np.zeros(nl, dtype=[("length", "<f8"), ("n_cells", "<i4"), ("turns", "<i4")])
-            rec["length"], rec["n_cells"], rec["turns"] = length, ncell, turns
-            res_all = torch.zeros((N, 2), dtype=torch.int64)
-            dm.exchange_results(res_all, torch.from_numpy(rec.view(np.int64).reshape(nl, 2).copy()), dist.group.WORLD)
-            allrec = res_all.numpy().view(rec.dtype).reshape(-1)
-            # word-major visited bitmaps of my ants: [W][nl]
-            vis = np.zeros((W, nl), np.int32)
-            vis[:tabu.shape[1], :] = tabu.view(np.int32).T
-            recv = torch.zeros(W * nl, dtype=torch.int32)
-            dm.exchange_visit_slices(recv, torch.from_numpy(vis.reshape(-1).copy()), dist.group.WORLD)
-            seg = recv.numpy().view(np.uint32).reshape(world, wn, nl)       # [source rank][my words][its ants]
+            buf = pack_buffer(cells, ncell, length, turns, C, cap)
+            buf_all = torch.zeros(world * buf.size, dtype=torch.uint8)
+            dm.exchange_buffers(buf_all, torch.from_numpy(buf), dist.group.WORLD)
+            allrec, visits = unpack_visits(buf_all.numpy(), world, nl, cap, sr * C + sc, R, C, rank * per * 32, per * 32)
+            # the replayed cells are exactly the visited set the oracle recorded (for my own ants: check)
+            for a in range(nl):
+                want = [c for c in cells[a, :ncell[a]] if rank * per * 32 <= c // C < (rank + 1) * per * 32]
+                assert visits[lo + a] == [int(c) for c in want]
             # replicated best tracking (MAACO.py:343-358) on the gathered results
             bl, bt, bi = np.inf, -1, -1
             for i in range(N):
@@ -61,26 +115,24 @@ def _worker(rank, world, port, ret):
                 mine.best_len, mine.best_turns = bl, bt
             elif abs(bl - mine.best_len) < 1e-9 and bt < mine.best_turns:
                 mine.best_turns = bt
-            # slice-wise ordered deposit == mpp_maaco_pheromone(n_seg=world, seg_ants=nl, word0=rank*wn, n_words=wn)
+            # slice-wise ordered deposit == mpp_maaco_pheromone(tile_row0 = rank*per, buf_tile_rows = per)
             p = mine.p
             tau = mine.tau
-            c0, c1 = rank * wn * 32, min(n, (rank + 1) * wn * 32)
-            sl = np.zeros(wn * 32)
+            c0, c1 = rank * per * 32 * C, min(n, (rank + 1) * per * 32 * C)
+            sl = np.zeros(per * 32 * C)
+            acc = {cell: tau[cell] * (1.0 - p.rho) for cell in range(c0, c1)}
+            for i in range(N):                                             # global ant order
+                l = allrec["length"][i]
+                if np.isfinite(l) and allrec["n_cells"][i] > 0 and l > 1e-6:
+                    for cell in visits[i]:
+                        acc[cell] += p.Q / l
+            best = mine.best_len if np.isfinite(mine.best_len) else float(p.rows + p.cols)
+            best = max(best, 1e-6)
+            tmax = (1.0 / (1.0 - p.rho)) * (1.0 / best)
+            tmin = tmax / (2.0 * max(p.cols, p.rows, 1))
             for cell in range(c0, c1):
-                t = tau[cell] * (1.0 - p.rho)
-                w, b = divmod(cell - c0, 32)
-                for s in range(world):
-                    for a in range(nl):
-                        if (seg[s, w, a] >> b) & 1:
-                            l = allrec["length"][s * nl + a]
-                            if np.isfinite(l) and allrec["n_cells"][s * nl + a] > 0 and l > 1e-6:
-                                t += p.Q / l
-                best = mine.best_len if np.isfinite(mine.best_len) else float(p.rows + p.cols)
-                best = max(best, 1e-6)
-                tmax = (1.0 / (1.0 - p.rho)) * (1.0 / best)
-                tmin = tmax / (2.0 * max(p.cols, p.rows, 1))
-                sl[cell - c0] = 1e-9 if grid[cell] == 1 else min(max(t, tmin), tmax)
-            tau_full = torch.zeros(W * 32, dtype=torch.float64)
+                sl[cell - c0] = 1e-9 if grid[cell] == 1 else min(max(acc[cell], tmin), tmax)
+            tau_full = torch.zeros(npad, dtype=torch.float64)
             dm.gather_tau(tau_full, torch.from_numpy(sl), dist.group.WORLD)
             mine.tau[:] = tau_full.numpy()[:n]
             assert np.array_equal(mine.tau, full.tau), f"rank {rank}: tau differs after pass {it}"
@@ -113,6 +165,6 @@ def test_shard_helpers():
     assert dm.shard_range(4096, 8, 3) == (1536, 2048)
     with pytest.raises(ValueError):
         dm.shard_range(10, 4, 0)
-    assert dm.padded_words(512 * 512, 8) == 8192 and dm.padded_words(20 * 20, 8) == 16
+    assert dm.padded_tile_rows(16, 8) == 16 and dm.padded_tile_rows(3, 2) == 4 and dm.padded_tile_rows(1, 8) == 8
     from maaco_path_planing_b200.batch import shard_maps
     assert shard_maps(7) == (0, 7)

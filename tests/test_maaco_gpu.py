@@ -26,14 +26,14 @@ def _check_pass(dev, orc, it, N, exact_tau=True, rtol=0.0):
 
 
 @pytest.mark.parametrize("name", MAACO_CASES)
-@pytest.mark.parametrize("lpa", [1, 32, 16, 8])
-def test_golden_trajectories(name, lpa):
+@pytest.mark.parametrize("apw", [0, 1, 4, 32])
+def test_golden_trajectories(name, apw):
     """CUDA vs the reference's own recorded trajectory (per-ant paths, tau after every pass)."""
     from maaco_path_planing_b200 import MAACO
     g = load_golden("maaco_" + name)
     N, K = int(g["N"]), int(g["K"])
     alpha1 = g["params"]["alpha"] == 1.0
-    dev = MAACO(g["grid"].astype(int), N, K, rng_seed=int(g["seed"]), lanes_per_ant=lpa, verbose=False, **g["params"])
+    dev = MAACO(g["grid"].astype(int), N, K, rng_seed=int(g["seed"]), ants_per_warp=apw, verbose=False, **g["params"])
     assert np.array_equal(dev.pheromone_matrix, g["tau0"])
     pos = 0
     for it in range(1, K + 1):
@@ -62,15 +62,15 @@ def test_golden_trajectories(name, lpa):
 
 
 @pytest.mark.parametrize("name", MAACO_DEFAULT_CASES)
-@pytest.mark.parametrize("lpa", [1, 32])
-def test_reference_default_trajectories(name, lpa):
+@pytest.mark.parametrize("apw", [0, 32])
+def test_reference_default_trajectories(name, apw):
     """BASELINE config 1 (MAACO at main.py:34-38's parameters: 50 ants x 100 iterations) on each demo map of env.py,
     and grid_map_from_image_data5 (256x256): every tour of every pass, tau after every pass, the returned best path and
     the convergence curve equal the reference's own recorded run."""
     from maaco_path_planing_b200 import MAACO
     g = load_golden("maaco_" + name)
     N, K = int(g["N"]), int(g["K"])
-    dev = MAACO(g["grid"].astype(int), N, K, rng_seed=int(g["seed"]), lanes_per_ant=lpa, verbose=False, **g["params"])
+    dev = MAACO(g["grid"].astype(int), N, K, rng_seed=int(g["seed"]), ants_per_warp=apw, verbose=False, **g["params"])
     assert np.array_equal(dev.pheromone_matrix, g["tau0"])
     pos = 0
     for it in range(1, K + 1):
@@ -91,13 +91,13 @@ def test_reference_default_trajectories(name, lpa):
     assert np.array_equal(curve, g["curve"])
 
 
-@pytest.mark.parametrize("lpa", [1, 32, 16, 8])
-def test_solve_matches_oracle_and_reference_api(lpa):
+@pytest.mark.parametrize("apw", [0, 1, 8, 32])
+def test_solve_matches_oracle_and_reference_api(apw):
     from maaco_path_planing_b200 import MAACO
     import pyoracle as O
     g = load_golden("maaco_fig7")
     N, K, seed = 50, 30, 77
-    dev = MAACO(g["grid"].astype(int), N, K, rng_seed=seed, lanes_per_ant=lpa, verbose=False, **MAACO_DEFAULT)
+    dev = MAACO(g["grid"].astype(int), N, K, rng_seed=seed, ants_per_warp=apw, verbose=False, **MAACO_DEFAULT)
     path, length, turns = dev.solve_path_planning()
     orc = O.MaacoOracle(g["grid"].astype(int), N, K, seed=seed, **MAACO_DEFAULT)
     opath, olen, oturns = orc.solve()
@@ -152,12 +152,12 @@ def test_config4_full_size_vs_oracle_and_properties():
 
 
 def test_lane_layouts_agree():
-    """8-lane and 32-lane tour kernels are the same function."""
+    """Every packing of ants into warps is the same function."""
     from maaco_path_planing_b200 import MAACO, blocks_map
     g = blocks_map(128, 0.2, seed=31)
     outs = []
-    for lpa in (1, 8, 16, 32):
-        dev = MAACO(g, 300, 2, rng_seed=5, lanes_per_ant=lpa, verbose=False, **MAACO_DEFAULT)
+    for apw in (0, 1, 2, 8, 16, 32):
+        dev = MAACO(g, 300, 2, rng_seed=5, ants_per_warp=apw, verbose=False, **MAACO_DEFAULT)
         dev.run_iteration(1)
         dev.run_iteration(2)
         outs.append((dev.last_tours(), dev.pheromone_matrix))
@@ -182,9 +182,9 @@ def test_large_unaligned_map_vs_oracle():
     assert (nc > 0).sum() > N // 2 and nc.max() > 1200
 
 
-def test_ants_per_warp_and_table_modes_agree(monkeypatch):
-    """The thread-per-ant kernel gives the same colony for every packing of ants into warps, and the
-    table-free path (use_rank=False: literal selection rules at every step) is the same function."""
+def test_ants_per_warp_env_override_agrees(monkeypatch):
+    """The tour kernel gives the same colony for every packing of ants into warps (here forced through the
+    MPP_TOUR_APW environment switch) on a map whose columns are not a multiple of the 32-cell tile."""
     from maaco_path_planing_b200 import MAACO, blocks_map
     import pyoracle as O
     g = blocks_map(150, 0.2, seed=77)                      # 150 columns: window words straddle bitmap words
@@ -192,12 +192,12 @@ def test_ants_per_warp_and_table_modes_agree(monkeypatch):
     orc = O.MaacoOracle(g, N, 2, seed=9, threads=0, **MAACO_DEFAULT)
     ref = [orc.iterate(1), orc.iterate(2)]
     tau_ref = orc.tau.copy()
-    for apw, use_rank in ((1, True), (4, True), (32, True), (0, False)):
+    for apw in (1, 4, 32, 0):
         if apw:
             monkeypatch.setenv("MPP_TOUR_APW", str(apw))
         else:
             monkeypatch.delenv("MPP_TOUR_APW", raising=False)
-        dev = MAACO(g, N, 2, rng_seed=9, use_rank=use_rank, verbose=False, **MAACO_DEFAULT)
+        dev = MAACO(g, N, 2, rng_seed=9, verbose=False, **MAACO_DEFAULT)
         for it in (1, 2):
             dev.run_iteration(it)
             nc, ln, tn, cells = dev.last_tours()
@@ -245,69 +245,140 @@ def test_sharded_colony_two_gpus():
 
 
 def test_batched_maps_equal_individual_solves():
-    """Config-5 style sweep: several independent maps solved concurrently (one stream per colony) give exactly
-    the per-map results."""
+    """Config-5 style sweep: independent maps solved as waves of one launch per colony pass (grid.y = map) give
+    exactly the per-map results -- every pass's per-ant records and pheromone fields, and the returned solutions."""
     from maaco_path_planing_b200 import MAACO, blocks_map
-    from maaco_path_planing_b200.batch import solve_maaco_batch
+    from maaco_path_planing_b200.batch import MAACOBatch, solve_maaco_batch
     grids = [blocks_map(64, 0.2, seed=500 + i) for i in range(5)]
     seeds = [900 + i for i in range(5)]
-    res = solve_maaco_batch(grids, 128, 4, MAACO_DEFAULT, seeds=seeds, concurrent=3)
+    res = solve_maaco_batch(grids, 128, 4, MAACO_DEFAULT, seeds=seeds, wave=3)
     assert [r[0] for r in res] == list(range(5))
+    solos = []
     for i, path, length, turns, curve in res:
         solo = MAACO(grids[i], 128, 4, rng_seed=seeds[i], verbose=False, **MAACO_DEFAULT)
         p2, l2, t2 = solo.solve_path_planning()
         assert path == p2 and length == l2 and turns == t2 and curve == solo.convergence_curve_data
+        solos.append(solo)
+    b = MAACOBatch(np.stack(grids), 128, 4, seeds=seeds, **MAACO_DEFAULT)
+    refs = [MAACO(grids[i], 128, 4, rng_seed=seeds[i], verbose=False, **MAACO_DEFAULT) for i in range(5)]
+    for it in (1, 2, 3):
+        b.run_iteration(it)
+        nc, ln, tn = b.last_results()
+        tau = b.pheromone()
+        for i, r in enumerate(refs):
+            r.run_iteration(it)
+            rn, rl, rt = r.last_results()
+            assert np.array_equal(nc[i], rn) and np.array_equal(ln[i], rl) and np.array_equal(tn[i], rt)
+            assert np.array_equal(tau[i], r.pheromone_matrix)
+    # maps with different start / target cannot share the wave's tables: they are grouped apart
+    g2 = [g.copy() for g in grids[:3]]
+    g2[1][0, 0], g2[1][0, 5] = 0, 2
+    res2 = solve_maaco_batch(g2, 64, 2, MAACO_DEFAULT, seeds=[1, 2, 3], wave=8)
+    for i, path, length, turns, curve in res2:
+        solo = MAACO(g2[i], 64, 2, rng_seed=[1, 2, 3][i], verbose=False, **MAACO_DEFAULT)
+        assert (path, length, turns) == solo.solve_path_planning()
 
 
-def test_segmented_pheromone_equals_single_segment():
-    """The segmented update used by the sharded colony ([segment][word][ant] bitmaps, one segment per source
-    rank) folds ants in the same global order as the single-segment kernel: identical tau for identical
-    (re-laid-out) visited bitmaps and deposits."""
+def test_pheromone_kernel_vs_numpy_and_tile_row_slices():
+    """mpp_maaco_pheromone on synthetic slabs: (a) equals a plain sequential fold in ant order (MAACO.py:304-332) on
+    every cell, (b) the update of a slice of tile rows from slice-shaped buffers (what a sharded colony's ranks run,
+    with clear_slabs) writes exactly the cells of that slice with the same values."""
     import ctypes as C
     import torch
-    from maaco_path_planing_b200 import _lib, GridMap, blocks_map
-    g = blocks_map(96, 0.2, seed=77)
-    gm = GridMap(g)
-    dev = torch.device("cuda", gm.device)
-    n = g.size
-    words = (n + 31) // 32
-    n_seg, seg_ants = 4, 96
-    N = n_seg * seg_ants
+    from maaco_path_planing_b200 import MAACO, _lib, blocks_map
+    g = blocks_map(0, 0.2, seed=77, rows=100, cols=150)                  # 4 x 5 tiles, ragged right / bottom edges
+    R, Cc = g.shape
+    N = 2500                                                              # > one list chunk (2048 ants)
+    m = MAACO(g, N, 2, rng_seed=1, verbose=False, **MAACO_DEFAULT)
+    dev = m.device
+    TR, TC = m.tile_rows, m.tile_cols
+    NW = (N + 31) // 32
     rng = np.random.default_rng(5)
-    vis = np.zeros((words, N), np.uint32)                                  # [word][global ant]
-    hits = rng.random((words, N)) < 0.05
-    vis[hits] = rng.integers(1, 2**32, hits.sum(), dtype=np.uint64).astype(np.uint32)
-    vis[:3, :] = rng.integers(1, 2**32, (3, N), dtype=np.uint64).astype(np.uint32)   # dense words (start region)
+    slabs = np.zeros((TR * TC, N, 32), np.uint32)
+    touched = np.zeros((TR * TC, NW), np.uint32)
+    pair = rng.random((TR * TC, N)) < 0.08
+    pair[0, :] = True                                                     # the start tile: every ant
+    for t, a in zip(*np.nonzero(pair)):
+        rows = rng.random(32) < 0.4
+        w = rng.integers(1, 2 ** 32, 32, dtype=np.uint64).astype(np.uint32) & rng.integers(0, 2 ** 32, 32, dtype=np.uint64).astype(np.uint32)
+        slabs[t, a] = np.where(rows, w, 0)
+        touched[t, a >> 5] |= np.uint32(1 << (a & 31))
+    slabs[0, :, 0] |= 1                                                   # cell (0, 0): visited by all
     dep = rng.random(N) * 0.01
-    dep[rng.random(N) < 0.3] = 0.0                                         # failed ants deposit nothing
-    tau0 = rng.random(words * 32) + 0.01
+    dep[rng.random(N) < 0.3] = 0.0                                        # failed ants deposit nothing
+    ok = np.zeros(NW, np.uint32)
+    for a in np.flatnonzero(dep != 0.0):
+        ok[a >> 5] |= np.uint32(1 << (a & 31))
+    tau0 = rng.random(R * Cc) + 0.01
     st = _lib.MaacoState(123.5, 7, 0, 0, -1, 0.0, -1, -1)
-    state = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(dev)
+    m._state.copy_(torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8))
+    m._deposit.copy_(torch.as_tensor(dep))
+    m._okbits.copy_(torch.as_tensor(ok.view(np.int32)))
     L = _lib.lib()
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    outs = []
-    for layout in ("single", "chained"):
-        tau = torch.as_tensor(tau0.copy(), device=dev)
-        if layout == "single":
-            v = torch.as_tensor(vis.view(np.int32).copy(), device=dev)
-            args = (1, N)
-        else:
-            seg = vis.reshape(words, n_seg, seg_ants).transpose(1, 0, 2).copy()   # [seg][word][ant in seg]
-            v = torch.as_tensor(seg.view(np.int32), device=dev)
-            args = (n_seg, seg_ants)
-        d = torch.as_tensor(dep, device=dev)
-        _lib.check(L.mpp_maaco_pheromone(gm.handle, _lib.ptr(tau), _lib.ptr(v), _lib.ptr(d), args[0], args[1], 0, words,
-                                         0.1, _lib.ptr(state), 0, stream), "mpp_maaco_pheromone")
-        torch.cuda.synchronize()
-        outs.append(tau.cpu().numpy())
-    assert np.array_equal(outs[0], outs[1])
-    # and against a plain numpy fold for a few cells
-    for cell in (0, 5, 33, 700, n - 1):
-        t = tau0[cell] * (1.0 - 0.1)
-        for a in range(N):
-            if (vis[cell >> 5, a] >> (cell & 31)) & 1:
-                t += dep[a]
-        tmax = (1.0 / (1.0 - 0.1)) * (1.0 / 123.5)
-        tmin = tmax / (2.0 * 96)
-        want = 1e-9 if g.ravel()[cell] == 1 else min(max(t, tmin), tmax)
-        assert outs[0][cell] == want
+    it = 3                                                                # parity 1
+    # ---- numpy truth ----
+    want = np.empty(R * Cc)
+    tmax = (1.0 / (1.0 - 0.1)) * (1.0 / 123.5)
+    tmin = tmax / (2.0 * max(R, Cc))
+    for r in range(R):
+        for c in range(Cc):
+            t_ = (r >> 5) * TC + (c >> 5)
+            t = tau0[r * Cc + c] * (1.0 - 0.1)
+            col = (slabs[t_, :, r & 31] >> np.uint32(c & 31)) & 1
+            for a in np.flatnonzero(col):
+                t += dep[a]                                               # + 0.0 for non-depositing ants: exact
+            want[r * Cc + c] = 1e-9 if g[r, c] == 1 else min(max(t, tmin), tmax)
+    # ---- (a) whole map ----
+    m._tau[:R * Cc].copy_(torch.as_tensor(tau0))
+    sl = torch.as_tensor(slabs.view(np.int32).reshape(-1), device=dev)
+    tb = torch.zeros(2 * TR * TC * NW, dtype=torch.int32, device=dev)
+    tb[TR * TC * NW:].copy_(torch.as_tensor(touched.view(np.int32).reshape(-1)))      # parity it & 1 = 1
+    tb[:TR * TC * NW] = -1                                                # the other parity must come back cleared
+    _lib.check(L.mpp_maaco_pheromone(m._maps, C.byref(m._colony), _lib.ptr(sl), _lib.ptr(tb), N, 0, TR, 0.1, it, 0, stream),
+               "mpp_maaco_pheromone")
+    got = m._tau[:R * Cc].cpu().numpy()
+    assert np.array_equal(got, want)
+    assert int(tb[:TR * TC * NW].abs().sum()) == 0
+    assert np.array_equal(sl.cpu().numpy(), slabs.view(np.int32).reshape(-1))          # clear_slabs = 0: untouched
+    # ---- (b) two slices of tile rows (the second one padded past the map, like the last rank's) ----
+    m._tau[:R * Cc].copy_(torch.as_tensor(tau0))
+    per = 3
+    for row0 in (0, per):
+        rows_in = max(0, min(TR, row0 + per) - row0)
+        s_sl = np.zeros((per * TC, N, 32), np.uint32)
+        s_tb = np.zeros((2, per * TC, NW), np.uint32)
+        s_sl[:rows_in * TC] = slabs[row0 * TC:(row0 + rows_in) * TC]
+        s_tb[it & 1, :rows_in * TC] = touched[row0 * TC:(row0 + rows_in) * TC]
+        d_sl = torch.as_tensor(s_sl.view(np.int32).reshape(-1), device=dev)
+        d_tb = torch.as_tensor(s_tb.view(np.int32).reshape(-1), device=dev)
+        _lib.check(L.mpp_maaco_pheromone(m._maps, C.byref(m._colony), _lib.ptr(d_sl), _lib.ptr(d_tb), N, row0, per, 0.1, it, 1,
+                                         stream), "mpp_maaco_pheromone")
+        # what was read (slabs of depositing ants) has been cleared
+        left = d_sl.cpu().numpy().view(np.uint32).reshape(per * TC, N, 32)
+        assert not left[:, dep != 0.0].any()
+    assert np.array_equal(m._tau[:R * Cc].cpu().numpy(), want)
+
+
+def test_host_buffer_pass_equals_device_pass():
+    """MAACO.run_iteration_host (C ABI mpp_maaco_pass_host: host pheromone field in; per-ant records, best path and
+    updated field out, synchronous) is the same function as the device-resident pass."""
+    from maaco_path_planing_b200 import MAACO, blocks_map
+    g = blocks_map(96, 0.2, seed=12)
+    N, K = 256, 3
+    a = MAACO(g, N, K, rng_seed=5, verbose=False, **MAACO_DEFAULT)
+    b = MAACO(g, N, K, rng_seed=5, verbose=False, **MAACO_DEFAULT)
+    tau = b.pheromone_matrix.ravel().copy()
+    res = np.zeros(N, dtype=[("length", "<f8"), ("n_cells", "<i4"), ("turns", "<i4")])
+    best = np.zeros(4096, np.int32)
+    for it in range(1, K + 1):
+        a.run_iteration(it)
+        st = b.run_iteration_host(it, tau_in=tau, tau_out=tau, result_out=res, best_out=best)
+        nc, ln, tn = a.last_results()
+        assert np.array_equal(res["n_cells"], nc) and np.array_equal(res["length"], ln) and np.array_equal(res["turns"], tn)
+        assert np.array_equal(tau, a.pheromone_matrix.ravel())
+        sa = a._read_state()
+        assert (st.best_len, st.best_turns, st.best_n_cells, st.best_ant) == (sa.best_len, sa.best_turns, sa.best_n_cells, sa.best_ant)
+        assert np.array_equal(best[:st.best_n_cells], a._best_cells[:sa.best_n_cells].cpu().numpy())
+    pa = a.solve_path_planning()
+    assert [r * 96 + c for r, c in pa[0]] == best[:st.best_n_cells].tolist()
