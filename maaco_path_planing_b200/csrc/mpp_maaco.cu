@@ -134,14 +134,16 @@ extern "C" int mpp_maaco_tables(const mpp_map_batch *maps, const mpp_maaco_param
 // ---------------------------------------------------------------------------------------------
 // sizes
 // ---------------------------------------------------------------------------------------------
-// Ranking buffer layout (uint32 words): [margin | 9*R*C strategy-1 words | margin | pad to even] [9*R*C full entries (2 words)].
+// Ranking buffer layout (uint32 words): [margin | 9*R*C strategy-1 words | margin | pad to even] [9*R*C full entries
+// (2 words)] [pad to 4] [R*C bundles of 4 words: word2 of the three cells P1's moves lead to, ready for one 16-byte load].
 // The margins let the tour kernel read the word of a neighbour cell without bounds checks.
-struct RankLayout { size_t margin, fast_words, total_words; };
+struct RankLayout { size_t margin, fast_words, bundle_words, total_words; };
 static RankLayout rank_layout(int R, int C) {
     RankLayout L;
     L.margin = (size_t)(C + 2) * 9;
     L.fast_words = ((size_t)9 * R * C + 2 * L.margin + 1) & ~(size_t)1;
-    L.total_words = L.fast_words + (size_t)18 * R * C;
+    L.bundle_words = (L.fast_words + (size_t)18 * R * C + 3) & ~(size_t)3;
+    L.total_words = L.bundle_words + (size_t)4 * R * C;
     return L;
 }
 static inline int tiles_r(int R) { return (R + 31) >> 5; }
@@ -180,7 +182,7 @@ extern "C" long long mpp_maaco_touched_words(int tile_rows, int cols, int n_ants
 struct TourArgs {
     const MppMapMeta *meta;      // [n_maps]
     const uint32_t *rank;        // [n_maps][rank_stride] ranking buffers (mpp_maaco_rank), layout: rank_layout()
-    size_t rank_stride, rank_margin, rank_fast_words;
+    size_t rank_stride, rank_margin, rank_fast_words, rank_bundle_words;
     int R, C;
     const double *tau, *E01;
     size_t tau_stride, E01_stride;
@@ -199,7 +201,9 @@ struct TourArgs {
 };
 
 #define MPP_SQRT2 1.4142135623730951  // sqrt(2.0) correctly rounded == math.sqrt(2)
+#ifndef MPP_TOUR1_THREADS
 #define MPP_TOUR1_THREADS 128
+#endif
 
 __device__ __noinline__ double pow_slow(double x, double y) { return pow(x, y); }
 
@@ -325,17 +329,39 @@ struct Tour1Move {          // one per move (order MAACO.py:98)
     int dcur;               // flat cell delta  dr*C + dc
     int dprow;              // byte delta of the window row pointer  dr*8
     int dc;                 // column delta
-    int pad;
+    int dphi;               // change of the start->target potential  dr*sgn(tr-sr) + dc*sgn(tc-sc)
 };
 #define T1_KTH_OFF 0                        // uint8  kth[256*8]   : index of the k-th set bit
 #define T1_SPREAD_OFF 2048                  // uint2  spread[256]  : byte m = 0xFF if bit m set
 #define T1_MOVE_OFF 4096                    // Tour1Move move[8]
 #define T1_DLEN_OFF (4096 + 128)            // double dlen[8]      : 1.0 or sqrt(2) (:293)
-#define T1_FAST_OFF (4096 + 256)            // uint4 fast[4*8]     : (k, subset) -> {dcur, dprow, dc, which | move << 8}
-#define T1_RNG_OFF (4096 + 256 + 512)       // per warp: double2 u[32] (512 B) + uint32 pack[32] (128 B)
-#define T1_WIN_OFF (T1_RNG_OFF + (MPP_TOUR1_THREADS / 32) * 640)
+#define T1_FAST_OFF (4096 + 256)            // uint4 fast[4]       : member of P1 -> {dcur, dprow, dc, move | dphi << 8}
+#define T1_FLEN_OFF (4096 + 256 + 64)       // double flen[4]      : step length of that member
+#define T1_RNG_OFF (4096 + 256 + 128)       // per warp: double2 u[32] (512 B) + uint32 pack[32] + uint32 pack2[32]
+#define T1_RNG_BYTES 768
+#define T1_WIN_OFF (T1_RNG_OFF + (MPP_TOUR1_THREADS / 32) * T1_RNG_BYTES)
 
-__global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(const TourArgs A, const int apw) {
+// Strategy-1 word, second form ("word2": what the tour's fast tiers work on; made from the ranking word by
+// tour_word2).  P1's three moves are "members" 0..2 (move order).  [0] 1 = the ranking does not apply here (some
+// attractiveness >= 1e-10); [3:1] A = members that are statically possible from this cell; [24:4] for every non-empty
+// candidate subset c (field c-1) what greedy selection keeps of it; [27:25] G = what it keeps of A.
+__device__ __forceinline__ uint32_t tour_word2(uint32_t w, int sm0, int sm1, int sm2) {
+    const uint32_t sv = w >> 24;
+    const uint32_t A3 = ((sv >> sm0) & 1u) | (((sv >> sm1) & 1u) << 1) | (((sv >> sm2) & 1u) << 2);
+    const uint32_t G = A3 ? ((w >> (3u * A3)) & 7u) : 0u;
+    return ((w & 7u) ? 1u : 0u) | (A3 << 1) | (((w >> 3) & 0x1FFFFFu) << 4) | (G << 25);
+}
+// the prefetch of the three possible next cells' word2 (one 16-byte line of the bundle table), pinned where it is issued
+__device__ __forceinline__ uint4 ldg128_pinned(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+#ifndef MPP_TOUR1_MINB
+#define MPP_TOUR1_MINB 4
+#endif
+__global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_tour1_kernel(const TourArgs A, const int apw) {
     extern __shared__ __align__(16) uint8_t t1_smem[];
     if (A.latch && *A.latch) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -343,7 +369,10 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
     const int map = blockIdx.y;
     const MppMapMeta &MM = A.meta[map];
     const MppS1 s1 = MM.s1;
+    const int target = MM.target;
+    const int tr = target / C, tc = target % C;
     {   // ---- tables ----
+        const int sgr = (tr > MM.start / C) - (tr < MM.start / C), sgc = (tc > MM.start % C) - (tc < MM.start % C);
         uint8_t *const kth = t1_smem + T1_KTH_OFF;
         uint2 *const spread = (uint2 *)(t1_smem + T1_SPREAD_OFF);
         for (int p = threadIdx.x; p < 256; p += MPP_TOUR1_THREADS) {
@@ -361,28 +390,28 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
             const int m = threadIdx.x;
             const int dr = (int)((0xA940u >> (2 * m)) & 3u) - 1, dc = (int)((0x9224u >> (2 * m)) & 3u) - 1;
             Tour1Move mv;
-            mv.dcur = dr * C + dc; mv.dprow = dr * 8; mv.dc = dc; mv.pad = 0;
+            mv.dcur = dr * C + dc; mv.dprow = dr * 8; mv.dc = dc; mv.dphi = dr * sgr + dc * sgc;
             ((Tour1Move *)(t1_smem + T1_MOVE_OFF))[m] = mv;
             ((double *)(t1_smem + T1_DLEN_OFF))[m] = (dr != 0 && dc != 0) ? MPP_SQRT2 : 1.0;
         }
-        if (threadIdx.x < 32) {                                    // (k, subset of P1's three moves) -> k-th member
-            const int k = threadIdx.x >> 3, p3 = threadIdx.x & 7;
-            const uint32_t P1t = s1.P1;
+        if (threadIdx.x < 4) {                                     // member of P1's three moves -> everything the move implies
+            const int k = threadIdx.x < 3 ? threadIdx.x : 2;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (__popc(P1t) == 3) {
-                const int s[3] = {__ffs(P1t) - 1, __ffs(P1t & (P1t - 1)) - 1, 31 - __clz(P1t)};
-                int seen = 0, which = 2;
-                for (int i = 0; i < 3; ++i)
-                    if ((p3 >> i) & 1) { if (seen == k) { which = i; break; } ++seen; }
-                const int mm = s[which];
+            double dl = 1.0;
+            if (s1.fast_ok) {
+                const int mm = s1.sm[k];
                 const int dr = (int)((0xA940u >> (2 * mm)) & 3u) - 1, dc = (int)((0x9224u >> (2 * mm)) & 3u) - 1;
-                v = make_uint4((uint32_t)(dr * C + dc), (uint32_t)(dr * 8), (uint32_t)dc, (uint32_t)which | ((uint32_t)mm << 8));
+                v = make_uint4((uint32_t)(dr * C + dc), (uint32_t)(dr * 8), (uint32_t)dc,
+                               (uint32_t)mm | ((uint32_t)(dr * sgr + dc * sgc) << 8));      // dphi = 1 or 2 for P1 moves
+                dl = (dr != 0 && dc != 0) ? MPP_SQRT2 : 1.0;
             }
             ((uint4 *)(t1_smem + T1_FAST_OFF))[threadIdx.x] = v;
+            ((double *)(t1_smem + T1_FLEN_OFF))[threadIdx.x] = dl;
         }
     }
-    double2 *const rngu = (double2 *)(t1_smem + T1_RNG_OFF + wib * 640);
-    uint32_t *const rngp = (uint32_t *)(t1_smem + T1_RNG_OFF + wib * 640 + 512);
+    double2 *const rngu = (double2 *)(t1_smem + T1_RNG_OFF + wib * T1_RNG_BYTES);
+    uint32_t *const rngp = (uint32_t *)(t1_smem + T1_RNG_OFF + wib * T1_RNG_BYTES + 512);
+    uint32_t *const rngq = (uint32_t *)(t1_smem + T1_RNG_OFF + wib * T1_RNG_BYTES + 640);
     uint2 *const win_w = (uint2 *)(t1_smem + T1_WIN_OFF) + (size_t)wib * apw * 64;   // the warp's windows: 64 rows x uint2 each
     for (int i = lane; i < apw * 64; i += 32) win_w[i] = make_uint2(0u, 0u);          // a tour starts with nothing visited
     __syncthreads();
@@ -391,7 +420,6 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
     if (a0 >= A.n_ants) return;                                    // whole warp
     const int a = a0 + lane;
     bool active = lane < apw && a < A.n_ants;
-    const int target = MM.target;
     int cur = MM.start;
     auto orient_mask = [](int dR, int dC) -> uint32_t {           // MAACO.py:146-157
         uint32_t k = 0xffu;
@@ -401,39 +429,45 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
         if (dR < 0) k &= ~0xE0u;
         return k;
     };
-    const int tr = target / C, tc = target % C;
     const uint32_t P1 = s1.P1;                                     // the same for every ant of a map
-    // the ranking entry of the next cell is fetched before the move is chosen: one load per strategy-1 move (the
-    // first three of P1; P1 has 3 moves unless start and target share a row or column)
-    const bool fast_ok = s1.fast_ok;
+    const bool fast_ok = s1.fast_ok;                               // P1 has 3 moves unless start and target share a row or column
     // (kept in registers: re-reading them inside the step costs a memory round trip each time)
 #define T1_KEEP(x) x = __shfl_sync(0xffffffffu, x, 0)   /* a value ptxas cannot re-derive from its source */
     int k_sm0 = s1.sm[0], k_sm1 = s1.sm[1], k_sm2 = s1.sm[2], k_dpr0 = s1.dpr[0], k_dpr1 = s1.dpr[1], k_dpr2 = s1.dpr[2];
-    int k_dc0 = s1.dc[0], k_dc1 = s1.dc[1], k_dc2 = s1.dc[2], k_so0 = s1.so[0], k_so1 = s1.so[1], k_so2 = s1.so[2];
+    int k_dc0 = s1.dc[0], k_dc1 = s1.dc[1], k_dc2 = s1.dc[2];
     T1_KEEP(k_sm0); T1_KEEP(k_sm1); T1_KEEP(k_sm2); T1_KEEP(k_dpr0); T1_KEEP(k_dpr1); T1_KEEP(k_dpr2);
-    T1_KEEP(k_dc0); T1_KEEP(k_dc1); T1_KEEP(k_dc2); T1_KEEP(k_so0); T1_KEEP(k_so1); T1_KEEP(k_so2);
+    T1_KEEP(k_dc0); T1_KEEP(k_dc1); T1_KEEP(k_dc2);
     TourSlabs V;
     V.slabs = A.slabs + (size_t)map * A.slab_stride;
     V.touched = A.touched + (size_t)map * A.touched_stride;
     V.n_ants = (size_t)A.n_ants; V.NW = (A.n_ants + 31) >> 5; V.TR = (R + 31) >> 5; V.TC = TC;
-    uint8_t *const moves_a = A.moves + ((size_t)map * A.n_ants + (active ? a : a0)) * A.max_cells;
+    uint8_t *mvp = A.moves + ((size_t)map * A.n_ants + (active ? a : a0)) * A.max_cells;   // next move-code slot
     const double *const tau_m = A.tau + (size_t)map * A.tau_stride;
     const double *const E01_m = A.E01 + (size_t)map * A.E01_stride;
     const uint32_t *__restrict__ rank_fast = A.rank + (size_t)map * A.rank_stride + A.rank_margin;
     const uint2 *const rank_slow = (const uint2 *)(A.rank + (size_t)map * A.rank_stride + A.rank_fast_words);
+    const uint4 *bundle = (const uint4 *)(A.rank + (size_t)map * A.rank_stride + A.rank_bundle_words);
     {
-        unsigned long long rf = (unsigned long long)rank_fast;
-        rf = __shfl_sync(0xffffffffu, rf, 0);
-        rank_fast = (const uint32_t *)rf;
+        unsigned long long bf = (unsigned long long)bundle;
+        bf = __shfl_sync(0xffffffffu, bf, 0);
+        bundle = (const uint4 *)bf;
     }
-    int k_target = target, k_max_cells = A.max_cells;
-    T1_KEEP(k_target); T1_KEEP(k_max_cells);
+    int k_target = target, k_max_cells = A.max_cells, k_max_path = 2 * R * C + 1;   // step cap 2*R*C (MAACO.py:283); R*C < 2^30
+    T1_KEEP(k_target); T1_KEEP(k_max_cells); T1_KEEP(k_max_path);
     const uint64_t seed = A.seeds[map];
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
-    int n_path = 1, prev_m = -1, turns = 0;
+    int n_path = 1, prev_m = -1, turns = -1;                       // (the first move is counted as a "turn": hence -1)
     double len = 0.0;
-    const int max_path = 2 * R * C + 1;                            // step cap 2*R*C (MAACO.py:283); R*C < 2^30
     bool failed = false;
+    // The start -> target potential phi = r*sgn(tr-sr) + c*sgn(tc-sc) grows with every move of P1, so while the ant
+    // stands on the largest phi it has ever reached (gap == 0) none of P1's target cells can have been visited:
+    // the tabu test (:93-95) of a strategy-1 step is then `gap == 0` instead of three window loads.
+    int gap = 0;                                                   // max phi reached - phi of the current cell
+#ifdef MPP_TOUR_STATS
+    int st_t1 = 0, st_t2 = 0, st_t3 = 0, st_slides = 0;
+    const long long st_c0 = clock64();
+    long long st_c1 = st_c0;
+#endif
     // window = tile rows {wr, wr+1} x tile cols {wc, wc+1} (64 x 64 cells); row lrow of it is the uint2 at prow,
     // bit lcol of that 64-bit row is the cell; the ant stays in [1, 62] x [1, 62]
     int wr, wc, lrow, lcol;
@@ -446,20 +480,18 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
     }
     uint32_t prow_s = (uint32_t)__cvta_generic_to_shared(win_w + (size_t)(lane < apw ? lane : 0) * 64 + lrow);   // the ant's window row
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(t1_smem);
-    uint32_t rngp_s = (uint32_t)__cvta_generic_to_shared(rngp) + 4u * (uint32_t)lane;
+    const uint32_t rngp_s = (uint32_t)__cvta_generic_to_shared(rngp) + 4u * (uint32_t)lane;
+    const uint32_t rngq_s = (uint32_t)__cvta_generic_to_shared(rngq) + 4u * (uint32_t)lane;
     uint32_t sbase_k = sbase;                                    // (opaque copy: otherwise re-derived from %cluster_ctaid every use)
     sbase_k = __shfl_sync(0xffffffffu, sbase_k, 0);
-    uint32_t fw = 0u;                                             // strategy-1 word of (cell, previous move)
-    uint32_t pf0 = 0u, pf1 = 0u, pf2 = 0u;                        // ... of the three strategy-1 neighbours, prefetched
+    uint32_t fw2 = 1u;                                            // word2 of (cell, previous move); 1 = "no fast tier here"
+    uint4 bq = make_uint4(1u, 1u, 1u, 1u);                        // word2 of the three strategy-1 neighbours, prefetched
     if (active) {
         asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(prow_s + 4u * ((uint32_t)lcol >> 5)), "r"(1u << (lcol & 31)) : "memory");
-        fw = rank_fast[(size_t)cur * 9];                          // context 0: no previous move
-        // (read it here: a first use inside the loop would make every step wait on this load's scoreboard, which the
-        // loop's own prefetches share.)  Field 0 is 0 or 7, so the test is never true.
-        if (cur == target || (fw & 7u) == 3u) active = false;
+        if (cur == target) active = false;
         if (fast_ok) {
-            const uint32_t *const rk = rank_fast + (size_t)cur * 9;
-            pf0 = ldg32_pinned(rk + k_so0); pf1 = ldg32_pinned(rk + k_so1); pf2 = ldg32_pinned(rk + k_so2);
+            fw2 = tour_word2(rank_fast[(size_t)cur * 9], k_sm0, k_sm1, k_sm2);   // context 0: no previous move
+            bq = ldg128_pinned(bundle + cur);
         }
     }
     __syncwarp();
@@ -468,29 +500,40 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
     // then be U cells from where the checks saw it, so the window keeps a margin of U cells instead of one
     const int U = (apw <= 16) ? 2 : 1;                             // a refill covers 32 / apw steps: must be a multiple of U
     const unsigned edge_lo = (unsigned)U, edge_span = 63u - 2u * (unsigned)U;
+    const uint32_t slot_bytes = 4u * (uint32_t)apw;
     for (uint32_t step = 0;; step += (uint32_t)U) {
         const uint32_t need0 = __ballot_sync(0xffffffffu, active && ((unsigned)lrow - edge_lo > edge_span || (unsigned)lcol - edge_lo > edge_span));
         if (!__any_sync(0xffffffffu, active)) break;
         if ((step & gmask) == 0 || need0) {
             if ((step & gmask) == 0) {
                 // uniforms: draws 2s (q-test) and 2s+1 (selection) of stream (seed, TOUR, it, ant) = Philox block s;
-                // lane L makes the block of ant L % apw for step + L / apw.  Besides u0/u1 (for the full rule) the
-                // pass leaves what the ranking path needs: the greedy flag u0 <= q0 (:240) and floor(u1 * n) for
-                // every pool size n = 1..8 (random.choice on n items).
+                // lane L makes the block of ant L % apw for step + L / apw.  Besides u0/u1 (for the literal rules) the
+                // pass leaves what the ranked tiers need: the greedy flag u0 <= q0 (:240), floor(u1 * n) for every
+                // pool size n = 1..8 (random.choice on n items: `pack`), and for every subset of P1's three members
+                // the member random.choice picks from it (`pack2`, two bits per subset; bit 16 = greedy flag).
                 const int la = lane & (apw - 1);
                 const mpp_u4 rb = mpp_philox(step + (uint32_t)(lane / apw), (uint32_t)(A.ant_offset + a0 + la), A.it,
                                              MPP_CLS_MAACO_TOUR, key0, key1);
                 const double u0 = mpp_u53(rb.x, rb.y), u1 = mpp_u53(rb.z, rb.w);
-                uint32_t pack = (u0 <= A.q0) ? (1u << 24) : 0u;
+                const bool greedy = u0 <= A.q0;
+                uint32_t pack = greedy ? (1u << 24) : 0u;
 #pragma unroll
                 for (int n = 2; n <= 8; ++n) {
                     int k = (int)(u1 * (double)n);
                     k = k < n ? k : n - 1;
                     pack |= (uint32_t)k << (3 * (n - 1));
                 }
+                const uint32_t k2 = (pack >> 3) & 7u, k3 = (pack >> 6) & 7u;     // floor(u1*2), floor(u1*3)
+                // subsets 1,2,4: the only member; 3 = {0,1}, 5 = {0,2}, 6 = {1,2}: k2-th; 7: k3-th
+                uint32_t pack2 = (greedy ? (1u << 16) : 0u) | (0u << 2) | (1u << 4) | (2u << 8);
+                pack2 |= (k2 ? 1u : 0u) << 6;
+                pack2 |= (k2 ? 2u : 0u) << 10;
+                pack2 |= (k2 ? 2u : 1u) << 12;
+                pack2 |= k3 << 14;
                 __syncwarp();
                 rngu[lane] = make_double2(u0, u1);
                 rngp[lane] = pack;
+                rngq[lane] = pack2;
                 __syncwarp();
             }
             // ---- slide the windows whose ant reached their edge (at most every 31 steps per ant) ----
@@ -526,6 +569,9 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
                     w_s[lane] = left ? make_uint2(x0, o0.x) : make_uint2(o0.y, x0);
                     w_s[lane + 32] = left ? make_uint2(x1, o1.x) : make_uint2(o1.y, x1);
                 }
+#ifdef MPP_TOUR_STATS
+                if (lane == src) ++st_slides;
+#endif
                 if (lane == src) {
                     wr += d_wr; wc += d_wc;
                     lrow -= d_wr << 5; lcol -= d_wc << 5;
@@ -537,36 +583,57 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
                 need = (need & (need - 1)) | __ballot_sync(0xffffffffu, again);
             }
         }
-        for (uint32_t su = step; su < step + (uint32_t)U; ++su)
+        uint32_t slot = (step & gmask) * slot_bytes;               // byte offset of this step's slot in the warp's rng arrays
+        for (int su = 0; su < U; ++su, slot += slot_bytes)
         if (active) {
-            int m = -1, dcur = 0, dpr = 0, dcc = 0;                   // the move taken this step and its deltas
-            uint32_t pi = 0u;                                         // which prefetched word applies next step
-            const uint32_t pack = lds_u32(rngp_s + 4u * ((su & gmask) * (uint32_t)apw));
-            if (fast_ok) {
-                // ---- strategy 1 (:165) on the three moves of P1 only ----
-                const uint2 ra = lds_u2(prow_s + k_dpr0), rb = lds_u2(prow_s + k_dpr1), rc = lds_u2(prow_s + k_dpr2);
-                const int c0 = lcol + k_dc0, c1 = lcol + k_dc1, c2 = lcol + k_dc2;           // 0..63
-                const uint32_t v0 = ((c0 & 32) ? ra.y : ra.x) >> (c0 & 31);            // tabu bit (:93-95) in bit 0
-                const uint32_t v1 = ((c1 & 32) ? rb.y : rb.x) >> (c1 & 31);
-                const uint32_t v2 = ((c2 & 32) ? rc.y : rc.x) >> (c2 & 31);
-                const uint32_t sv = fw >> 24;                                          // static mask (:93-120)
-                const uint32_t c3 = (((sv >> k_sm0) & ~v0) & 1u) | ((((sv >> k_sm1) & ~v1) & 1u) << 1) |
-                                    ((((sv >> k_sm2) & ~v2) & 1u) << 2);                 // candidate subset of {k_sm0, k_sm1, k_sm2}
-                if (c3 != 0u && (fw & 7u) == 0u) {
-                    // greedy (:241-250): field c3 of the word = first arg-max + every later candidate, precomputed;
-                    // roulette (:251-254): all candidates.  Then random.choice: the floor(u1*n)-th member.
-                    const uint32_t p3 = (pack & (1u << 24)) ? ((fw >> (3u * c3)) & 7u) : c3;
-                    const uint32_t sh = (0x63303000u >> (4u * p3)) & 15u;              // 3 * (popc(p3) - 1)
-                    const uint32_t k = (pack >> sh) & 7u;
-                    // k-th member of subset p3 and everything that follows from the move: one table row
-                    const uint4 fv = lds_u4(sbase_k + T1_FAST_OFF + 16u * ((k << 3) | p3));
+            int m = -1, dcur = 0, dpr = 0, dcc = 0, dphi = 0;         // the move taken this step and what it implies
+            double dl = 0.0;
+            // ---- tiers 1 and 2: strategy 1 (:165) on the three moves of P1, from the prefetched word2 ----
+            if (!(fw2 & 1u)) {
+                const uint32_t p2 = lds_u32(rngq_s + slot);
+                const uint32_t A3 = (fw2 >> 1) & 7u;                              // static candidates among P1's members
+                uint32_t pool;
+#ifdef MPP_TOUR_STATS
+                if (gap == 0) ++st_t1; else ++st_t2;
+#endif
+                if (gap == 0) {
+                    // tier 1: nothing ahead can be tabu.  greedy (:241-250) keeps G of A; roulette (:251-254) all of A
+                    pool = (p2 & 0x10000u) ? ((fw2 >> 25) & 7u) : A3;
+                } else {
+                    // tier 2: tabu bits (:93-95) of the three target cells from the window
+                    const uint2 ra = lds_u2(prow_s + k_dpr0), rb = lds_u2(prow_s + k_dpr1), rc = lds_u2(prow_s + k_dpr2);
+                    const int c0 = lcol + k_dc0, c1 = lcol + k_dc1, c2 = lcol + k_dc2;           // 0..63
+                    const uint32_t v0 = ((c0 & 32) ? ra.y : ra.x) >> (c0 & 31);
+                    const uint32_t v1 = ((c1 & 32) ? rb.y : rb.x) >> (c1 & 31);
+                    const uint32_t v2 = ((c2 & 32) ? rc.y : rc.x) >> (c2 & 31);
+                    const uint32_t c3 = A3 & ~((v0 & 1u) | ((v1 & 1u) << 1) | ((v2 & 1u) << 2));
+                    pool = (p2 & 0x10000u) ? ((fw2 >> (1u + 3u * c3)) & 7u) : c3;   // (c3 == 0: field -1 -> bits of A, masked below)
+                    if (c3 == 0u) pool = 0u;
+                }
+                if (pool != 0u) {
+                    // random.choice (:250 / :254): the member chosen from `pool`, and everything the move implies
+                    const uint32_t mem = (p2 >> (2u * pool)) & 3u;
+                    const uint4 fv = lds_u4(sbase_k + T1_FAST_OFF + 16u * mem);
+                    dl = lds_f64(sbase_k + T1_FLEN_OFF + 8u * mem);
                     dcur = (int)fv.x; dpr = (int)fv.y; dcc = (int)fv.z;
-                    pi = fv.w & 3u;
-                    m = (int)(fv.w >> 8);
+                    m = (int)(fv.w & 0xFFu);
+                    dphi = (int)(fv.w >> 8);
+                    // word2 of the cell moved to: one of the three prefetched (bitwise select, opaque to the compiler:
+                    // as a ternary the default operand is copied early and that copy waits for the prefetch too soon)
+                    const uint32_t m1 = 0u - (mem & 1u), m2 = 0u - (mem >> 1);
+                    uint32_t t;
+                    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(t) : "r"(bq.x), "r"(bq.y), "r"(m1));
+                    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(fw2) : "r"(t), "r"(bq.z), "r"(m2));
                 }
             }
+#ifdef MPP_TOUR_STATS
+            if (m < 0) { ++st_t3; if (!(fw2 & 1u)) { if (gap == 0) --st_t1; else --st_t2; } }
+#endif
             if (m < 0) {
-                // ---- general step: all eight moves, strategies 1-3, full ranking entry or the literal rules ----
+                // ---- tier 3: all eight moves, strategies 1-3, full ranking entry or the literal rules ----
+                const uint32_t ctx = (n_path >= 2) ? (uint32_t)(prev_m + 1) : 0u;
+                const uint32_t fw = rank_fast[(size_t)cur * 9 + ctx];  // ranking word of (cell, previous move)
+                const uint32_t pack = lds_u32(rngp_s + slot);
                 const uint2 q0r = lds_u2(prow_s - 8u), q1r = lds_u2(prow_s), q2r = lds_u2(prow_s + 8u);
                 const int rot = lcol - 1;                             // 0..61
                 const bool sw = rot & 32;
@@ -587,14 +654,14 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
                     if ((cand & (cand - 1u)) == 0u) {
                         m = __ffs(cand) - 1;                          // one candidate: every rule picks it
                     } else if ((fw & 7u) != 0u) {                     // some attractiveness >= 1e-10: literal rules
-                        const double2 uu = rngu[(su & gmask) * apw + lane];
+                        const double2 uu = rngu[(slot >> 2) + lane];
                         m = tour_select_slow(cand, cur / C, cur % C, C, n_path >= 2, prev_m, tau_m, E01_m, A.alpha, A.q0, uu.x, uu.y);
                     } else {
                         uint32_t pool = cand;                         // roulette over tiny values: uniform (:253-254)
                         if (pack & (1u << 24)) {
                             // greedy: first arg-max = best-ranked candidate (full entry: permute the candidate flags
                             // into rank order, take the first) and every later candidate
-                            const uint2 rws = rank_slow[(size_t)cur * 9 + (n_path >= 2 ? prev_m + 1 : 0)];
+                            const uint2 rws = rank_slow[(size_t)cur * 9 + ctx];
                             const uint2 sp = lds_u2(sbase_k + T1_SPREAD_OFF + 8u * cand);
                             const uint32_t f0 = __byte_perm(sp.x, sp.y, rws.x & 0xFFFFu), f1 = __byte_perm(sp.x, sp.y, rws.x >> 16);
                             const uint32_t ff = f0 ? f0 : f1;
@@ -607,39 +674,31 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
                         m = (int)lds_u8(sbase_k + T1_KTH_OFF + pool * 8u + (uint32_t)k);
                     }
                     const uint4 mvv = lds_u4(sbase_k + T1_MOVE_OFF + 16u * (uint32_t)m);
-                    dcur = (int)mvv.x; dpr = (int)mvv.y; dcc = (int)mvv.z;
-                    // (loaded into a prefetch register, never straight into fw: see the note at the first load)
-                    pf0 = ldg32_pinned(rank_fast + (size_t)(cur + dcur) * 9 + (m + 1));
-                    pi = 0u;
+                    dcur = (int)mvv.x; dpr = (int)mvv.y; dcc = (int)mvv.z; dphi = (int)mvv.w;
+                    dl = lds_f64(sbase_k + T1_DLEN_OFF + 8u * (uint32_t)m);
+                    if (fast_ok) fw2 = tour_word2(rank_fast[(size_t)(cur + dcur) * 9 + (m + 1)], k_sm0, k_sm1, k_sm2);
                 }
             }
             if (active) {
                 // ---- advance :293-297 ----
                 cur += dcur;
-                // bitwise select on `pi`, opaque to the compiler: as a ternary the default operand is copied early,
-                // and that copy waits for the prefetches a whole selection too soon
-                {
-                    const uint32_t m1 = 0u - (pi & 1u), m2 = 0u - (pi >> 1);
-                    uint32_t t;
-                    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(t) : "r"(pf0), "r"(pf1), "r"(m1));
-                    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(fw) : "r"(t), "r"(pf2), "r"(m2));
-                }
-                if (fast_ok) {
-                    // the word of each strategy-1 neighbour of the NEW cell, for the end of the next step (the table has
-                    // margins: every index is readable); a whole step of work hides the L2 latency
-                    const uint32_t *const rk = rank_fast + (size_t)cur * 9;
-                    pf0 = ldg32_pinned(rk + k_so0); pf1 = ldg32_pinned(rk + k_so1); pf2 = ldg32_pinned(rk + k_so2);
-                }
+                if (fast_ok) bq = ldg128_pinned(bundle + cur);        // the three possible next cells' word2: a step ahead
+                gap -= dphi;
+                gap = gap > 0 ? gap : 0;
                 prow_s += (uint32_t)dpr;
                 lrow += dpr >> 3;
                 lcol += dcc;
                 asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(prow_s + 4u * ((uint32_t)lcol >> 5)), "r"(1u << (lcol & 31)) : "memory");
-                if (n_path <= k_max_cells) moves_a[n_path - 1] = (uint8_t)m;   // move code of step n_path-1
-                len += lds_f64(sbase_k + T1_DLEN_OFF + 8u * (uint32_t)m);
-                if (n_path >= 2 && m != prev_m) ++turns;              // :264-276 counted on the fly
+                if (n_path <= k_max_cells) *mvp = (uint8_t)m;         // move code of step n_path-1
+                ++mvp;
+                len += dl;                                            // :293 (1.0 or sqrt(2), plain += in path order)
+                if (m != prev_m) ++turns;                             // :264-276 counted on the fly
                 prev_m = m;
                 ++n_path;
-                if (cur == k_target || n_path >= max_path) active = false;
+                if (cur == k_target || n_path >= k_max_path) active = false;
+#ifdef MPP_TOUR_STATS
+                st_c1 = clock64();
+#endif
             }
         }
     }
@@ -657,9 +716,14 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, 4) mpp_maaco_tour1_kernel(c
         mpp_ant_result res;
         res.length = ok ? len : __longlong_as_double(0x7ff0000000000000ll);
         res.n_cells = ok ? n_path : 0;
-        res.turns = ok ? turns : -1;
+        res.turns = ok ? (turns > 0 ? turns : 0) : -1;
         A.result[(size_t)map * A.result_stride + A.ant_offset + a] = res;
         if (A.steps) atomicAdd(A.steps, (unsigned long long)(n_path - 1));
+#ifdef MPP_TOUR_STATS
+        int *st = (int *)(A.moves + ((size_t)map * A.n_ants + a + 1) * A.max_cells - 32);
+        st[0] = st_t1; st[1] = st_t2; st[2] = st_t3; st[3] = st_slides; st[4] = (int)(st_c1 - st_c0); st[5] = n_path - 1;
+        st[6] = ok ? 1 : 0;
+#endif
     }
 }
 
@@ -684,6 +748,7 @@ extern "C" int mpp_maaco_tours(const mpp_map_batch *maps, const mpp_colony *c, i
     TourArgs A;
     A.meta = maps->meta_dev;
     A.rank = c->rank; A.rank_stride = L.total_words; A.rank_margin = L.margin; A.rank_fast_words = L.fast_words;
+    A.rank_bundle_words = L.bundle_words;
     A.R = maps->rows; A.C = maps->cols;
     A.tau = c->tau; A.tau_stride = (size_t)c->tau_stride; A.E01 = c->E01; A.E01_stride = (size_t)c->E01_stride;
     A.it = (uint32_t)iteration; A.q0 = q0; A.alpha = alpha;
@@ -742,7 +807,7 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
                                                              double alpha, int R, int C,
                                                              const MppMapMeta *__restrict__ meta, uint32_t *__restrict__ rank_all,
                                                              size_t rank_stride, size_t rank_margin, size_t rank_fast_words,
-                                                             const int32_t *__restrict__ latch) {
+                                                             size_t rank_bundle_words, const int32_t *__restrict__ latch) {
     // one thread per cell: the eight neighbours' tau / eta' are read once and serve all nine contexts
     const int cell = blockIdx.x * 128 + threadIdx.x;
     if (cell >= R * C) return;
@@ -753,6 +818,7 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
     const double *E01 = E01_all + (size_t)map * E01_stride;
     uint32_t *rank_fast = rank_all + (size_t)map * rank_stride + rank_margin;
     uint2 *rank_slow = (uint2 *)(rank_all + (size_t)map * rank_stride + rank_fast_words);
+    uint32_t *bundle = rank_all + (size_t)map * rank_stride + rank_bundle_words;
     const uint32_t P1 = meta[map].s1.P1;
     const uint32_t sv = svalid[cell];
     double a0[8], a1[8];                                          // attractiveness without / with the turn factor (:238)
@@ -806,6 +872,16 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
         const size_t t = (size_t)cell * 9 + ctx;
         rank_fast[t] = fast | (sv << 24);
         rank_slow[t] = make_uint2(perm, word | (sv << 24));
+        if (p1_three) {
+            // the cell this one is entered from by P1's member k (context = that move): its bundle gets this word
+            const int k = (ctx == s0 + 1) ? 0 : ((ctx == s1 + 1) ? 1 : ((ctx == s2 + 1) ? 2 : -1));
+            if (k >= 0) {
+                const int mv = ctx - 1;
+                const int pr = cell / C - ((int)((0xA940u >> (2 * mv)) & 3u) - 1), pc = cell % C - ((int)((0x9224u >> (2 * mv)) & 3u) - 1);
+                if (pr >= 0 && pr < R && pc >= 0 && pc < C)
+                    bundle[((size_t)pr * C + pc) * 4 + k] = tour_word2(fast | (sv << 24), s0, s1, s2);
+            }
+        }
     }
 }
 
@@ -817,7 +893,7 @@ extern "C" int mpp_maaco_rank(const mpp_map_batch *maps, const mpp_colony *c, do
     const RankLayout L = rank_layout(maps->rows, maps->cols);
     mpp_maaco_rank_kernel<<<dim3((total + 127) / 128, maps->n_maps), 128, 0, (cudaStream_t)stream>>>(
         maps->svalid_dev, c->tau, (size_t)c->tau_stride, c->E01, (size_t)c->E01_stride, alpha, maps->rows, maps->cols,
-        maps->meta_dev, c->rank, L.total_words, L.margin, L.fast_words, c->latch);
+        maps->meta_dev, c->rank, L.total_words, L.margin, L.fast_words, L.bundle_words, c->latch);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
