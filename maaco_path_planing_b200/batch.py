@@ -34,18 +34,19 @@ class MAACOBatch:
     Same parameters as MAACO (MAACO.py:11-14); `seeds` = one Philox seed per map."""
 
     def __init__(self, grids, num_ants, num_iterations, alpha, beta, rho, Q, a_turn_coef, wh_max, wh_min, k_h_adaptive,
-                 q0_initial, C0_initial_pheromone=0.1, *, seeds=None, device=None, max_cells=None, ants_per_warp=0):
+                 q0_initial, C0_initial_pheromone=0.1, *, seeds=None, device=None, max_cells=None, ants_per_warp=0,
+                 reuse=None):
         import torch
         L = _lib.lib()
         g = np.ascontiguousarray(np.asarray(grids, dtype=int))
         if g.ndim != 3:
             raise ValueError("grids must be [n_maps, rows, cols]")
         self.n_maps, self.rows, self.cols = g.shape
-        for k in range(self.n_maps):
-            if not (g[k] == START_NODE_VAL).any():
-                raise ValueError("MAACO: Start node not found.")              # MAACO.py:35-36
-            if not (g[k] == TARGET_NODE_VAL).any():
-                raise ValueError("MAACO: Target node not found.")             # MAACO.py:37-38
+        flat = g.reshape(self.n_maps, -1)
+        if not (flat == START_NODE_VAL).any(axis=1).all():
+            raise ValueError("MAACO: Start node not found.")                  # MAACO.py:35-36
+        if not (flat == TARGET_NODE_VAL).any(axis=1).all():
+            raise ValueError("MAACO: Target node not found.")                 # MAACO.py:37-38
         _lib.require_device()
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
@@ -70,23 +71,33 @@ class MAACOBatch:
         self.seeds = [int(s) & (2 ** 64 - 1) for s in seeds]
         dev = self.device
         f64, i32, i64, u8 = torch.float64, torch.int32, torch.int64, torch.uint8
-        self._tau = torch.zeros((M, n), dtype=f64, device=dev)
-        self._E01 = torch.empty(2 * n, dtype=f64, device=dev)                 # shared by the whole wave
-        self._dist_t = torch.empty(n, dtype=f64, device=dev)
+        K = max(1, self.num_iterations)
+        key = (M, R, Cc, N, self.max_cells, K, self.device_index)
+        if reuse is not None and getattr(reuse, "_key", None) == key:
+            # the previous wave's device buffers (same shapes): nothing to allocate, only `touched` / counters to clear
+            for name in ("_tau", "_E01", "_dist_t", "_rank", "_slabs", "_touched", "_moves", "_result", "_deposit", "_okbits",
+                         "_best_cells", "_steps", "_log"):
+                setattr(self, name, getattr(reuse, name))
+            self._touched.zero_()
+            self._steps.zero_()
+        else:
+            self._tau = torch.empty((M, n), dtype=f64, device=dev)
+            self._E01 = torch.empty(2 * n, dtype=f64, device=dev)             # shared by the whole wave
+            self._dist_t = torch.empty(n, dtype=f64, device=dev)
+            self._rank = torch.empty(M * L.mpp_maaco_rank_words(R, Cc), dtype=i32, device=dev)
+            self._slabs = torch.empty(M * L.mpp_maaco_slab_words(TR, Cc, N), dtype=i32, device=dev)
+            self._touched = torch.zeros(M * L.mpp_maaco_touched_words(TR, Cc, N), dtype=i32, device=dev)
+            self._moves = torch.empty(M * N * self.max_cells, dtype=u8, device=dev)
+            self._result = torch.zeros((M, N, 2), dtype=i64, device=dev)
+            self._deposit = torch.zeros((M, N), dtype=f64, device=dev)
+            self._okbits = torch.zeros((M, (N + 31) // 32), dtype=i32, device=dev)
+            self._best_cells = torch.zeros((M, self.max_cells + 1), dtype=i32, device=dev)
+            self._steps = torch.zeros(1, dtype=i64, device=dev)
+            self._log = torch.zeros((M, K, 4), dtype=f64, device=dev)
+        self._key = key
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(L.mpp_maaco_tables(self._maps, C.byref(self._params), _lib.ptr(self._tau), n, _lib.ptr(self._E01),
                                       _lib.ptr(self._dist_t), stream), "mpp_maaco_tables")
-        self._rank = torch.empty(M * L.mpp_maaco_rank_words(R, Cc), dtype=i32, device=dev)
-        self._slabs = torch.empty(M * L.mpp_maaco_slab_words(TR, Cc, N), dtype=i32, device=dev)
-        self._touched = torch.zeros(M * L.mpp_maaco_touched_words(TR, Cc, N), dtype=i32, device=dev)
-        self._moves = torch.zeros(M * N * self.max_cells, dtype=u8, device=dev)
-        self._result = torch.zeros((M, N, 2), dtype=i64, device=dev)
-        self._deposit = torch.zeros((M, N), dtype=f64, device=dev)
-        self._okbits = torch.zeros((M, (N + 31) // 32), dtype=i32, device=dev)
-        self._best_cells = torch.zeros((M, self.max_cells + 1), dtype=i32, device=dev)
-        self._steps = torch.zeros(1, dtype=i64, device=dev)
-        K = max(1, self.num_iterations)
-        self._log = torch.zeros((M, K, 4), dtype=f64, device=dev)
         self._seeds = torch.from_numpy(np.array(self.seeds, np.uint64).view(np.int64)).to(dev)
         st = bytes(_lib.MaacoState(INF, -1, 0, 0, -1, INF, -1, -1))
         self._state = torch.frombuffer(bytearray(st * M), dtype=u8).to(dev)
@@ -180,13 +191,15 @@ def solve_maaco_batch(grids, num_ants, num_iterations, params, seeds=None, wave=
     are identical to solving each map alone (same seeds => same Philox streams)."""
     lo, hi = shard_maps(len(grids), group)
     out = []
+    prev = None
     for idx in _waves(grids, lo, hi, wave):
         b = MAACOBatch(np.stack([np.asarray(grids[i]) for i in idx]), num_ants, num_iterations,
                        seeds=None if seeds is None else [seeds[i] for i in idx], device=device, max_cells=max_cells,
-                       **params)
+                       reuse=prev, **params)
         for i, (path, length, turns, curve) in zip(idx, b.solve()):
             out.append((i, path, length, turns, curve))
         b.close()
+        prev = b
     out.sort(key=lambda r: r[0])
     return out
 

@@ -63,11 +63,14 @@ def blocks_map(n, frac=0.20, seed=0, rows=None, cols=None):
     rng = np.random.default_rng(seed)
     g = np.zeros((rows, cols), dtype=np.int64)
     m = max(2, min(rows, cols) // 12)
-    while g.mean() < frac:
+    filled, size = 0, rows * cols                     # (running count: the same decisions as `while g.mean() < frac`)
+    while filled / size < frac:
         h, w = rng.integers(1, m, 2)
         r = rng.integers(0, rows - h)
         c = rng.integers(0, cols - w)
-        g[r:r + h, c:c + w] = 1
+        blk = g[r:r + h, c:c + w]
+        filled += blk.size - int(blk.sum())
+        blk[...] = 1
     g[:2, :2] = 0
     g[-2:, -2:] = 0
     g[0, 0] = START_NODE_VAL
