@@ -323,6 +323,42 @@ int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_predators, i
                       uint32_t *avoid_dev, void *scratch_dev, size_t scratch_bytes, int n_slots, int heap_cap,
                       int32_t *status_dev, unsigned long long *counters_dev, void *stream);
 
+/* MPA over a batch of independent same-shape maps (BASELINE config 5), one launch per iteration for every map.
+ * Population buffers are [n_maps][n_predators][...] (cells: max_cells int32 per predator; stats: 5 doubles).
+ * mpp_mpa_init_batch: MPA._initialize_population_with_safety (MPA.py:231-245) -- ONE private-A* search start -> target
+ *   per map (the reference runs N identical ones); writes row 0 of every map (path, n_cells, stats); the caller
+ *   replicates it.  scratch: 256 + n_maps * slot bytes (mpp_astar_scratch_bytes of a same-shape map with n_maps slots).
+ * mpp_mpa_iteration_batch: mpp_mpa_iteration for every map at once.  order_dev [n_maps][n_predators] = stable argsort of
+ *   the old population's fitness column (the sorts of MPA.py:333,412 as an index, no path is moved): predator i reads row
+ *   order[i], the elite is row order[0]; results go to row i of the out buffers.  seeds_dev: one Philox seed per map;
+ *   queue_dev: n_maps uint32 scratch; scratch: 256 + n_maps * warps_per_map slots. */
+int mpp_mpa_init_batch(const mpp_map_batch *maps, const mpp_policy *policy, int n_predators, int max_cells,
+                       int32_t *cells_dev, int32_t *n_cells_dev, double *stats_dev, void *scratch_dev,
+                       size_t scratch_bytes, int heap_cap, int32_t *status_dev, unsigned long long *counters_dev,
+                       void *stream);
+int mpp_mpa_iteration_batch(const mpp_map_batch *maps, const mpp_policy *policy, int n_predators, int iteration, int phase,
+                            double P_const, double CF, double FADs_rate, double levy_sigma, double levy_beta,
+                            const uint64_t *seeds_dev, const int32_t *order_dev, const int32_t *cells_dev,
+                            const int32_t *n_cells_dev, const double *stats_dev, int max_cells, int32_t *out_cells_dev,
+                            int32_t *out_n_dev, double *out_stats_dev, int32_t *tmp_cells_dev, uint32_t *avoid_dev,
+                            void *scratch_dev, size_t scratch_bytes, int warps_per_map, int heap_cap, uint32_t *queue_dev,
+                            int32_t *status_dev, unsigned long long *counters_dev, void *stream);
+/* bytes of one search slot's scratch for a rows x cols map (the per-slot term of mpp_astar_scratch_bytes) */
+size_t mpp_astar_slot_bytes(int rows, int cols, int heap_cap);
+
+/* replaces the attempt generation of PSOSolver._initialize_particles (pso.py:97-105: W uniform waypoints + W x 2
+ * uniform velocities per attempt) for attempts [attempt_offset, attempt_offset + n_attempts): pos_dev / vel_dev are
+ * n_attempts x W x 2 doubles, waypoint_cells_dev the rounded, clamped cells (pso.py:61,69-70).  Stream (seed, PSO_INIT, 0,
+ * attempt).  The accept / pad bookkeeping (pso.py:107-160) stays with the caller. */
+int mpp_pso_init(const mpp_map *map, int n_attempts, int attempt_offset, int n_waypoints, double max_vel, uint64_t seed,
+                 double *pos_dev, double *vel_dev, int32_t *waypoint_cells_dev, void *stream);
+
+/* replaces GASolver._create_chromosome (ga_solver.py:48-56: integer genes redrawn until the cell is free) for attempts
+ * [attempt_offset, attempt_offset + n_attempts) of _initialize_population (:95-104).  chrom_dev: n_attempts x W cells.
+ * Stream (seed, GA_INIT, 0, attempt). */
+int mpp_ga_init(const mpp_map *map, int n_attempts, int attempt_offset, int n_waypoints, uint64_t seed, int32_t *chrom_dev,
+                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

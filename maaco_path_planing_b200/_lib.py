@@ -97,6 +97,15 @@ _SIGS = {
     "mpp_ga_select": (c_int, [c_void_p, c_int, c_int, c_u64, c_int, c_void_p, c_void_p]),
     "mpp_ga_breed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_u64, c_int, c_void_p,
                              c_void_p]),
+    "mpp_astar_slot_bytes": (C.c_size_t, [c_int, c_int, c_int]),
+    "mpp_mpa_init_batch": (c_int, [c_void_p, C.POINTER(Policy), c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   C.c_size_t, c_int, c_void_p, c_void_p, c_void_p]),
+    "mpp_mpa_iteration_batch": (c_int, [c_void_p, C.POINTER(Policy), c_int, c_int, c_int, c_double, c_double, c_double,
+                                        c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_size_t, c_int,
+                                        c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mpp_pso_init": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mpp_ga_init": (c_int, [c_void_p, c_int, c_int, c_int, c_u64, c_void_p, c_void_p]),
     "mpp_mpa_iteration": (c_int, [c_void_p, C.POINTER(Policy), c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
                                   c_double, c_double, c_u64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, C.c_size_t, c_int, c_int, c_void_p, c_void_p,

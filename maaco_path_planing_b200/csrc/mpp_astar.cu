@@ -115,6 +115,11 @@ extern "C" size_t mpp_astar_scratch_bytes(const mpp_map *map, int n_slots, int h
     return 256 + (size_t)n_slots * astar_slot_bytes(map->rows * map->cols, heap_cap);
 }
 
+extern "C" size_t mpp_astar_slot_bytes(int rows, int cols, int heap_cap) {
+    if (rows <= 0 || cols <= 0 || heap_cap <= 0) return 0;
+    return astar_slot_bytes(rows * cols, heap_cap);
+}
+
 extern "C" int mpp_astar_max_slots(const mpp_map *map) { return map ? map->sm_count * 3 * MPP_AS_WARPS : 0; }
 
 struct BatchArgs {

@@ -36,6 +36,12 @@ struct MpaArgs {
     int n_slots, heap_cap;
     int32_t *status;                  // [0] = worst status seen (0 ok, 1 = heap overflow, 2 = path truncated)
     unsigned long long *counters;
+    // ---- batches of independent same-shape maps (blockIdx.y = map; a single map is a batch of one) ----
+    const MppMapMeta *meta;           // per-map start / target (null: A.start / A.target)
+    const uint64_t *seeds;            // per-map Philox seed (null: k0 / k1)
+    const int32_t *order;             // [n_maps][N]: predator i of the (sorted) population is row order[i] (null: identity)
+    unsigned int *queue;              // [n_maps] work counters
+    int warps_per_map;                // search slots serving one map
 };
 
 // CPython random.normalvariate (Kinderman-Monahan) over the stream
@@ -117,31 +123,46 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
     AStarGrid G = A.G;
     StatsCtx X = A.X;
     if (OCC_SMEM) {
-        mpp_stage_bulk(s_occ, A.G.occ, (uint32_t)A.occ_words * 4u, &s_bar);
+        mpp_stage_bulk(s_occ, A.G.occ + (size_t)blockIdx.y * A.occ_words, (uint32_t)A.occ_words * 4u, &s_bar);
         G.occ = s_occ;
         X.occ = s_occ;
+    } else {
+        G.occ = A.G.occ + (size_t)blockIdx.y * A.occ_words;
+        X.occ = G.occ;
     }
     const int lane = threadIdx.x & 31;
-    const int slot = (blockIdx.x * MPP_MPA_THREADS + threadIdx.x) >> 5;
-    if (slot >= A.n_slots) return;
+    const int map = blockIdx.y;
+    const int slot_in_map = (blockIdx.x * MPP_MPA_THREADS + threadIdx.x) >> 5;
+    if (slot_in_map >= A.warps_per_map) return;
+    const int slot = map * A.warps_per_map + slot_in_map;
     const int rc = G.R * G.C, C = G.C;
     AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap,
                                 s_cnt[threadIdx.x >> 5]);
-    unsigned int *next = (unsigned int *)A.scratch;
+    unsigned int *next = A.queue + map;
     uint32_t *avoid = A.avoid + (size_t)slot * A.words;
     int32_t *tmp = A.tmp_cells + (size_t)slot * A.max_cells;
+    if (A.meta) { A.start = A.meta[map].start; A.target = A.meta[map].target; }
+    if (A.seeds) { const uint64_t sd = A.seeds[map]; A.k0 = (uint32_t)sd; A.k1 = (uint32_t)(sd >> 32); }
+    {   // this map's slice of the population buffers
+        const size_t pm = (size_t)map * A.N;
+        A.cells += pm * A.max_cells; A.n_cells += pm; A.stats += pm * 5;
+        A.out_cells += pm * A.max_cells; A.out_n += pm; A.out_stats += pm * 5;
+        if (A.order) A.order += pm;
+    }
     for (;;) {
         int i = 0;
         if (lane == 0) i = A.pred_begin + (int)atomicAdd(next, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= A.pred_end) break;
         int st_flag = 0;
-        const int32_t *old_path = A.cells + (size_t)i * A.max_cells;
-        const int old_n = A.n_cells[i];
-        const double *old_stats = A.stats + (size_t)i * 5;
+        const int row_i = A.order ? A.order[i] : i, row_0 = A.order ? A.order[0] : 0;   // rows of predator i / the elite
+        const int32_t *old_path = A.cells + (size_t)row_i * A.max_cells;
+        const int old_n = A.n_cells[row_i];
+        const double *old_stats = A.stats + (size_t)row_i * 5;
         const double old_fit = old_stats[4];
-        const int32_t *elite_path = A.cells;                       // population[0] after the sort (MPA.py:333-334)
-        const int elite_n = A.n_cells[0];
+        const int32_t *elite_path = A.cells + (size_t)row_0 * A.max_cells;   // population[0] after the sort (MPA.py:333-334)
+        const int elite_n = A.n_cells[row_0];
+        const double *elite_stats = A.stats + (size_t)row_0 * 5;
         int32_t *out = A.out_cells + (size_t)i * A.max_cells;
         double *ostats = A.out_stats + (size_t)i * 5;
         // ---------------- phase move (MPA.py:339-377) ----------------
@@ -157,11 +178,11 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
             scale = A.P_const; gate_p = A.P_const;
         } else if (A.phase == 2) {
             levy = i < A.N / 2;
-            P = levy ? old_path : elite_path; nP = levy ? old_n : elite_n; Pstats = levy ? old_stats : A.stats;
+            P = levy ? old_path : elite_path; nP = levy ? old_n : elite_n; Pstats = levy ? old_stats : elite_stats;
             ref = levy ? elite_path : old_path; nref = levy ? elite_n : old_n;
             scale = levy ? A.P_const : A.P_const * A.CF; gate_p = scale;
         } else {
-            P = elite_path; nP = elite_n; Pstats = A.stats; ref = old_path; nref = old_n; levy = true;
+            P = elite_path; nP = elite_n; Pstats = elite_stats; ref = old_path; nref = old_n; levy = true;
             scale = A.P_const * A.CF; gate_p = scale;
         }
         int n_new = nP;            // candidate defaults to path_to_modify with its stats
@@ -276,6 +297,21 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
     }
 }
 
+static int mpa_launch(MpaArgs &A, int n_maps, size_t occ_bytes, cudaStream_t s) {
+    const int blocks = (A.warps_per_map + MPP_MPA_WARPS - 1) / MPP_MPA_WARPS;
+    const dim3 grid(blocks, n_maps);
+    if (occ_bytes <= 32 * 1024) {
+        mpp_mpa_iteration_kernel<true><<<grid, MPP_MPA_THREADS, occ_bytes, s>>>(A);
+    } else if (occ_bytes <= 40 * 1024) {
+        MPP_CUDA(cudaFuncSetAttribute(mpp_mpa_iteration_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occ_bytes));
+        mpp_mpa_iteration_kernel<true><<<grid, MPP_MPA_THREADS, occ_bytes, s>>>(A);
+    } else {
+        mpp_mpa_iteration_kernel<false><<<grid, MPP_MPA_THREADS, 0, s>>>(A);
+    }
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}
+
 extern "C" int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_predators, int pred_begin, int pred_end,
                                  int iteration, int phase,
                                  double P_const, double CF, double FADs_rate, double levy_sigma, double levy_beta,
@@ -312,16 +348,115 @@ extern "C" int mpp_mpa_iteration(mpp_map *map, const mpp_policy *policy, int n_p
     A.tmp_cells = tmp_cells_dev; A.avoid = avoid_dev; A.words = (map->rows * map->cols + 31) / 32;
     A.scratch = (char *)scratch_dev; A.n_slots = n_slots; A.heap_cap = heap_cap; A.status = status_dev;
     A.counters = counters_dev;
-    const size_t smem = (size_t)map->occ_words * 4;
-    const int blocks = (n_slots + MPP_MPA_WARPS - 1) / MPP_MPA_WARPS;
-    if (smem <= 32 * 1024) {
-        mpp_mpa_iteration_kernel<true><<<blocks, MPP_MPA_THREADS, smem, s>>>(A);
-    } else if (smem <= 40 * 1024) {
-        MPP_CUDA(cudaFuncSetAttribute(mpp_mpa_iteration_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mpp_mpa_iteration_kernel<true><<<blocks, MPP_MPA_THREADS, smem, s>>>(A);
-    } else {
-        mpp_mpa_iteration_kernel<false><<<blocks, MPP_MPA_THREADS, 0, s>>>(A);
+    A.meta = nullptr; A.seeds = nullptr; A.order = nullptr; A.queue = (unsigned int *)scratch_dev; A.warps_per_map = n_slots;
+    return mpa_launch(A, 1, (size_t)map->occ_words * 4, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batches of independent same-shape maps (BASELINE config 5): one launch serves the predators of every map
+// (blockIdx.y = map; `warps_per_map` search slots and one work queue per map).  The population buffers are
+// [n_maps][N][...]; the kernel reads the OLD population through `order` (the stable argsort of its fitness column,
+// computed on the device by the caller), so the sorts of MPA.py:333,412 never move a path.
+// ---------------------------------------------------------------------------------------------
+extern "C" int mpp_mpa_iteration_batch(const mpp_map_batch *maps, const mpp_policy *policy, int n_predators, int iteration,
+                                       int phase, double P_const, double CF, double FADs_rate, double levy_sigma,
+                                       double levy_beta, const uint64_t *seeds_dev, const int32_t *order_dev,
+                                       const int32_t *cells_dev, const int32_t *n_cells_dev, const double *stats_dev,
+                                       int max_cells, int32_t *out_cells_dev, int32_t *out_n_dev, double *out_stats_dev,
+                                       int32_t *tmp_cells_dev, uint32_t *avoid_dev, void *scratch_dev, size_t scratch_bytes,
+                                       int warps_per_map, int heap_cap, uint32_t *queue_dev, int32_t *status_dev,
+                                       unsigned long long *counters_dev, void *stream) {
+    MPP_REQUIRE(maps && policy && seeds_dev && order_dev && cells_dev && n_cells_dev && stats_dev && out_cells_dev &&
+                    out_n_dev && out_stats_dev && tmp_cells_dev && avoid_dev && scratch_dev && queue_dev && status_dev,
+                "mpp_mpa_iteration_batch: null argument");
+    MPP_REQUIRE(n_predators > 0 && max_cells > 1 && phase >= 1 && phase <= 3 && warps_per_map > 0 && heap_cap >= 64,
+                "mpp_mpa_iteration_batch: bad sizes");
+    MPP_REQUIRE(maps->rows < 32768 && maps->cols < 65536, "mpp_mpa_iteration_batch: map exceeds the packed-node limit");
+    const int rc = maps->rows * maps->cols;
+    const size_t need = 256 + (size_t)warps_per_map * maps->n_maps * astar_slot_bytes(rc, heap_cap);
+    MPP_REQUIRE(scratch_bytes >= need, "mpp_mpa_iteration_batch: scratch too small (%zu < %zu)", scratch_bytes, need);
+    for (int k = 0; k < maps->n_maps; ++k)
+        MPP_REQUIRE(maps->meta_host[k].start >= 0 && maps->meta_host[k].target >= 0, "mpp_mpa_iteration_batch: map %d has no start/target", k);
+    MPP_CUDA(cudaSetDevice(maps->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    MpaArgs A;
+    A.X.occ = maps->occ_dev; A.X.pitch = maps->pitch_words; A.X.R = maps->rows; A.X.C = maps->cols;
+    A.X.pol = *policy; A.X.pol.mode = 1; A.X.cls = nullptr; A.X.lut = nullptr;     // MPA.py:164-173: safety = 0.0
+    MPP_CUDA(cudaMemsetAsync(queue_dev, 0, sizeof(uint32_t) * maps->n_maps, s));
+    A.G.occ = maps->occ_dev; A.G.pitch = maps->pitch_words; A.G.R = maps->rows; A.G.C = maps->cols;
+    A.G.allow_diag = policy->allow_diagonal; A.G.restrict_corner = policy->restrict_policy;
+    A.occ_words = maps->occ_words; A.start = -1; A.target = -1;
+    A.N = n_predators; A.iteration = iteration; A.phase = phase;
+    A.pred_begin = 0; A.pred_end = n_predators;
+    A.P_const = P_const; A.CF = CF; A.FADs_rate = FADs_rate; A.levy_sigma = levy_sigma; A.levy_inv_beta = 1.0 / levy_beta;
+    A.k0 = 0; A.k1 = 0;
+    A.cells = cells_dev; A.n_cells = n_cells_dev; A.stats = stats_dev; A.max_cells = max_cells;
+    A.out_cells = out_cells_dev; A.out_n = out_n_dev; A.out_stats = out_stats_dev;
+    A.tmp_cells = tmp_cells_dev; A.avoid = avoid_dev; A.words = (rc + 31) / 32;
+    A.scratch = (char *)scratch_dev; A.n_slots = warps_per_map * maps->n_maps; A.heap_cap = heap_cap; A.status = status_dev;
+    A.counters = counters_dev;
+    A.meta = maps->meta_dev; A.seeds = seeds_dev; A.order = order_dev; A.queue = queue_dev; A.warps_per_map = warps_per_map;
+    return mpa_launch(A, maps->n_maps, (size_t)maps->occ_words * 4, s);
+}
+
+// The initial population of every map (MPA.py:231-245): N identical runs of the private A* start -> target are ONE
+// search per map; row 0 of each map's buffers receives the path ([start, target] when there is none, :236) and its
+// statistics -- the caller replicates the row.  One warp per map.
+__global__ void __launch_bounds__(MPP_MPA_THREADS) mpp_mpa_init_kernel(MpaArgs A, int n_maps) {
+    __shared__ __align__(16) uint8_t s_cnt[MPP_MPA_WARPS][MPP_PQ_NB];
+    const int lane = threadIdx.x & 31;
+    const int map = (blockIdx.x * MPP_MPA_THREADS + threadIdx.x) >> 5;
+    if (map >= n_maps) return;
+    AStarGrid G = A.G;
+    StatsCtx X = A.X;
+    G.occ = A.G.occ + (size_t)map * A.occ_words;
+    X.occ = G.occ;
+    const int rc = G.R * G.C;
+    AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)map * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap,
+                                s_cnt[threadIdx.x >> 5]);
+    const int start = A.meta[map].start, target = A.meta[map].target;
+    int32_t *out = A.out_cells + (size_t)map * A.N * A.max_cells;
+    int sl = astar_search(G, S, 1, start, target, nullptr, out, A.max_cells, nullptr, A.counters);
+    int st_flag = 0;
+    if (sl < 0) { st_flag = 1; sl = 0; }
+    else if (sl > A.max_cells) { st_flag = 2; sl = 0; }
+    if (sl == 0) {                                                     // :236 (the target cell is never an obstacle)
+        if (lane == 0) { out[0] = start; out[1] = target; }
+        sl = 2;
+        __syncwarp();
     }
+    path_stats_warp(X, out, sl, A.out_stats + (size_t)map * A.N * 5);
+    if (lane == 0) {
+        A.out_n[(size_t)map * A.N] = sl;
+        if (st_flag) atomicMax(A.status, st_flag);
+    }
+}
+
+extern "C" int mpp_mpa_init_batch(const mpp_map_batch *maps, const mpp_policy *policy, int n_predators, int max_cells,
+                                  int32_t *cells_dev, int32_t *n_cells_dev, double *stats_dev, void *scratch_dev,
+                                  size_t scratch_bytes, int heap_cap, int32_t *status_dev, unsigned long long *counters_dev,
+                                  void *stream) {
+    MPP_REQUIRE(maps && policy && cells_dev && n_cells_dev && stats_dev && scratch_dev && status_dev,
+                "mpp_mpa_init_batch: null argument");
+    MPP_REQUIRE(n_predators > 0 && max_cells > 1 && heap_cap >= 64, "mpp_mpa_init_batch: bad sizes");
+    MPP_REQUIRE(maps->rows < 32768 && maps->cols < 65536, "mpp_mpa_init_batch: map exceeds the packed-node limit");
+    const int rc = maps->rows * maps->cols;
+    MPP_REQUIRE(scratch_bytes >= 256 + (size_t)maps->n_maps * astar_slot_bytes(rc, heap_cap), "mpp_mpa_init_batch: scratch too small");
+    for (int k = 0; k < maps->n_maps; ++k)
+        MPP_REQUIRE(maps->meta_host[k].start >= 0 && maps->meta_host[k].target >= 0, "mpp_mpa_init_batch: map %d has no start/target", k);
+    MPP_CUDA(cudaSetDevice(maps->device));
+    MpaArgs A;
+    memset(&A, 0, sizeof(A));
+    A.X.occ = maps->occ_dev; A.X.pitch = maps->pitch_words; A.X.R = maps->rows; A.X.C = maps->cols;
+    A.X.pol = *policy; A.X.pol.mode = 1; A.X.cls = nullptr; A.X.lut = nullptr;
+    A.G.occ = maps->occ_dev; A.G.pitch = maps->pitch_words; A.G.R = maps->rows; A.G.C = maps->cols;
+    A.G.allow_diag = policy->allow_diagonal; A.G.restrict_corner = policy->restrict_policy;
+    A.occ_words = maps->occ_words; A.N = n_predators; A.max_cells = max_cells;
+    A.out_cells = cells_dev; A.out_n = n_cells_dev; A.out_stats = stats_dev;
+    A.scratch = (char *)scratch_dev; A.heap_cap = heap_cap; A.status = status_dev; A.counters = counters_dev;
+    A.meta = maps->meta_dev;
+    const int blocks = (maps->n_maps + MPP_MPA_WARPS - 1) / MPP_MPA_WARPS;
+    mpp_mpa_init_kernel<<<blocks, MPP_MPA_THREADS, 0, (cudaStream_t)stream>>>(A, maps->n_maps);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }

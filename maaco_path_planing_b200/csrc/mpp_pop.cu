@@ -193,3 +193,66 @@ extern "C" int mpp_ga_breed(const mpp_map *map, const int32_t *chrom_dev, const 
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Population initialisers (pso.py:97-105, ga_solver.py:48-56, :95-104): the attempts of the reference's
+// "generate -> evaluate -> accept if valid" loops, a batch at a time.  Attempt a draws from stream
+// (seed, PSO_INIT / GA_INIT, 0, a), so a batch is any range of attempts and every rank can regenerate any of them.
+// ---------------------------------------------------------------------------------------------
+// PSO attempt: W waypoints [uniform(0, R-1), uniform(0, C-1)] (pso.py:50-51, draws 0..2W-1), then W velocities
+// [uniform(-max_vel/5, max_vel/5)] x 2 (pso.py:105, draws 2W..4W-1); also the rounded, clamped cells (pso.py:61,69-70).
+__global__ void mpp_pso_init_kernel(int n, int W, int attempt0, int R, int C, double max_vel, uint32_t k0, uint32_t k1,
+                                    double *__restrict__ pos, double *__restrict__ vel, int32_t *__restrict__ wp_cells) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * W) return;
+    const int p = t / W, dim = t % W;
+    const uint32_t att = (uint32_t)(attempt0 + p);
+    // draws 2*dim, 2*dim+1 = block dim; draws 2W + 2*dim, +1 = block W + dim
+    const mpp_u4 a = mpp_philox((uint32_t)dim, att, 0u, MPP_CLS_PSO_INIT, k0, k1);
+    const mpp_u4 b = mpp_philox((uint32_t)(W + dim), att, 0u, MPP_CLS_PSO_INIT, k0, k1);
+    const double lo = -max_vel / 5, hi = max_vel / 5;
+    const size_t i = ((size_t)p * W + dim) * 2;
+    const double xr = 0 + ((double)(R - 1) - 0) * mpp_u53(a.x, a.y);   // random.uniform(a, b) = a + (b-a)*random()
+    const double xc = 0 + ((double)(C - 1) - 0) * mpp_u53(a.z, a.w);
+    pos[i] = xr; pos[i + 1] = xc;
+    vel[i] = lo + (hi - lo) * mpp_u53(b.x, b.y);
+    vel[i + 1] = lo + (hi - lo) * mpp_u53(b.z, b.w);
+    int ir = (int)rint(xr), ic = (int)rint(xc);
+    ir = max(0, min(R - 1, ir)); ic = max(0, min(C - 1, ic));
+    wp_cells[(size_t)p * W + dim] = ir * C + ic;
+}
+
+extern "C" int mpp_pso_init(const mpp_map *map, int n_attempts, int attempt_offset, int n_waypoints, double max_vel,
+                            uint64_t seed, double *pos_dev, double *vel_dev, int32_t *waypoint_cells_dev, void *stream) {
+    MPP_REQUIRE(map && pos_dev && vel_dev && waypoint_cells_dev && n_attempts > 0 && n_waypoints > 0 && attempt_offset >= 0,
+                "mpp_pso_init: bad argument");
+    MPP_CUDA(cudaSetDevice(map->device));
+    const int total = n_attempts * n_waypoints;
+    mpp_pso_init_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        n_attempts, n_waypoints, attempt_offset, map->rows, map->cols, max_vel, (uint32_t)seed, (uint32_t)(seed >> 32),
+        pos_dev, vel_dev, waypoint_cells_dev);
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}
+
+// GA attempt: W genes, each (randint(0, R-1), randint(0, C-1)) redrawn until the cell is free (ga_solver.py:48-56)
+__global__ void mpp_ga_init_kernel(const uint32_t *__restrict__ occ, int pitch, int R, int C, int n, int W, int attempt0,
+                                   uint32_t k0, uint32_t k1, int32_t *__restrict__ chrom) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    mpp_stream_rng rng;
+    rng.init(((uint64_t)k1 << 32) | k0, MPP_CLS_GA_INIT, 0u, (uint32_t)(attempt0 + p));
+    for (int k = 0; k < W; ++k) chrom[(size_t)p * W + k] = ga_random_free_cell(rng, occ, pitch, R, C);
+}
+
+extern "C" int mpp_ga_init(const mpp_map *map, int n_attempts, int attempt_offset, int n_waypoints, uint64_t seed,
+                           int32_t *chrom_dev, void *stream) {
+    MPP_REQUIRE(map && chrom_dev && n_attempts > 0 && n_waypoints > 0 && attempt_offset >= 0, "mpp_ga_init: bad argument");
+    MPP_REQUIRE(map->n_obstacles < map->rows * map->cols, "mpp_ga_init: map has no free cell");
+    MPP_CUDA(cudaSetDevice(map->device));
+    mpp_ga_init_kernel<<<(n_attempts + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        map->occ_dev, map->pitch_words, map->rows, map->cols, n_attempts, n_waypoints, attempt_offset, (uint32_t)seed,
+        (uint32_t)(seed >> 32), chrom_dev);
+    MPP_CUDA(cudaGetLastError());
+    return MPP_OK;
+}

@@ -68,22 +68,13 @@ class GASolver(BasePathfinder):
         dev = self.engine.device
         N, W = self.population_size, self.num_waypoints
         max_total = N * 20
-        free = self.grid != OBSTACLE
         acc = []
         n_acc, attempts = 0, 0
         while n_acc < N and attempts < max_total:
             batch = min(max_total - attempts, max(32, int(1.25 * (N - n_acc)) + 8))
-            chrom = np.empty((batch, W), np.int32)
-            for b in range(batch):                                          # _create_chromosome :55-56
-                st = rng.Stream(self.rng_seed, rng.CLS_GA_INIT, 0, attempts + b, prefetch=4 * W)
-                for k in range(W):
-                    while True:                                             # rejection until a free cell :48-53
-                        r = st.below(self.rows)
-                        c = st.below(self.cols)
-                        if free[r, c]:
-                            break
-                    chrom[b, k] = r * self.cols + c
-            chrom_d = t.as_tensor(chrom, device=dev)
+            chrom_d = t.empty((batch, W), dtype=t.int32, device=dev)             # _create_chromosome :55-56 on the device
+            _lib.check(_lib.lib().mpp_ga_init(self.map.handle, batch, attempts, W, C.c_uint64(self.rng_seed),
+                                              _lib.ptr(chrom_d), self.engine._stream()), "mpp_ga_init")
             cells, ncell, stats = self._evaluate(chrom_d)
             take = np.flatnonzero((ncell > 0).cpu().numpy())
             room = N - n_acc

@@ -78,18 +78,20 @@ class PSOSolver(BasePathfinder):
         dev = self.engine.device
         N, W = self.num_particles, self.num_waypoints
         max_total = N * 20
-        lo, hi = -self.max_vel / 5, self.max_vel / 5
         acc_pos, acc_vel, acc_stats, acc_cells, acc_ncell = [], [], [], [], []
         n_acc, attempts = 0, 0
         while n_acc < N and attempts < max_total:
             batch = min(max_total - attempts, max(32, int(1.25 * (N - n_acc)) + 8))
-            u = rng.stream_block(self.rng_seed, rng.CLS_PSO_INIT, 0, np.arange(attempts, attempts + batch), 4 * W)
-            pos = np.empty((batch, W, 2))
-            pos[:, :, 0] = 0 + (self.rows - 1 - 0) * u[:, 0:2 * W:2]          # uniform(0, rows-1)  pso.py:50
-            pos[:, :, 1] = 0 + (self.cols - 1 - 0) * u[:, 1:2 * W:2]          # uniform(0, cols-1)  pso.py:51
-            vel = (lo + (hi - lo) * u[:, 2 * W:]).reshape(batch, W, 2)        # pso.py:105
-            pos_d = t.as_tensor(pos, device=dev)
-            cells, ncell, stats = self._evaluate_positions(pos_d)
+            # the attempts of this batch are generated on the device (mpp_pso_init: same Philox streams as the reference
+            # harness, pso.py:50-51,105) and evaluated in one launch
+            pos_d = t.empty((batch, W, 2), dtype=t.float64, device=dev)
+            vel_d = t.empty((batch, W, 2), dtype=t.float64, device=dev)
+            wp = t.empty((batch, W), dtype=t.int32, device=dev)
+            _lib.check(_lib.lib().mpp_pso_init(self.map.handle, batch, attempts, W, self.max_vel, C.c_uint64(self.rng_seed),
+                                               _lib.ptr(pos_d), _lib.ptr(vel_d), _lib.ptr(wp), self.engine._stream()),
+                       "mpp_pso_init")
+            self.fitness_evaluations += batch
+            cells, ncell, stats = self.engine.waypoint_fitness(wp, self.policy)
             valid = (ncell > 0).cpu().numpy()
             take = np.flatnonzero(valid)
             room = N - n_acc
@@ -100,7 +102,7 @@ class PSOSolver(BasePathfinder):
                 attempts += batch
             if take.size:
                 idx = t.as_tensor(take, device=dev)
-                acc_pos.append(pos_d[idx]); acc_vel.append(t.as_tensor(vel[take], device=dev))
+                acc_pos.append(pos_d[idx]); acc_vel.append(vel_d[idx])
                 acc_stats.append(stats[idx]); acc_cells.append(cells[idx]); acc_ncell.append(ncell[idx])
                 n_acc += take.size
         self.init_attempts = attempts

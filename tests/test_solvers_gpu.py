@@ -155,6 +155,42 @@ def test_mpa_trajectory(name, N):
         assert np.array_equal(cells[i, :ncell[i]], g[k + "_pop_cells"][offs[i]:offs[i + 1]]), f"predator {i}"
 
 
+def test_mpa_batched_maps_equal_individual_solves():
+    """Config-5 style sweep: MPA over several independent maps in one launch per iteration (device-side stable sorts read
+    through an index, best cascade vectorised over the maps) returns exactly what MPA returns map by map -- and the
+    golden-pinned single-map run is among them."""
+    from maaco_path_planing_b200 import blocks_map
+    from maaco_path_planing_b200.batch import MPABatch, solve_mpa_batch
+    from maaco_path_planing_b200.mpa import MPA
+    g = load_golden("solver_cases")
+    k = "mpa_blocks40_24"
+    N, K, seed, beta10 = (int(x) for x in g[k + "_meta"])
+    kw = dict(FADs_rate=0.2, P_const=0.5, levy_beta=beta10 / 10.0, turn_penalty_factor=0.1, safety_penalty_factor=0.8,
+              min_safe_distance=1.8, diagonal_obstacle_penalty=100.0)
+    grids = [g[k + "_grid"].astype(int)] + [blocks_map(40, 0.2, seed=60 + i) for i in range(3)]
+    seeds = [seed, 11, 12, 13]
+    b = MPABatch(np.stack(grids), N, K, seeds=seeds, **kw)
+    res = b.solve()
+    for i, (path, length, turns, sp, dp, fit, curve) in enumerate(res):
+        solo = MPA(grids[i], N, K, rng_seed=seeds[i], verbose=False, **kw)
+        want = solo.solve_path_planning()
+        assert (path, length, turns, sp, dp, fit) == tuple(want), i
+        assert curve == solo.convergence_curve_data, i
+    assert np.array_equal(np.array([r * 40 + c for r, c in res[0][0]], np.int32), g[k + "_best"])
+    assert np.array_equal(np.array(res[0][6], dtype=float), g[k + "_curve"])
+    # the sweep helper: maps of two shapes, waves of 2
+    mixed = grids + [blocks_map(24, 0.2, seed=70)]
+    out = solve_mpa_batch(mixed, 16, 4, kw, seeds=[5, 6, 7, 8, 9], wave=2)
+    assert [r[0] for r in out] == [0, 1, 2, 3, 4]
+    for r in out:
+        solo = MPA(mixed[r[0]], 16, 4, rng_seed=[5, 6, 7, 8, 9][r[0]], verbose=False, **kw)
+        assert tuple(r[1:7]) == tuple(solo.solve_path_planning()) and r[7] == solo.convergence_curve_data
+    # tiny path buffers / heaps: the solve notices on the device and repeats itself with more room
+    small = MPABatch(np.stack(grids[:2]), 12, 3, seeds=[1, 2], max_cells=16, heap_cap=64, **kw)
+    big = MPABatch(np.stack(grids[:2]), 12, 3, seeds=[1, 2], **kw)
+    assert small.solve() == big.solve()
+
+
 def test_mpa_anchor_and_errors():
     """the initial MPA population on fig7 is the private-A* S->T path: 28 cells,
     L=31.556349186104047, fitness = L + 0.1*turns."""
