@@ -490,6 +490,28 @@ def side_workloads(args, dev, world, rank, group, max_over_ranks, sync_all):
                      "achieved": BYTES_PER_ANT_STEP * int(tot[1]) / dev_s / 1e9 / world, "peak": peak, "unit": "GB/s",
                      "frac": BYTES_PER_ANT_STEP * int(tot[1]) / dev_s / 1e9 / world / peak,
                      "algorithmic_bytes_per_unit": BYTES_PER_ANT_STEP}}
+    # ---- config 5, MPA part: the same maps, MPA populations of 1024 paths, a bounded number of maps / iterations ----
+    from maaco_path_planing_b200.batch import MPABatch
+    mw, mit = min(args.mpa_batch_maps, hi - lo), args.mpa_batch_iters
+    sync_all()
+    t0 = time.perf_counter()
+    mb = MPABatch(all_grids[:mw], 1024, mit, seeds=list(range(lo, lo + mw)), **MPA_PARAMS)
+    mres = mb.solve()
+    torch.cuda.synchronize()
+    mwall = max_over_ranks(time.perf_counter() - t0)
+    mexp = torch.tensor([mb.expansions], dtype=torch.int64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(mexp, group=group)
+    out["batched_maps_mpa"] = {
+        "workload": f"{mw * world} independent 256x256 blocks maps x 1024 predators x {mit} MPA iterations ({mw} maps/GPU in one "
+                    "wave: one launch per iteration for every map; BASELINE config 5, MPA part; from host grids, incl. "
+                    "the initial searches and the result read-back = end to end)",
+        "value": mw * world * 1024 * mit / mwall, "unit": "predator-iterations/s", "seconds": mwall,
+        "astar_expansions_per_s": int(mexp.item()) / mwall, "solved_maps": sum(1 for r in mres if r[0]), "scaling": "weak"}
+    mb.close()
+    del mb
+    torch.cuda.empty_cache()
     if world > 1 or rank != 0:
         return out
     if not args.no_cpu:
@@ -600,6 +622,8 @@ def main():
     ap.add_argument("--batch-maps", type=int, default=256, help="independent maps per GPU (config 5 is 10000 over 8 GPUs = 1250)")
     ap.add_argument("--batch-iters", type=int, default=10)
     ap.add_argument("--batch-wave", type=int, default=128)
+    ap.add_argument("--mpa-batch-maps", type=int, default=16, help="maps per GPU in the MPA part of config 5 (bounded sample)")
+    ap.add_argument("--mpa-batch-iters", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
