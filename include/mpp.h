@@ -264,14 +264,17 @@ int mpp_astar_batch(mpp_map *map, int variant, const int32_t *src_dev, const int
 
 /* replaces PSOSolver._reconstruct_path_from_position (pso.py:56-94, after rounding/clamping) /
  * GASolver._reconstruct_path_from_chromosome (ga_solver.py:58-93) followed by
- * BasePathfinder._calculate_stats_for_path (helper.py:138-147) for a whole population: one warp per
- * individual runs its W+1 connector searches with the growing avoid set and the statistics of the joined
- * path.  waypoints_dev: N x W cells.  visited_dev: N x ceil(rows*cols/32) words of scratch.
- * n_cells_dev[i]: 0 = invalid individual ([]), -1 = heap overflow, > max_cells = truncated. */
+ * BasePathfinder._calculate_stats_for_path (helper.py:138-147) for a whole population: one lane group (a warp)
+ * per individual runs its W+1 connector searches with the growing avoid set and the statistics of the
+ * joined path.  waypoints_dev: N x W cells.  visited_dev: N x ceil(rows*cols/32) words of scratch.
+ * n_cells_dev[i]: 0 = invalid individual ([]), -1 = heap overflow, > max_cells = truncated.
+ * order_dev: optional permutation of 0..N-1 = the order in which free search slots take individuals (the evaluation
+ * lasts as long as its longest chain of searches: start the long ones first); results stay indexed by individual. */
 int mpp_waypoint_fitness(mpp_map *map, const int32_t *waypoints_dev, int n_individuals, int n_waypoints,
                          const mpp_policy *policy, int32_t *cells_dev, int max_cells, int32_t *n_cells_dev,
                          double *stats_dev, uint32_t *visited_dev, void *scratch_dev, size_t scratch_bytes,
-                         int n_slots, int heap_cap, unsigned long long *counters_dev, void *stream);
+                         int n_slots, int heap_cap, unsigned long long *counters_dev, const int32_t *order_dev,
+                         void *stream);
 
 /* ---- PSO / GA population updates (pso.py, ga_solver.py) ------------------------------------------- */
 

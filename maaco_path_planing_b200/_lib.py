@@ -90,7 +90,8 @@ _SIGS = {
     "mpp_astar_batch": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                 c_void_p, c_void_p, c_void_p, C.c_size_t, c_int, c_int, c_void_p, c_void_p]),
     "mpp_waypoint_fitness": (c_int, [c_void_p, c_void_p, c_int, c_int, C.POINTER(Policy), c_void_p, c_int, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, C.c_size_t, c_int, c_int, c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, C.c_size_t, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p]),
     "mpp_pso_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double,
                                c_double, c_double, c_double, c_u64, c_int, c_void_p, c_void_p]),
     "mpp_pso_round": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

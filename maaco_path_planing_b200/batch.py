@@ -253,7 +253,7 @@ class MPABatch:
             seeds = [int.from_bytes(np.random.bytes(8), "little") for _ in range(self.n_maps)]
         self.seeds = [int(s) & (2 ** 64 - 1) for s in seeds]
         sm = torch.cuda.get_device_properties(self.device).multi_processor_count
-        # search slots: three CTAs of 8 warps per SM in total, split evenly over the maps (at least one CTA each)
+        # search slots (one warp each): three CTAs of 8 warps per SM in total, split evenly over the maps (at least one CTA each)
         self.warps_per_map = int(warps_per_map or max(8, ((sm * 24) // self.n_maps) // 8 * 8))
         self._ctor = dict(grids=grids, num_predators=num_predators, num_iterations=num_iterations, FADs_rate=FADs_rate,
                           P_const=P_const, levy_beta=levy_beta, turn_penalty_factor=turn_penalty_factor,

@@ -7,8 +7,9 @@
 #include "mpp_astar.cuh"
 #include "mpp_stats.cuh"
 
-#define MPP_AS_THREADS 256
+#define MPP_AS_THREADS (MPP_GL == 32 ? 256 : 128)
 #define MPP_AS_WARPS (MPP_AS_THREADS / 32)
+#define MPP_AS_GROUPS (MPP_AS_THREADS / MPP_GL)     // searches (lane groups) per CTA
 
 // ---------------------------------------------------------------------------------------------
 // K1b: safety-class table (helper.py:67-80 as a per-cell function of the map)
@@ -73,11 +74,12 @@ extern "C" int mpp_map_safety_table(mpp_map *map, double msd, void *stream) {
 __global__ void __launch_bounds__(MPP_AS_THREADS)
 mpp_path_stats_kernel(StatsCtx X, const int32_t *__restrict__ cells, int max_cells, const int32_t *__restrict__ n_cells,
                       int n_paths, double *stats) {
-    const int w = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) >> 5;
+    const LaneGroup L = lane_group();
+    const int w = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) / MPP_GL;
     if (w >= n_paths) return;
     int n = n_cells[w];
     if (n > max_cells) n = max_cells;
-    path_stats_warp(X, cells + (size_t)w * max_cells, n, stats + (size_t)w * 5);
+    path_stats_warp(L, X, cells + (size_t)w * max_cells, n, stats + (size_t)w * 5);
 }
 
 static int make_stats_ctx(mpp_map *map, const mpp_policy *pol, void *stream, StatsCtx *X) {
@@ -100,7 +102,7 @@ extern "C" int mpp_path_stats(mpp_map *map, const int32_t *cells_dev, int max_ce
     StatsCtx X;
     int rc = make_stats_ctx(map, policy, stream, &X);
     if (rc) return rc;
-    const int blocks = (n_paths + MPP_AS_WARPS - 1) / MPP_AS_WARPS;
+    const int blocks = (n_paths + MPP_AS_GROUPS - 1) / MPP_AS_GROUPS;
     mpp_path_stats_kernel<<<blocks, MPP_AS_THREADS, 0, (cudaStream_t)stream>>>(X, cells_dev, max_cells, n_cells_dev,
                                                                              n_paths, stats_dev);
     MPP_CUDA(cudaGetLastError());
@@ -120,7 +122,8 @@ extern "C" size_t mpp_astar_slot_bytes(int rows, int cols, int heap_cap) {
     return astar_slot_bytes(rows * cols, heap_cap);
 }
 
-extern "C" int mpp_astar_max_slots(const mpp_map *map) { return map ? map->sm_count * 3 * MPP_AS_WARPS : 0; }
+// search slots (lane groups) that are resident at once: three CTAs of MPP_AS_GROUPS groups per SM
+extern "C" int mpp_astar_max_slots(const mpp_map *map) { return map ? map->sm_count * 3 * MPP_AS_GROUPS : 0; }
 
 struct BatchArgs {
     AStarGrid G;
@@ -142,26 +145,27 @@ template <bool OCC_SMEM>
 __global__ void __launch_bounds__(MPP_AS_THREADS, 3) mpp_astar_batch_kernel(BatchArgs A) {
     extern __shared__ __align__(16) uint32_t s_occ[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ __align__(16) uint8_t s_cnt[MPP_AS_WARPS][MPP_PQ_NB];
+    __shared__ __align__(16) uint8_t s_cnt[MPP_AS_GROUPS][MPP_PQ_NB];
     AStarGrid G = A.G;
     if (OCC_SMEM) {
         mpp_stage_bulk(s_occ, A.G.occ, (uint32_t)A.occ_words * 4u, &s_bar);
         G.occ = s_occ;
     }
-    const int lane = threadIdx.x & 31;
-    const int slot = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) >> 5;
+    const LaneGroup L = lane_group();
+    const int lane = L.gl;
+    const int slot = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) / MPP_GL;
     if (slot >= A.n_slots) return;
     const int rc = G.R * G.C;
     AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap,
-                                s_cnt[threadIdx.x >> 5]);
+                                s_cnt[threadIdx.x / MPP_GL]);
     unsigned int *next = (unsigned int *)A.scratch;
     for (;;) {
         int i = 0;
         if (lane == 0) i = (int)atomicAdd(next, 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
+        i = grp_shfl(L, i, 0);
         if (i >= A.n) break;
         double g;
-        const int len = astar_search(G, S, A.variant, A.src[i], A.dst[i], A.avoid ? A.avoid + (size_t)i * A.words : nullptr,
+        const int len = astar_search(L, G, S, A.variant, A.src[i], A.dst[i], A.avoid ? A.avoid + (size_t)i * A.words : nullptr,
                                      A.cells + (size_t)i * A.max_cells, A.max_cells, &g, A.counters);
         if (lane == 0) { A.n_cells[i] = len; if (A.g) A.g[i] = g; }
     }
@@ -198,7 +202,7 @@ extern "C" int mpp_astar_batch(mpp_map *map, int variant, const int32_t *src_dev
     A.n_cells = n_cells_dev; A.g = g_dev; A.scratch = (char *)scratch_dev; A.n_slots = n_slots; A.heap_cap = heap_cap;
     A.counters = counters_dev;
     const size_t smem = (size_t)map->occ_words * 4;
-    const int blocks = (n_slots + MPP_AS_WARPS - 1) / MPP_AS_WARPS;
+    const int blocks = (n_slots + MPP_AS_GROUPS - 1) / MPP_AS_GROUPS;
     if (smem <= 32 * 1024) {
         mpp_astar_batch_kernel<true><<<blocks, MPP_AS_THREADS, smem, s>>>(A);
     } else if (smem <= 40 * 1024) {
@@ -232,13 +236,14 @@ struct ChainArgs {
     char *scratch;
     int n_slots, heap_cap;
     unsigned long long *counters;
+    const int32_t *order;  // optional processing order of the individuals (null: index order)
 };
 
 template <bool OCC_SMEM>
 __global__ void __launch_bounds__(MPP_AS_THREADS, 3) mpp_waypoint_fitness_kernel(ChainArgs A) {
     extern __shared__ __align__(16) uint32_t s_occ[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ __align__(16) uint8_t s_cnt[MPP_AS_WARPS][MPP_PQ_NB];
+    __shared__ __align__(16) uint8_t s_cnt[MPP_AS_GROUPS][MPP_PQ_NB];
     AStarGrid G = A.G;
     StatsCtx X = A.X;
     if (OCC_SMEM) {
@@ -246,52 +251,55 @@ __global__ void __launch_bounds__(MPP_AS_THREADS, 3) mpp_waypoint_fitness_kernel
         G.occ = s_occ;
         X.occ = s_occ;
     }
-    const int lane = threadIdx.x & 31;
-    const int slot = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) >> 5;
+    const LaneGroup L = lane_group();
+    const int lane = L.gl;
+    const int slot = (blockIdx.x * MPP_AS_THREADS + threadIdx.x) / MPP_GL;
     if (slot >= A.n_slots) return;
     const int rc = G.R * G.C;
     AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap,
-                                s_cnt[threadIdx.x >> 5]);
+                                s_cnt[threadIdx.x / MPP_GL]);
     unsigned int *next = (unsigned int *)A.scratch;
     for (;;) {
         int i = 0;
         if (lane == 0) i = (int)atomicAdd(next, 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
+        i = grp_shfl(L, i, 0);
         if (i >= A.N) break;
+        if (A.order) i = A.order[i];                                   // longest chains first (see mpp_waypoint_fitness)
         uint32_t *vis = A.visited + (size_t)i * A.words;
         int32_t *path = A.cells + (size_t)i * A.max_cells;
-        for (int w = lane; w < A.words; w += 32) vis[w] = 0u;
-        __syncwarp();
+        for (int w = lane; w < A.words; w += MPP_GL) vis[w] = 0u;
+        grp_sync(L);
         int n = 1, cur = A.start, status = 1;
         if (lane == 0) { path[0] = A.start; vis[A.start >> 5] |= 1u << (A.start & 31); }   // pso.py:63-65
-        __syncwarp();
+        grp_sync(L);
         for (int k = 0; k <= A.W; ++k) {
             const int goal = (k < A.W) ? A.wps[(size_t)i * A.W + k] : A.target;
             // the segment is written over the tail cell of the path (segment[0] == current_start)
             const int cap = A.max_cells - (n - 1);
-            const int sl = astar_search(G, S, 0, cur, goal, vis, path + (n - 1), cap, nullptr, A.counters);
+            const int sl = astar_search(L, G, S, 0, cur, goal, vis, path + (n - 1), cap, nullptr, A.counters);
             if (sl < 0) { status = -1; break; }
             if (sl == 0 || (sl == 1 && cur != goal)) { status = 0; break; }          // pso.py:77,87 -> []
             if (sl > cap) { status = 2; n += sl - 1; break; }                        // truncated
-            for (int t = 1 + lane; t < sl; t += 32) {                                // nodes_in_path_so_far.update
+            for (int t = 1 + lane; t < sl; t += MPP_GL) {                            // nodes_in_path_so_far.update
                 const int c = path[n - 1 + t];
                 atomicOr(&vis[c >> 5], 1u << (c & 31));
             }
-            __syncwarp();
+            grp_sync(L);
             n += sl - 1;
             cur = goal;
         }
         // (consecutive duplicates cannot occur: a segment never repeats its first cell; pso.py:91-93 is a no-op)
         int n_out = status == 1 ? n : (status == 2 ? n : status);
         if (lane == 0) A.n_cells[i] = n_out;
-        path_stats_warp(X, path, status == 1 ? n : 0, A.stats + (size_t)i * 5);
+        path_stats_warp(L, X, path, status == 1 ? n : 0, A.stats + (size_t)i * 5);
     }
 }
 
 extern "C" int mpp_waypoint_fitness(mpp_map *map, const int32_t *waypoints_dev, int n_individuals, int n_waypoints,
                                     const mpp_policy *policy, int32_t *cells_dev, int max_cells, int32_t *n_cells_dev,
                                     double *stats_dev, uint32_t *visited_dev, void *scratch_dev, size_t scratch_bytes,
-                                    int n_slots, int heap_cap, unsigned long long *counters_dev, void *stream) {
+                                    int n_slots, int heap_cap, unsigned long long *counters_dev, const int32_t *order_dev,
+                                    void *stream) {
     MPP_REQUIRE(map && policy && cells_dev && n_cells_dev && stats_dev && visited_dev && scratch_dev,
                 "mpp_waypoint_fitness: null argument");
     MPP_REQUIRE(n_individuals > 0 && n_waypoints >= 0 && max_cells > 1, "mpp_waypoint_fitness: bad sizes");
@@ -311,8 +319,9 @@ extern "C" int mpp_waypoint_fitness(mpp_map *map, const int32_t *waypoints_dev, 
     A.wps = waypoints_dev; A.N = n_individuals; A.W = n_waypoints; A.words = (map->rows * map->cols + 31) / 32;
     A.cells = cells_dev; A.max_cells = max_cells; A.n_cells = n_cells_dev; A.stats = stats_dev; A.visited = visited_dev;
     A.scratch = (char *)scratch_dev; A.n_slots = n_slots; A.heap_cap = heap_cap; A.counters = counters_dev;
+    A.order = order_dev;
     const size_t smem = (size_t)map->occ_words * 4;
-    const int blocks = (n_slots + MPP_AS_WARPS - 1) / MPP_AS_WARPS;
+    const int blocks = (n_slots + MPP_AS_GROUPS - 1) / MPP_AS_GROUPS;
     if (smem <= 32 * 1024) {
         mpp_waypoint_fitness_kernel<true><<<blocks, MPP_AS_THREADS, smem, s>>>(A);
     } else if (smem <= 40 * 1024) {

@@ -1,7 +1,7 @@
 // mpp_mpa.cu -- one MPA iteration for the whole predator population (MPA.py:339-410): phase move
 // (Brownian / Levy target generation MPA.py:250-282 + path-segment reconstruction :284-318 with the
 // private A* :106-151), marine-memory saving (:380-384) and the FADs step (:387-410).
-// One warp per individual; every individual reads only the old (sorted) population and the elite, so
+// One lane group (mpp_astar.cuh: a warp by default) per individual; every individual reads only the old (sorted) population and the elite, so
 // the loop bodies of MPA.py:340/349/366/387 are data-parallel.  Streams: (seed, MPA_PHASE, it, i) and
 // (seed, MPA_FADS, it, i), draws consumed in the reference's order.
 #include <cmath>
@@ -9,8 +9,8 @@
 #include "mpp_astar.cuh"
 #include "mpp_stats.cuh"
 
-#define MPP_MPA_THREADS 256
-#define MPP_MPA_WARPS (MPP_MPA_THREADS / 32)
+#define MPP_MPA_THREADS (MPP_GL == 32 ? 256 : 128)
+#define MPP_MPA_GROUPS (MPP_MPA_THREADS / MPP_GL)   // predators (lane groups) served by one CTA at a time
 #define MPP_NV_MAGICCONST 1.7155277699214135  // random.NV_MAGICCONST = 4*exp(-0.5)/sqrt(2.0)
 
 struct MpaArgs {
@@ -102,24 +102,24 @@ __device__ int mpa_brownian_target(mpp_stream_rng &rng, const MpaArgs &A, int cu
     return clampi(tr_, 0, R - 1) * C + clampi(tc_, 0, C - 1);
 }
 
-__device__ __forceinline__ void warp_copy_path(int32_t *dst, const int32_t *src, int n) {
-    for (int i = threadIdx.x & 31; i < n; i += 32) dst[i] = src[i];
-    __syncwarp();
+__device__ __forceinline__ void warp_copy_path(const LaneGroup &L, int32_t *dst, const int32_t *src, int n) {
+    for (int i = L.gl; i < n; i += MPP_GL) dst[i] = src[i];
+    grp_sync(L);
 }
-__device__ __forceinline__ void warp_mark(uint32_t *bits, const int32_t *cells, int n) {
-    for (int i = threadIdx.x & 31; i < n; i += 32) atomicOr(&bits[cells[i] >> 5], 1u << (cells[i] & 31));
-    __syncwarp();
+__device__ __forceinline__ void warp_mark(const LaneGroup &L, uint32_t *bits, const int32_t *cells, int n) {
+    for (int i = L.gl; i < n; i += MPP_GL) atomicOr(&bits[cells[i] >> 5], 1u << (cells[i] & 31));
+    grp_sync(L);
 }
-__device__ __forceinline__ void copy_stats(double *dst, const double *src) {
-    if ((threadIdx.x & 31) < 5) dst[threadIdx.x & 31] = src[threadIdx.x & 31];
-    __syncwarp();
+__device__ __forceinline__ void copy_stats(const LaneGroup &L, double *dst, const double *src) {
+    if (L.gl < 5) dst[L.gl] = src[L.gl];
+    grp_sync(L);
 }
 
 template <bool OCC_SMEM>
 __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(MpaArgs A) {
     extern __shared__ __align__(16) uint32_t s_occ[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ __align__(16) uint8_t s_cnt[MPP_MPA_WARPS][MPP_PQ_NB];
+    __shared__ __align__(16) uint8_t s_cnt[MPP_MPA_GROUPS][MPP_PQ_NB];
     AStarGrid G = A.G;
     StatsCtx X = A.X;
     if (OCC_SMEM) {
@@ -130,14 +130,15 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
         G.occ = A.G.occ + (size_t)blockIdx.y * A.occ_words;
         X.occ = G.occ;
     }
-    const int lane = threadIdx.x & 31;
+    const LaneGroup L = lane_group();
+    const int lane = L.gl;
     const int map = blockIdx.y;
-    const int slot_in_map = (blockIdx.x * MPP_MPA_THREADS + threadIdx.x) >> 5;
+    const int slot_in_map = (blockIdx.x * MPP_MPA_THREADS + threadIdx.x) / MPP_GL;
     if (slot_in_map >= A.warps_per_map) return;
     const int slot = map * A.warps_per_map + slot_in_map;
     const int rc = G.R * G.C, C = G.C;
     AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)slot * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap,
-                                s_cnt[threadIdx.x >> 5]);
+                                s_cnt[threadIdx.x / MPP_GL]);
     unsigned int *next = A.queue + map;
     uint32_t *avoid = A.avoid + (size_t)slot * A.words;
     int32_t *tmp = A.tmp_cells + (size_t)slot * A.max_cells;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
     for (;;) {
         int i = 0;
         if (lane == 0) i = A.pred_begin + (int)atomicAdd(next, 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
+        i = grp_shfl(L, i, 0);
         if (i >= A.pred_end) break;
         int st_flag = 0;
         const int row_i = A.order ? A.order[i] : i, row_0 = A.order ? A.order[0] : 0;   // rows of predator i / the elite
@@ -194,10 +195,10 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
             if (rng.draw() < gate_p) {
                 // ---- _reconstruct_path_segment MPA.py:284-318 ----
                 const int cur = P[idx];
-                for (int w = lane; w < A.words; w += 32) avoid[w] = 0u;
-                __syncwarp();
-                warp_mark(avoid, P, idx);                                          // set(prefix[:-1])
-                warp_copy_path(out, P, idx + 1);                                   // prefix
+                for (int w = lane; w < A.words; w += MPP_GL) avoid[w] = 0u;
+                grp_sync(L);
+                warp_mark(L, avoid, P, idx);                                          // set(prefix[:-1])
+                warp_copy_path(L, out, P, idx + 1);                                   // prefix
                 int n = idx + 1;
                 int inter;
                 if (levy) inter = mpa_levy_target(rng, A, cur, scale);
@@ -208,18 +209,18 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
                 int a_start = cur;
                 if (!occ_bit(G, inter / C, inter % C) && inter != a_start) {       // :298
                     const int cap = A.max_cells - (n - 1);
-                    const int sl = astar_search(G, S, 1, a_start, inter, avoid, out + (n - 1), cap, nullptr, A.counters);
+                    const int sl = astar_search(L, G, S, 1, a_start, inter, avoid, out + (n - 1), cap, nullptr, A.counters);
                     if (sl < 0) st_flag = 1;
                     else if (sl > cap) st_flag = 2;
                     else if (sl > 1) {                                             // :300-305
-                        warp_mark(avoid, out + n, sl - 1);
+                        warp_mark(L, avoid, out + n, sl - 1);
                         n += sl - 1;
                         a_start = inter;
                     }
                 }
                 if (a_start != A.target && st_flag == 0) {                         // :306-309
                     const int cap = A.max_cells - (n - 1);
-                    const int sl = astar_search(G, S, 1, a_start, A.target, avoid, out + (n - 1), cap, nullptr, A.counters);
+                    const int sl = astar_search(L, G, S, 1, a_start, A.target, avoid, out + (n - 1), cap, nullptr, A.counters);
                     if (sl < 0) st_flag = 1;
                     else if (sl > cap) st_flag = 2;
                     else if (sl > 1) n += sl - 1;
@@ -228,8 +229,8 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
                 if (st_flag == 0 && n > 0 && out[0] == A.start && out[n - 1] == A.target) {   // :316
                     n_new = n;
                     rebuilt = true;
-                    path_stats_warp(X, out, n, ostats);
-                    __syncwarp();
+                    path_stats_warp(L, X, out, n, ostats);
+                    grp_sync(L);
                 }
             }
         }
@@ -238,11 +239,11 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
         int cur_n;
         double cur_fit;
         if (cand_fit < old_fit) {
-            if (!rebuilt) { warp_copy_path(out, P, nP < A.max_cells ? nP : A.max_cells); copy_stats(ostats, Pstats); }
+            if (!rebuilt) { warp_copy_path(L, out, P, nP < A.max_cells ? nP : A.max_cells); copy_stats(L, ostats, Pstats); }
             cur_n = n_new; cur_fit = cand_fit;
         } else {
-            warp_copy_path(out, old_path, old_n < A.max_cells ? old_n : A.max_cells);
-            copy_stats(ostats, old_stats);
+            warp_copy_path(L, out, old_path, old_n < A.max_cells ? old_n : A.max_cells);
+            copy_stats(L, ostats, old_stats);
             cur_n = old_n; cur_fit = old_fit;
         }
         // ---------------- FADs MPA.py:387-410 ----------------
@@ -254,15 +255,15 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
                 const int r = fr.below(G.R), c = fr.below(G.C);                    // :391
                 const int node = r * C + c;
                 if (!occ_bit(G, r, c)) {
-                    const int sl1 = astar_search(G, S, 1, A.start, node, nullptr, tmp, A.max_cells, nullptr, A.counters);
+                    const int sl1 = astar_search(L, G, S, 1, A.start, node, nullptr, tmp, A.max_cells, nullptr, A.counters);
                     if (sl1 < 0) st_flag = 1;
                     else if (sl1 > A.max_cells) st_flag = 2;
                     else if (sl1 > 0) {
-                        for (int w = lane; w < A.words; w += 32) avoid[w] = 0u;
-                        __syncwarp();
-                        warp_mark(avoid, tmp, sl1 - 1);                            // set(p1[:-1]) :396
+                        for (int w = lane; w < A.words; w += MPP_GL) avoid[w] = 0u;
+                        grp_sync(L);
+                        warp_mark(L, avoid, tmp, sl1 - 1);                            // set(p1[:-1]) :396
                         const int cap = A.max_cells - (sl1 - 1);
-                        const int sl2 = astar_search(G, S, 1, node, A.target, avoid, tmp + (sl1 - 1), cap, nullptr, A.counters);
+                        const int sl2 = astar_search(L, G, S, 1, node, A.target, avoid, tmp + (sl1 - 1), cap, nullptr, A.counters);
                         if (sl2 < 0) st_flag = 1;
                         else if (sl2 > cap) st_flag = 2;
                         else if (sl2 > 0) {
@@ -272,19 +273,19 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
                     }
                 }
             } else {
-                const int sl = astar_search(G, S, 1, A.start, A.target, nullptr, tmp, A.max_cells, nullptr, A.counters);  // :405
+                const int sl = astar_search(L, G, S, 1, A.start, A.target, nullptr, tmp, A.max_cells, nullptr, A.counters);  // :405
                 if (sl < 0) st_flag = 1;
                 else if (sl > A.max_cells) st_flag = 2;
                 else if (sl > 0) n2 = sl;
             }
             if (n2 > 0 && st_flag == 0) {
                 double *slot_stats = (double *)((char *)S.hdr + 64);               // 5 doubles in the slot header
-                path_stats_warp(X, tmp, n2, slot_stats);
-                __syncwarp();
+                path_stats_warp(L, X, tmp, n2, slot_stats);
+                grp_sync(L);
                 const double f2 = slot_stats[4];
                 if (f2 < cur_fit) {                                                // :402 / :408
-                    warp_copy_path(out, tmp, n2);
-                    copy_stats(ostats, slot_stats);
+                    warp_copy_path(L, out, tmp, n2);
+                    copy_stats(L, ostats, slot_stats);
                     cur_n = n2; cur_fit = f2;
                 }
             }
@@ -293,12 +294,12 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS, 3) mpp_mpa_iteration_kernel(M
             A.out_n[i] = cur_n;
             if (st_flag) atomicMax(A.status, st_flag);
         }
-        __syncwarp();
+        grp_sync(L);
     }
 }
 
 static int mpa_launch(MpaArgs &A, int n_maps, size_t occ_bytes, cudaStream_t s) {
-    const int blocks = (A.warps_per_map + MPP_MPA_WARPS - 1) / MPP_MPA_WARPS;
+    const int blocks = (A.warps_per_map + MPP_MPA_GROUPS - 1) / MPP_MPA_GROUPS;
     const dim3 grid(blocks, n_maps);
     if (occ_bytes <= 32 * 1024) {
         mpp_mpa_iteration_kernel<true><<<grid, MPP_MPA_THREADS, occ_bytes, s>>>(A);
@@ -403,9 +404,10 @@ extern "C" int mpp_mpa_iteration_batch(const mpp_map_batch *maps, const mpp_poli
 // search per map; row 0 of each map's buffers receives the path ([start, target] when there is none, :236) and its
 // statistics -- the caller replicates the row.  One warp per map.
 __global__ void __launch_bounds__(MPP_MPA_THREADS) mpp_mpa_init_kernel(MpaArgs A, int n_maps) {
-    __shared__ __align__(16) uint8_t s_cnt[MPP_MPA_WARPS][MPP_PQ_NB];
-    const int lane = threadIdx.x & 31;
-    const int map = (blockIdx.x * MPP_MPA_THREADS + threadIdx.x) >> 5;
+    __shared__ __align__(16) uint8_t s_cnt[MPP_MPA_GROUPS][MPP_PQ_NB];
+    const LaneGroup L = lane_group();
+    const int lane = L.gl;
+    const int map = (blockIdx.x * MPP_MPA_THREADS + threadIdx.x) / MPP_GL;
     if (map >= n_maps) return;
     AStarGrid G = A.G;
     StatsCtx X = A.X;
@@ -413,19 +415,19 @@ __global__ void __launch_bounds__(MPP_MPA_THREADS) mpp_mpa_init_kernel(MpaArgs A
     X.occ = G.occ;
     const int rc = G.R * G.C;
     AStarSlot S = astar_slot_at(A.scratch + 256 + (size_t)map * astar_slot_bytes(rc, A.heap_cap), rc, A.heap_cap,
-                                s_cnt[threadIdx.x >> 5]);
+                                s_cnt[threadIdx.x / MPP_GL]);
     const int start = A.meta[map].start, target = A.meta[map].target;
     int32_t *out = A.out_cells + (size_t)map * A.N * A.max_cells;
-    int sl = astar_search(G, S, 1, start, target, nullptr, out, A.max_cells, nullptr, A.counters);
+    int sl = astar_search(L, G, S, 1, start, target, nullptr, out, A.max_cells, nullptr, A.counters);
     int st_flag = 0;
     if (sl < 0) { st_flag = 1; sl = 0; }
     else if (sl > A.max_cells) { st_flag = 2; sl = 0; }
     if (sl == 0) {                                                     // :236 (the target cell is never an obstacle)
         if (lane == 0) { out[0] = start; out[1] = target; }
         sl = 2;
-        __syncwarp();
+        grp_sync(L);
     }
-    path_stats_warp(X, out, sl, A.out_stats + (size_t)map * A.N * 5);
+    path_stats_warp(L, X, out, sl, A.out_stats + (size_t)map * A.N * 5);
     if (lane == 0) {
         A.out_n[(size_t)map * A.N] = sl;
         if (st_flag) atomicMax(A.status, st_flag);
@@ -455,7 +457,7 @@ extern "C" int mpp_mpa_init_batch(const mpp_map_batch *maps, const mpp_policy *p
     A.out_cells = cells_dev; A.out_n = n_cells_dev; A.out_stats = stats_dev;
     A.scratch = (char *)scratch_dev; A.heap_cap = heap_cap; A.status = status_dev; A.counters = counters_dev;
     A.meta = maps->meta_dev;
-    const int blocks = (maps->n_maps + MPP_MPA_WARPS - 1) / MPP_MPA_WARPS;
+    const int blocks = (maps->n_maps + MPP_MPA_GROUPS - 1) / MPP_MPA_GROUPS;
     mpp_mpa_init_kernel<<<blocks, MPP_MPA_THREADS, 0, (cudaStream_t)stream>>>(A, maps->n_maps);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;

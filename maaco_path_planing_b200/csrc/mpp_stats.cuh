@@ -1,9 +1,9 @@
-// mpp_stats.cuh -- warp-level path statistics shared by the fitness and MPA kernels.
+// mpp_stats.cuh -- lane-group path statistics shared by the fitness and MPA kernels (one path per lane group, mpp_astar.cuh).
 #pragma once
 #include "mpp_astar.cuh"
 
 // ---------------------------------------------------------------------------------------------
-// K7: path statistics by one warp (helper.py:98-113 / MPA.py:215-229)
+// K7: path statistics by one lane group (helper.py:98-113 / MPA.py:215-229)
 // out[5] = length, turns, safety penalty, diagonal penalty, fitness
 // ---------------------------------------------------------------------------------------------
 struct StatsCtx {
@@ -14,8 +14,8 @@ struct StatsCtx {
     mpp_policy pol;
 };
 
-static __device__ void path_stats_warp(const StatsCtx &X, const int32_t *cells, int n, double *out) {
-    const int lane = threadIdx.x & 31;
+static __device__ void path_stats_warp(const LaneGroup &L, const StatsCtx &X, const int32_t *cells, int n, double *out) {
+    const int lane = L.gl;
     const double INF = __longlong_as_double(MPP_INF_BITS);
     if (n <= 0) {                                                        // helper.py:104-105
         if (lane == 0) { out[0] = INF; out[1] = 0.0; out[2] = 0.0; out[3] = 0.0; out[4] = INF; }
@@ -25,7 +25,7 @@ static __device__ void path_stats_warp(const StatsCtx &X, const int32_t *cells, 
     double f = 0.0, comp = 0.0, saf = 0.0;
     int turns = 0, ndiag = 0;
     const bool want_safety = (X.pol.mode == 0) && X.cls != nullptr;
-    for (int base = 0; base < n; base += 32) {
+    for (int base = 0; base < n; base += MPP_GL) {
         const int i = base + lane;
         const int c0 = i < n ? cells[i] : 0;
         const int c1 = (i + 1) < n ? cells[i + 1] : c0;
@@ -44,13 +44,13 @@ static __device__ void path_stats_warp(const StatsCtx &X, const int32_t *cells, 
         }
         double pen = 0.0;
         if (want_safety && i < n) pen = X.lut[X.cls[c0]];               // helper.py:70-79
-        turns += __popc(__ballot_sync(0xffffffffu, is_turn));
-        ndiag += __popc(__ballot_sync(0xffffffffu, is_diag_cut));
+        turns += __popc(grp_ballot(L, is_turn));
+        ndiag += __popc(grp_ballot(L, is_diag_cut));
         // sequential folds in path order (fp64 addition is not associative)
-        const int cnt = (n - base) < 32 ? (n - base) : 32;
+        const int cnt = (n - base) < MPP_GL ? (n - base) : MPP_GL;
         for (int l = 0; l < cnt; ++l) {
-            const double xl = __shfl_sync(0xffffffffu, x, l);
-            const double pl = __shfl_sync(0xffffffffu, pen, l);
+            const double xl = grp_shfl(L, x, l);
+            const double pl = grp_shfl(L, pen, l);
             const int gi = base + l;
             if (gi + 1 < n) {
                 if (gi == 0) f = xl;                                    // 0 + x0 leaves CPython's int fast path

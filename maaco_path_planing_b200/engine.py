@@ -135,13 +135,24 @@ class SearchEngine:
             ncell = t.empty(N, dtype=t.int32, device=self.device)
             stats = t.empty((N, 5), dtype=t.float64, device=self.device)
             visited = t.empty((N, self.words), dtype=t.int32, device=self.device)
+            order = self._longest_first(wps) if N > slots // 2 and W > 0 else None
             _lib.check(_lib.lib().mpp_waypoint_fitness(
                 self.map.handle, _lib.ptr(wps), N, W, C.byref(policy), _lib.ptr(cells), self.max_cells,
                 _lib.ptr(ncell), _lib.ptr(stats), _lib.ptr(visited), _lib.ptr(scratch), scratch.numel(), slots,
-                self.heap_cap, _lib.ptr(self.counters), self._stream()), "mpp_waypoint_fitness")
+                self.heap_cap, _lib.ptr(self.counters), _lib.ptr(order), self._stream()), "mpp_waypoint_fitness")
             self.launches += 1
             if not retry or not self._grow_if_needed(ncell):
                 return cells, ncell, stats
+
+    def _longest_first(self, wps):
+        """Individuals ordered by the Euclidean length of their waypoint chain, longest first: the searches of a chain
+        cost roughly its length squared, and the evaluation ends with its slowest individual."""
+        t = self.torch
+        s, g = self.map.start_cell, self.map.target_cell
+        chain = t.cat([t.full_like(wps[:, :1], s), wps, t.full_like(wps[:, :1], g)], dim=1).to(t.float64)
+        r, c = t.div(chain, self.cols, rounding_mode="floor"), chain % self.cols
+        d = ((r[:, 1:] - r[:, :-1]) ** 2 + (c[:, 1:] - c[:, :-1]) ** 2).sqrt().sum(dim=1)
+        return t.argsort(d, descending=True).to(t.int32).contiguous()
 
     def _grow_if_needed(self, ncell):
         """Heap overflow (-1) or truncated paths (> max_cells) -> enlarge and tell the caller to repeat."""

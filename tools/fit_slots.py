@@ -2,6 +2,9 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+from maaco_path_planing_b200 import _lib
+if os.environ.get('MPP_SO'):
+    _lib.SO_PATH = os.environ['MPP_SO']
 from maaco_path_planing_b200 import GridMap, blocks_map
 from maaco_path_planing_b200.engine import SearchEngine, make_policy
 size, N, W = 512, int(sys.argv[1]) if len(sys.argv) > 1 else 4096, 5
@@ -12,7 +15,8 @@ wps = torch.as_tensor(free[rng.integers(0, len(free), (N, W))].astype(np.int32),
 pol = make_policy(0.3, 0.8, 1.8, 100.0)
 gm = GridMap(grid)
 for slots in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["3552", "1776", "888"])]:
-    eng = SearchEngine(gm, n_slots=slots)
+    eng = SearchEngine(gm, n_slots=slots if slots > 0 else None)
+    slots = eng.n_slots
     eng.waypoint_fitness(wps[:256], pol)
     torch.cuda.synchronize(); eng.counters.zero_()
     t0 = time.perf_counter()

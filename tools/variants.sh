@@ -7,5 +7,5 @@ for v in "$@"; do
   i=$((i+1))
   nvcc $FLAGS $v -o /tmp/libv$i.so maaco_path_planing_b200/csrc/*.cu || exit 1
   echo "== variant $i: $v"
-  MPP_SO=/tmp/libv$i.so python tools/tour_time.py
+  MPP_SO=/tmp/libv$i.so ${VCMD:-python tools/tour_time.py}
 done
