@@ -761,7 +761,7 @@ extern "C" int mpp_maaco_tours(const mpp_map_batch *maps, const mpp_colony *c, i
     A.result = c->result; A.result_stride = (size_t)n_ants_total;
     A.steps = c->steps; A.latch = c->latch;
     // ants per warp: enough warps for every SM sub-partition first, full warps only for big colonies
-    int apw = 32;
+    int apw = 16;                                                  // measured (tools/batch_time.py): 16 beats 32 even at 131 k ants
     const char *e = getenv("MPP_TOUR_APW");
     if (e) apw = atoi(e);
     else if (ants_per_warp) apw = ants_per_warp;
