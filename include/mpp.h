@@ -184,10 +184,12 @@ int mpp_maaco_best(const mpp_map_batch *maps, const mpp_colony *colony, int move
  * obstacles <- 1e-9.  slabs_dev / touched_dev are laid out like colony->slabs / touched but cover buf_tile_rows tile rows
  * starting at tile_row0 and n_ants_total ants (single GPU: the colony's own buffers, tile_row0 = 0,
  * buf_tile_rows = TR; sharded: the receive buffers mpp_maaco_xunpack fills).  Clears the `touched` buffer of the next
- * pass, and (clear_slabs != 0) the slab words it read. */
+ * pass, and (clear_slabs != 0) the slab words it read.  tau_peers_dev (optional, sharded colony over NVLink peer memory):
+ * device array of n_peers pointers to every rank's pheromone field (this rank's included); the updated values are then
+ * stored straight into all of them -- the all-gather of the tau slices fused into the update -- instead of colony->tau. */
 int mpp_maaco_pheromone(const mpp_map_batch *maps, const mpp_colony *colony, uint32_t *slabs_dev, uint32_t *touched_dev,
                         int n_ants_total, int tile_row0, int buf_tile_rows, double rho, int iteration, int clear_slabs,
-                        void *stream);
+                        double *const *tau_peers_dev, int n_peers, void *stream);
 
 /* one whole pass of a non-sharded colony: rank + tours + best + pheromone, enqueued on `stream` (asynchronous) */
 int mpp_maaco_pass(const mpp_map_batch *maps, const mpp_colony *colony, const mpp_maaco_params *p, int iteration,
@@ -209,6 +211,9 @@ int mpp_maaco_pass_host(const mpp_map_batch *maps, const mpp_colony *colony, con
  *   [n_local x mpp_ant_result][int32 total code bytes + 12 pad bytes][codes: `capacity` bytes]
  * (mpp_maaco_xhdr_bytes(n_local) + capacity bytes; one all-gather moves it to every rank).
  * mpp_maaco_xpack   fills this rank's buffer from colony->result / moves (offsets_local_dev: n_local int32 scratch).
+ *   With peer_xbuf_dev (device array of n_peers pointers to every rank's gathered buffer, NVLink peer memory) it writes
+ *   slot `rank` of all of them directly instead -- the all-gather fused into the producer; the caller then only needs a
+ *   barrier between the ranks.
  * mpp_maaco_xunpack on the gathered buffers (n_seg = ranks, seg_ants = ants per rank): copies all results into
  *   colony->result, computes per-ant code offsets (offsets_dev: n_seg*seg_ants int32), replays every ant's codes into
  *   the receive slabs / touched of tile rows [tile_row0, tile_row0 + buf_tile_rows) -- the input of
@@ -218,7 +223,8 @@ int mpp_maaco_pass_host(const mpp_map_batch *maps, const mpp_colony *colony, con
  *   no-op until the host clears it and repeats the pass with more room. */
 long long mpp_maaco_xhdr_bytes(int n_local);
 int mpp_maaco_xpack(const mpp_map_batch *maps, const mpp_colony *colony, int ant_offset, int n_local, int n_ants_total,
-                    int32_t *offsets_local_dev, uint8_t *xbuf_local_dev, long long capacity, void *stream);
+                    int32_t *offsets_local_dev, uint8_t *xbuf_local_dev, long long capacity,
+                    uint8_t *const *peer_xbuf_dev, int n_peers, int rank, void *stream);
 int mpp_maaco_xunpack(const mpp_map_batch *maps, const mpp_colony *colony, const uint8_t *xbuf_all_dev, long long capacity,
                       int n_seg, int seg_ants, int iteration, int32_t *offsets_dev, int tile_row0, int buf_tile_rows,
                       uint32_t *slabs_recv_dev, uint32_t *touched_recv_dev, uint32_t *touched_local_dev, void *stream);

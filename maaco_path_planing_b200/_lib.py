@@ -74,13 +74,13 @@ _SIGS = {
                                 c_void_p]),
     "mpp_maaco_best": (c_int, [c_void_p, C.POINTER(Colony), c_int, c_int, c_int, c_double, c_int, c_void_p]),
     "mpp_maaco_pheromone": (c_int, [c_void_p, C.POINTER(Colony), c_void_p, c_void_p, c_int, c_int, c_int, c_double,
-                                    c_int, c_int, c_void_p]),
+                                    c_int, c_int, c_void_p, c_int, c_void_p]),
     "mpp_maaco_pass": (c_int, [c_void_p, C.POINTER(Colony), C.POINTER(MaacoParams), c_int, c_int, c_int, c_void_p]),
     "mpp_maaco_pass_host": (c_int, [c_void_p, C.POINTER(Colony), C.POINTER(MaacoParams), c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mpp_maaco_xhdr_bytes": (C.c_longlong, [c_int]),
     "mpp_maaco_xpack": (c_int, [c_void_p, C.POINTER(Colony), c_int, c_int, c_int, c_void_p, c_void_p, C.c_longlong,
-                                c_void_p]),
+                                c_void_p, c_int, c_int, c_void_p]),
     "mpp_maaco_xunpack": (c_int, [c_void_p, C.POINTER(Colony), c_void_p, C.c_longlong, c_int, c_int, c_int, c_void_p,
                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpp_map_safety_table": (c_int, [c_void_p, c_double, c_void_p]),

@@ -1077,7 +1077,9 @@ extern "C" int mpp_maaco_best(const mpp_map_batch *maps, const mpp_colony *c, in
 // ---------------------------------------------------------------------------------------------
 #define MPP_PHER_THREADS 256
 #define MPP_PHER_CHUNK 2048                   // ants per list-building round (64 bitmap words)
-struct __align__(16) PherEntry { double d; uint32_t w; uint32_t pad; };
+#ifndef MPP_PHER_WIDE
+#define MPP_PHER_WIDE 1                       // rounds of 32 ants a warp takes per trip
+#endif
 
 // MMAS clip + obstacle reset (MAACO.py:312-332) for one cell
 __device__ __forceinline__ double pher_finalize(double t, int r, int c, const uint32_t *occ, int pitch, int R, int C,
@@ -1109,16 +1111,56 @@ struct PherArgs {
     const mpp_maaco_state *state;
     int clear_slabs;                            // zero the slab words that were read (sharded colony: rebuilt by OR next pass)
     const int32_t *latch;
+    double *const *tau_peers; int n_peers;      // sharded colony over peer memory: every rank's tau (this rank's included)
+    const MppMapMeta *meta;
 };
 
-__global__ void __launch_bounds__(MPP_PHER_THREADS) mpp_maaco_pheromone_kernel(const PherArgs A) {
+#ifdef MPP_PHER_PROF
+__device__ unsigned long long g_pher_prof[8192 * 8];
+extern "C" int mpp_debug_pher_prof(unsigned long long *out) {
+    return cudaMemcpyFromSymbol(out, g_pher_prof, sizeof(g_pher_prof)) == cudaSuccess ? 0 : -1;
+}
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
+
+#ifndef MPP_PHER_MINB
+#define MPP_PHER_MINB 7
+#endif
+__global__ void __launch_bounds__(MPP_PHER_THREADS, MPP_PHER_MINB) mpp_maaco_pheromone_kernel(const PherArgs A) {
     __shared__ int s_list[MPP_PHER_CHUNK];
-    __shared__ PherEntry s_buf[MPP_PHER_THREADS / 32][32];
+#ifdef MPP_PHER_PROF
+    const unsigned long long prof_t0 = gtimer();
+    unsigned long long prof_hits = 0, prof_rounds = 0, prof_list = 0, prof_loop = 0, prof_tl = 0;
+#endif
+    __shared__ __align__(16) double s_dep[MPP_PHER_THREADS / 32][32 * MPP_PHER_WIDE];   // per warp: the deposits of a trip's ants
     __shared__ int s_wcnt[2];
     if (A.latch && *A.latch) return;
+#ifdef MPP_PHER_ONLY
+    if ((blockIdx.x >> 2) != MPP_PHER_ONLY) return;
+#endif
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, map = blockIdx.y;
     const int TC = (A.C + 31) >> 5;
-    const int tile_l = blockIdx.x >> 2, rg = blockIdx.x & 3;          // tile index inside the buffers, row group
+    // the start and the target tile carry the longest chains (every depositing ant): their CTAs go first
+    int tile_l = blockIdx.x >> 2;                                     // tile index inside the buffers
+    const int rg = blockIdx.x & 3;                                    // row group
+    {
+        const int nt = gridDim.x >> 2;
+        const MppMapMeta &MM = A.meta[map];
+        int h0 = ((MM.start / A.C >> 5) - A.tile_row0) * TC + (MM.start % A.C >> 5);
+        int h1 = ((MM.target / A.C >> 5) - A.tile_row0) * TC + (MM.target % A.C >> 5);
+        if (h0 < 0 || h0 >= nt) h0 = -1;
+        if (h1 < 0 || h1 >= nt || h1 == h0) h1 = -1;
+        if (h0 < 0) { h0 = h1; h1 = -1; }
+        const int nh = (h0 >= 0) + (h1 >= 0);
+        if (tile_l < nh) {
+            tile_l = tile_l == 0 ? h0 : h1;
+        } else {
+            const int lo = (nh == 2 && h1 < h0) ? h1 : h0, hi = (nh == 2 && h1 < h0) ? h0 : h1;
+            tile_l -= nh;
+            if (nh >= 1 && tile_l >= lo) ++tile_l;
+            if (nh == 2 && tile_l >= hi) ++tile_l;
+        }
+    }
     const int trow = A.tile_row0 + tile_l / TC, tcx = tile_l % TC;
     const int row_in_tile = rg * 8 + wid;
     const int r = (trow << 5) + row_in_tile, c = (tcx << 5) + lane;
@@ -1131,10 +1173,12 @@ __global__ void __launch_bounds__(MPP_PHER_THREADS) mpp_maaco_pheromone_kernel(c
     const double *dep = A.deposit + (size_t)map * A.n_ants;
     double t = 0.0;
     if (live) t = tau[(size_t)r * A.C + c] * (1.0 - A.rho);            // :305
-    PherEntry *sb = s_buf[wid];
-    const uint32_t lt = (1u << lane) - 1u;
+    double *sd = s_dep[wid];
     for (int w0 = 0; w0 < NW; w0 += MPP_PHER_CHUNK / 32) {
         // ---- the ants of this chunk that have a slab here and deposit, in index order ----
+#ifdef MPP_PHER_PROF
+        prof_tl = gtimer();
+#endif
         int cnt = 0;
         uint32_t bits = 0u;
         if (wid < 2) {
@@ -1155,52 +1199,106 @@ __global__ void __launch_bounds__(MPP_PHER_THREADS) mpp_maaco_pheromone_kernel(c
             while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; s_list[o++] = abase + b; }
         }
         __syncthreads();
-        // ---- this warp's row: words of those ants, 32 per round, the next round in flight during the fold ----
-        int a_n = (lane < k) ? s_list[lane] : 0;
-        uint32_t w_n = (lane < k) ? __ldcg(slab_t + (size_t)a_n * 32) : 0u;
-        double d_n = (lane < k) ? dep[a_n] : 0.0;
-        for (int base = 0; base < k; base += 32) {
-            const uint32_t word = w_n;
-            const double d = d_n;
-            const int a_c = a_n;
-            const int i = base + 32 + lane;
+#ifdef MPP_PHER_PROF
+        { const unsigned long long g_ = gtimer(); prof_list += g_ - prof_tl; prof_tl = g_; }
+#endif
+        // ---- this warp's row.  A round = 32 ants of the list: lane i loads the row word of the i-th ant's slab and its
+        //      deposit (the next trip's loads are in flight during this one); the 32x32 bit matrix (ant x cell) is transposed across
+        //      the warp, so that lane c (= cell c of the row) holds the set of ants that visited ITS cell, and each lane
+        //      adds the deposits of its own ants in index order (:306, :311).  Near the start and the target every ant
+        //      crosses the same few cells, so some lane usually has all 32 bits set and a round lasts 32 dependent adds
+        //      whatever the form: the fold is straight-line DADDs whose OPERAND is selected (t + 0.0 == t exactly; the
+        //      loop-carried chain is the bare add, 8.2 cycles each: tools/ubench/dadd_chain.cu), the deposits come from
+        //      broadcast 16-byte shared-memory loads.  tools/ubench/fold_round.cu times the forms that were tried
+        //      (compacted (word, deposit) lists with every lane adding every entry: 27-36 cycles per add; this: 14). ----
+        // A trip of the loop takes MPP_PHER_WIDE rounds at once: their loads, transposes and shared-memory traffic are
+        // independent and overlap, only the adds stay in sequence.
+        int a_n[MPP_PHER_WIDE];
+        uint32_t w_n[MPP_PHER_WIDE];
+        double d_n[MPP_PHER_WIDE];
+        auto fetch = [&](int i, int &a, uint32_t &w, double &d) {
+            a = 0; w = 0u; d = 0.0;
             if (i < k) {
-                a_n = s_list[i];
-                w_n = __ldcg(slab_t + (size_t)a_n * 32);
-                d_n = dep[a_n];
-            } else {
-                w_n = 0u;
+                a = s_list[i];
+                w = slab_t[(size_t)a * 32];    // (plain load: the 8 row warps of the CTA read the same 32-byte sector)
+                d = dep[a];
             }
-            const uint32_t nz = __ballot_sync(0xffffffffu, word != 0u);
-            if (!nz) continue;
-            if (word != 0u) {
-                PherEntry e; e.d = d; e.w = word; e.pad = 0u;
-                sb[__popc(nz & lt)] = e;
-                if (A.clear_slabs) slab_t[(size_t)a_c * 32] = 0u;
+        };
+#pragma unroll
+        for (int u = 0; u < MPP_PHER_WIDE; ++u) fetch(u * 32 + lane, a_n[u], w_n[u], d_n[u]);
+        for (int base = 0; base < k; base += 32 * MPP_PHER_WIDE) {
+            int a_c[MPP_PHER_WIDE];
+            uint32_t m[MPP_PHER_WIDE], nz[MPP_PHER_WIDE], any = 0u;
+            double d_c[MPP_PHER_WIDE];
+#pragma unroll
+            for (int u = 0; u < MPP_PHER_WIDE; ++u) {
+                a_c[u] = a_n[u]; m[u] = w_n[u]; d_c[u] = d_n[u];
+                fetch(base + 32 * MPP_PHER_WIDE + u * 32 + lane, a_n[u], w_n[u], d_n[u]);   // the next trip's, in flight during this one
+                nz[u] = __ballot_sync(0xffffffffu, m[u] != 0u);
+                any |= nz[u];
+            }
+            if (!any) continue;
+#pragma unroll
+            for (int u = 0; u < MPP_PHER_WIDE; ++u) {
+                if (A.clear_slabs && m[u] != 0u) slab_t[(size_t)a_c[u] * 32] = 0u;
+                sd[32 * u + lane] = d_c[u];
+            }
+#pragma unroll
+            for (int j = 16, mk = 0x0000FFFF; j; j >>= 1, mk ^= mk << j) {
+#pragma unroll
+                for (int u = 0; u < MPP_PHER_WIDE; ++u) {
+                    const uint32_t y = __shfl_xor_sync(0xffffffffu, m[u], j);
+                    m[u] = (lane & j) ? ((m[u] & ~(uint32_t)mk) | ((y >> j) & (uint32_t)mk)) : ((m[u] & (uint32_t)mk) | ((y << j) & ~(uint32_t)mk));
+                }
             }
             __syncwarp();
-            const int n = __popc(nz);
-            int q = 0;
-            for (; q + 4 <= n; q += 4) {
-                // select the operand, not the sum: the loop-carried chain is a bare DADD (t + 0.0 == t exactly)
-                const PherEntry x0 = sb[q], x1 = sb[q + 1], x2 = sb[q + 2], x3 = sb[q + 3];
-                const double a0 = ((x0.w >> lane) & 1u) ? x0.d : 0.0, a1 = ((x1.w >> lane) & 1u) ? x1.d : 0.0;
-                const double a2 = ((x2.w >> lane) & 1u) ? x2.d : 0.0, a3 = ((x3.w >> lane) & 1u) ? x3.d : 0.0;
-                t += a0;                                                     // :311, ants in index order :306
-                t += a1;
-                t += a2;
-                t += a3;
-            }
-            for (; q < n; ++q) {
-                const PherEntry x = sb[q];
-                t += ((x.w >> lane) & 1u) ? x.d : 0.0;
+#pragma unroll
+            for (int u = 0; u < MPP_PHER_WIDE; ++u) {
+#ifdef MPP_PHER_PROF
+                prof_hits += __popc(nz[u]); prof_rounds += 1;
+#endif
+                const double2 *sd2 = (const double2 *)(sd + 32 * u);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (!(nz[u] & (0xFFu << (8 * g)))) continue;       // (warp-uniform) none of these eight ants has a word here
+                    const double2 v0 = sd2[4 * g], v1 = sd2[4 * g + 1], v2 = sd2[4 * g + 2], v3 = sd2[4 * g + 3];
+                    const uint32_t mg = m[u] >> (8 * g);
+                    const double a0 = (mg & 1u) ? v0.x : 0.0, a1 = (mg & 2u) ? v0.y : 0.0, a2 = (mg & 4u) ? v1.x : 0.0;
+                    const double a3 = (mg & 8u) ? v1.y : 0.0, a4 = (mg & 16u) ? v2.x : 0.0, a5 = (mg & 32u) ? v2.y : 0.0;
+                    const double a6 = (mg & 64u) ? v3.x : 0.0, a7 = (mg & 128u) ? v3.y : 0.0;
+                    t += a0;
+                    t += a1;
+                    t += a2;
+                    t += a3;
+                    t += a4;
+                    t += a5;
+                    t += a6;
+                    t += a7;
+                }
             }
             __syncwarp();
         }
+#ifdef MPP_PHER_PROF
+        prof_loop += gtimer() - prof_tl;
+#endif
         __syncthreads();                                               // s_list is rebuilt by the next chunk
     }
-    if (live) tau[(size_t)r * A.C + c] = pher_finalize(t, r, c, A.occ + (size_t)map * A.occ_words, A.pitch, A.R, A.C, A.rho,
-                                                      A.state + map);
+    if (live) {
+        const double v = pher_finalize(t, r, c, A.occ + (size_t)map * A.occ_words, A.pitch, A.R, A.C, A.rho, A.state + map);
+        if (A.tau_peers) {
+            // fused with the "all-gather" of the tau slices: the value goes straight into every rank's field (NVLink stores)
+            for (int k = 0; k < A.n_peers; ++k) A.tau_peers[k][(size_t)r * A.C + c] = v;
+        } else {
+            tau[(size_t)r * A.C + c] = v;
+        }
+    }
+#ifdef MPP_PHER_PROF
+    if (lane == 0 && blockIdx.y == 0 && blockIdx.x * 8 + wid < 8192) {
+        unsigned long long *o = g_pher_prof + (size_t)(blockIdx.x * 8 + wid) * 8;
+        o[0] = prof_t0; o[1] = gtimer(); o[2] = prof_hits; o[3] = prof_rounds;
+        o[4] = prof_list; o[5] = prof_loop; o[6] = o[7] = 0;
+    }
+#endif
     // the bitmaps the NEXT pass will fill are the ones the previous pass consumed: clear this tile's share
     {
         uint32_t *tn = A.touched_next + (size_t)map * A.touched_stride + (size_t)tile_l * NW;
@@ -1210,7 +1308,7 @@ __global__ void __launch_bounds__(MPP_PHER_THREADS) mpp_maaco_pheromone_kernel(c
 
 extern "C" int mpp_maaco_pheromone(const mpp_map_batch *maps, const mpp_colony *c, uint32_t *slabs_dev, uint32_t *touched_dev,
                                    int n_ants_total, int tile_row0, int buf_tile_rows, double rho, int iteration,
-                                   int clear_slabs, void *stream) {
+                                   int clear_slabs, double *const *tau_peers_dev, int n_peers, void *stream) {
     int rc = colony_check(maps, c, "mpp_maaco_pheromone");
     if (rc) return rc;
     const int TR = tiles_r(maps->rows), TC = tiles_c(maps->cols);
@@ -1233,6 +1331,9 @@ extern "C" int mpp_maaco_pheromone(const mpp_map_batch *maps, const mpp_colony *
     A.deposit = c->deposit; A.okbits = c->okbits; A.n_ants = n_ants_total;
     A.tile_row0 = tile_row0; A.rho = rho; A.state = c->state; A.clear_slabs = clear_slabs;
     A.latch = c->latch;
+    A.tau_peers = tau_peers_dev; A.n_peers = n_peers;
+    A.meta = maps->meta_dev;
+    MPP_REQUIRE(!tau_peers_dev || (n_peers > 0 && maps->n_maps == 1), "mpp_maaco_pheromone: peer tau needs n_peers > 0 and one map");
     mpp_maaco_pheromone_kernel<<<dim3(n_tile_rows * TC * 4, maps->n_maps), MPP_PHER_THREADS, 0, (cudaStream_t)stream>>>(A);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
@@ -1279,19 +1380,26 @@ __device__ __forceinline__ void xscan_segment(const mpp_ant_result *__restrict__
 }
 
 // step 1 on the sending rank: header (results + total) and the offsets of the local ants
+// (peers != null: the buffer is written straight into slot `peer_off` of every rank's receive buffer -- the
+// "all-gather" fused into the producer over NVLink peer memory; peers == null: into this rank's send buffer xbuf)
 __global__ void __launch_bounds__(1024) mpp_maaco_xpack_scan_kernel(const mpp_ant_result *__restrict__ res_local, int n_local,
                                                                     int32_t *__restrict__ offsets_local, uint8_t *__restrict__ xbuf,
+                                                                    uint8_t *const *__restrict__ peers, int n_peers, size_t peer_off,
                                                                     const int32_t *__restrict__ latch) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     if (latch && *latch) return;
     int total;
     xscan_segment(res_local, n_local, offsets_local, s_warp, &s_carry, &total);
-    mpp_ant_result *hdr = (mpp_ant_result *)xbuf;
-    for (int a = threadIdx.x; a < n_local; a += 1024) hdr[a] = res_local[a];
-    if (threadIdx.x == 0) {
-        int32_t *tail = (int32_t *)(xbuf + (size_t)16 * n_local);
-        tail[0] = total; tail[1] = 0; tail[2] = 0; tail[3] = 0;
+    const int nd = peers ? n_peers : 1;
+    for (int k = 0; k < nd; ++k) {
+        uint8_t *dst = peers ? peers[k] + peer_off : xbuf;
+        mpp_ant_result *hdr = (mpp_ant_result *)dst;
+        for (int a = threadIdx.x; a < n_local; a += 1024) hdr[a] = res_local[a];
+        if (threadIdx.x == 0) {
+            int32_t *tail = (int32_t *)(dst + (size_t)16 * n_local);
+            tail[0] = total; tail[1] = 0; tail[2] = 0; tail[3] = 0;
+        }
     }
 }
 
@@ -1301,6 +1409,7 @@ __global__ void __launch_bounds__(256) mpp_maaco_xpack_copy_kernel(const uint8_t
                                                                    const mpp_ant_result *__restrict__ res_local,
                                                                    const int32_t *__restrict__ offsets_local, int n_local,
                                                                    uint8_t *__restrict__ xbuf, long long cap,
+                                                                   uint8_t *const *__restrict__ peers, int n_peers, size_t peer_off,
                                                                    const int32_t *__restrict__ latch) {
     if (latch && *latch) return;
     const int a = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1310,8 +1419,11 @@ __global__ void __launch_bounds__(256) mpp_maaco_xpack_copy_kernel(const uint8_t
     const long long off = offsets_local[a];
     if (n - 1 > max_cells || off + (n - 1) > cap) return;
     const uint8_t *src = moves + (size_t)a * max_cells;
-    uint8_t *dst = xbuf + MPP_XHDR(n_local) + off;
-    for (int i = lane; i < n - 1; i += 32) dst[i] = src[i];
+    const int nd = peers ? n_peers : 1;
+    for (int i = lane; i < n - 1; i += 32) {
+        const uint8_t v = src[i];
+        for (int k = 0; k < nd; ++k) ((peers ? peers[k] + peer_off : xbuf) + MPP_XHDR(n_local) + off)[i] = v;
+    }
 }
 
 // step 3 on every rank after the all-gather: results of all segments into the contiguous table, per-ant code offsets,
@@ -1389,17 +1501,22 @@ __global__ void __launch_bounds__(256) mpp_maaco_rebuild_kernel(const uint8_t *_
 extern "C" long long mpp_maaco_xhdr_bytes(int n_local) { return (long long)MPP_XHDR(n_local); }
 
 extern "C" int mpp_maaco_xpack(const mpp_map_batch *maps, const mpp_colony *c, int ant_offset, int n_local, int n_ants_total,
-                               int32_t *offsets_local_dev, uint8_t *xbuf_local_dev, long long capacity, void *stream) {
+                               int32_t *offsets_local_dev, uint8_t *xbuf_local_dev, long long capacity,
+                               uint8_t *const *peer_xbuf_dev, int n_peers, int rank, void *stream) {
     int rc = colony_check(maps, c, "mpp_maaco_xpack");
     if (rc) return rc;
     MPP_REQUIRE(maps->n_maps == 1, "mpp_maaco_xpack: a sharded colony is one map");
-    MPP_REQUIRE(offsets_local_dev && xbuf_local_dev && n_local > 0 && capacity >= 0 && ant_offset + n_local <= n_ants_total,
-                "mpp_maaco_xpack: bad argument");
+    MPP_REQUIRE(offsets_local_dev && (xbuf_local_dev || peer_xbuf_dev) && n_local > 0 && capacity >= 0 &&
+                    ant_offset + n_local <= n_ants_total, "mpp_maaco_xpack: bad argument");
+    MPP_REQUIRE(!peer_xbuf_dev || (n_peers > 0 && rank >= 0 && rank < n_peers), "mpp_maaco_xpack: bad peer arguments");
+    const size_t peer_off = (size_t)rank * (MPP_XHDR(n_local) + (size_t)capacity);   // this rank's slot in every receive buffer
     MPP_CUDA(cudaSetDevice(maps->device));
     cudaStream_t s = (cudaStream_t)stream;
-    mpp_maaco_xpack_scan_kernel<<<1, 1024, 0, s>>>(c->result + ant_offset, n_local, offsets_local_dev, xbuf_local_dev, c->latch);
+    mpp_maaco_xpack_scan_kernel<<<1, 1024, 0, s>>>(c->result + ant_offset, n_local, offsets_local_dev, xbuf_local_dev,
+                                                   peer_xbuf_dev, n_peers, peer_off, c->latch);
     mpp_maaco_xpack_copy_kernel<<<(n_local + 7) / 8, 256, 0, s>>>(c->moves, c->max_cells, c->result + ant_offset,
-                                                                  offsets_local_dev, n_local, xbuf_local_dev, capacity, c->latch);
+                                                                  offsets_local_dev, n_local, xbuf_local_dev, capacity,
+                                                                  peer_xbuf_dev, n_peers, peer_off, c->latch);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
@@ -1446,7 +1563,7 @@ extern "C" int mpp_maaco_pass(const mpp_map_batch *maps, const mpp_colony *c, co
     if (rc) return rc;
     rc = mpp_maaco_best(maps, c, 0, n_ants, n_ants, p->Q, iteration, stream);
     if (rc) return rc;
-    return mpp_maaco_pheromone(maps, c, c->slabs, c->touched, n_ants, 0, tiles_r(maps->rows), p->rho, iteration, 0, stream);
+    return mpp_maaco_pheromone(maps, c, c->slabs, c->touched, n_ants, 0, tiles_r(maps->rows), p->rho, iteration, 0, nullptr, 0, stream);
 }
 
 extern "C" int mpp_maaco_pass_host(const mpp_map_batch *maps, const mpp_colony *c, const mpp_maaco_params *p, int iteration,

@@ -111,10 +111,18 @@ class MAACO:
         if max_cells is None:
             max_cells = min(n, max(1024, 8 * (R + Cc)))
         self.max_cells = int(max_cells)
+        self.max_cells_hint = self.max_cells
         dev = self.device
         f64, i32, i64, u8 = torch.float64, torch.int32, torch.int64, torch.uint8
         nl = self.n_local
-        self._tau = torch.zeros(npad, dtype=f64, device=dev)        # padded so tau slices all-gather evenly
+        self._p2p = None
+        if self.world > 1 and os.environ.get("MPP_P2P", "1") != "0":
+            self._p2p = self._setup_peer_memory(npad)                # NVLink peer memory for the two exchanges (or None)
+        if self._p2p is not None:
+            self._tau = self._p2p["tau"]
+            self._tau.zero_()
+        else:
+            self._tau = torch.zeros(npad, dtype=f64, device=dev)    # padded so tau slices all-gather evenly
         self._E01 = torch.empty(2 * n, dtype=f64, device=dev)       # eta'**beta, interleaved by turn flag
         self._dist_t = torch.empty(n, dtype=f64, device=dev)
         self._rank = torch.empty(L.mpp_maaco_rank_words(R, Cc), dtype=i32, device=dev)
@@ -150,8 +158,13 @@ class MAACO:
             # headers); an overflow raises the device latch and the pass is repeated with more room
             self._cap_max = _round64k(nl * min(self.max_cells, max(64, 2 * (R + Cc))))
             self._cap = self._cap_max
-            self._xbuf_local = torch.zeros(self._xhdr + self._cap_max, dtype=u8, device=dev)
-            self._xbuf_all = torch.zeros(self.world * (self._xhdr + self._cap_max), dtype=u8, device=dev)
+            if self._p2p is not None:
+                self._xbuf_local = None                              # every rank writes straight into the peers' buffers
+                self._xbuf_all = self._p2p["xbuf"]
+                self._xbuf_all.zero_()
+            else:
+                self._xbuf_local = torch.zeros(self._xhdr + self._cap_max, dtype=u8, device=dev)
+                self._xbuf_all = torch.zeros(self.world * (self._xhdr + self._cap_max), dtype=u8, device=dev)
             self._ring = [torch.zeros(self.world + 1, dtype=i32).pin_memory() for _ in range(4)]
             self._ring_ev = [None] * 4
             self._ring_cap = [0] * 4
@@ -169,6 +182,35 @@ class MAACO:
         self.convergence_curve_data = []
         self._iter_done = 0
         self.kernel_launches = 0
+
+    def _setup_peer_memory(self, npad):
+        """Symmetric (peer-mapped) allocations for the sharded colony's two exchanges: every rank's receive buffer of the
+        tours and every rank's pheromone field, each addressable from all ranks over NVLink.  Then the producers write
+        straight into the peers (mpp_maaco_xpack / mpp_maaco_pheromone with peer pointers) and a pass needs two
+        device-side barriers instead of two NCCL all-gathers.  Returns None when the platform cannot map peer memory
+        (the NCCL all-gathers are then used; same results)."""
+        import torch
+        import torch.distributed as dist
+        ok = 1
+        out = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nl, R, Cc = self.n_local, self.rows, self.cols
+            xhdr = int(_lib.lib().mpp_maaco_xhdr_bytes(nl))
+            cap = _round64k(nl * min(self.max_cells_hint, max(64, 2 * (R + Cc))))
+            xbuf = symm.empty(self.world * (xhdr + cap), dtype=torch.uint8, device=self.device)
+            tau = symm.empty(npad, dtype=torch.float64, device=self.device)
+            hx = symm.rendezvous(xbuf, self.group)
+            ht = symm.rendezvous(tau, self.group)
+            xp = torch.tensor([int(p) for p in hx.buffer_ptrs], dtype=torch.int64, device=self.device)
+            tp = torch.tensor([int(p) for p in ht.buffer_ptrs], dtype=torch.int64, device=self.device)
+            out = dict(xbuf=xbuf, tau=tau, hx=hx, ht=ht, xpeers=xp, tpeers=tp)
+        except Exception as e:                                       # noqa: BLE001 -- any failure = no peer memory here
+            ok = 0
+            self._p2p_error = f"{type(e).__name__}: {e}"
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)   # all ranks or none
+        return out if int(flag.item()) == 1 else None
 
     # ---- reference attributes materialised from device state ------------------------------
     @property
@@ -203,13 +245,23 @@ class MAACO:
         stream = C.c_void_p(cur.cuda_stream)
         col = C.byref(self._colony)
         nl, off, N = self.n_local, self.ant_offset, self.num_ants
+        plog = getattr(self, "_phase_log", None)                      # tools/shard_time.py: [(phase, event)] per pass
+
+        def mark(name):
+            if plog is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(cur)
+                plog.append((name, ev))
+        mark("start")
         if events:
             events[0].record(cur)
         _lib.check(L.mpp_maaco_rank(self._maps, col, self.alpha, stream), "mpp_maaco_rank")
+        mark("rank")
         if events and len(events) > 4:
             events[4].record(cur)
         _lib.check(L.mpp_maaco_tours(self._maps, col, it, self._calculate_adaptive_q0(it), self.alpha, nl, off, N,
                                      self._apw, stream), "mpp_maaco_tours")
+        mark("tours")
         if events:
             events[1].record(cur)
         if self.world == 1:
@@ -217,27 +269,45 @@ class MAACO:
             if events:
                 events[2].record(cur)
             _lib.check(L.mpp_maaco_pheromone(self._maps, col, _lib.ptr(self._slabs), _lib.ptr(self._touched), N, 0,
-                                             self.tile_rows, self.rho, it, 0, stream), "mpp_maaco_pheromone")
+                                             self.tile_rows, self.rho, it, 0, None, 0, stream), "mpp_maaco_pheromone")
             self.kernel_launches += 4
         else:
-            cap = self._cap
+            p2p = self._p2p
+            cap = self._cap_max if p2p is not None else self._cap     # peer memory: no collective to size, fixed slots
             seg = self._xhdr + cap
             _lib.check(L.mpp_maaco_xpack(self._maps, col, off, nl, N, _lib.ptr(self._offsets_local),
-                                         _lib.ptr(self._xbuf_local), cap, stream), "mpp_maaco_xpack")
-            # ONE all-gather per pass carries the results and the tours (move codes) of every rank
-            dist_mod.exchange_buffers(self._xbuf_all[:self.world * seg], self._xbuf_local[:seg], self.group)
+                                         _lib.ptr(self._xbuf_local), cap, _lib.ptr(p2p["xpeers"]) if p2p else None,
+                                         self.world, self.rank, stream), "mpp_maaco_xpack")
+            mark("xpack")
+            if p2p is not None:
+                # the pack kernels wrote this rank's results + tours into every peer's buffer: one device-side barrier
+                # (also: every rank is past its tours, so the update may now overwrite the peers' tau)
+                p2p["hx"].barrier(channel=0)
+            else:
+                # ONE all-gather per pass carries the results and the tours (move codes) of every rank
+                dist_mod.exchange_buffers(self._xbuf_all[:self.world * seg], self._xbuf_local[:seg], self.group)
+            mark("exchange")
             tr = self.tile_rows_per_rank
             _lib.check(L.mpp_maaco_xunpack(self._maps, col, _lib.ptr(self._xbuf_all), cap, self.world, nl, it,
                                            _lib.ptr(self._offsets), self.rank * tr, tr, _lib.ptr(self._slabs_recv),
                                            _lib.ptr(self._touched_recv), _lib.ptr(self._touched), stream),
                        "mpp_maaco_xunpack")
+            mark("xunpack")
             _lib.check(L.mpp_maaco_best(self._maps, col, off, nl, N, self.Q, it, stream), "mpp_maaco_best")
+            mark("best")
             if events:
                 events[2].record(cur)
             _lib.check(L.mpp_maaco_pheromone(self._maps, col, _lib.ptr(self._slabs_recv), _lib.ptr(self._touched_recv),
-                                             N, self.rank * tr, tr, self.rho, it, 1, stream), "mpp_maaco_pheromone")
-            sl = tr * 32 * self.cols
-            dist_mod.gather_tau(self._tau, self._tau[self.rank * sl:(self.rank + 1) * sl], self.group)
+                                             N, self.rank * tr, tr, self.rho, it, 1,
+                                             _lib.ptr(p2p["tpeers"]) if p2p else None, self.world, stream),
+                       "mpp_maaco_pheromone")
+            mark("pheromone")
+            if p2p is not None:
+                p2p["ht"].barrier(channel=0)                           # every rank's slice has landed in every field
+            else:
+                sl = tr * 32 * self.cols
+                dist_mod.gather_tau(self._tau, self._tau[self.rank * sl:(self.rank + 1) * sl], self.group)
+            mark("tau exchange")
             # what the host needs two passes later: every segment's code total (from the gathered headers) + the latch
             slot = it & 3
             hdr_tot = self._xbuf_all.view(torch.int32).as_strided((self.world,), (seg // 4,), (16 * nl) // 4)
@@ -279,7 +349,12 @@ class MAACO:
             raise _PathOverflow()
         self._cap_max = max(self._cap_max, _round64k(2 * max(totals)))
         self._cap = self._cap_max
-        if self._xbuf_local.numel() < self._xhdr + self._cap_max:
+        if self._p2p is not None:
+            # the peer-mapped receive buffers have a fixed size: from here on the tours travel by NCCL all-gather
+            # (tau stays where it is: a symmetric allocation is an ordinary local tensor as well)
+            self._p2p = None
+            self._xbuf_local = None
+        if self._xbuf_local is None or self._xbuf_local.numel() < self._xhdr + self._cap_max:
             self._xbuf_local = torch.zeros(self._xhdr + self._cap_max, dtype=torch.uint8, device=self.device)
             self._xbuf_all = torch.zeros(self.world * (self._xhdr + self._cap_max), dtype=torch.uint8, device=self.device)
         self._latch.zero_()

@@ -335,7 +335,7 @@ def test_pheromone_kernel_vs_numpy_and_tile_row_slices():
     tb = torch.zeros(2 * TR * TC * NW, dtype=torch.int32, device=dev)
     tb[TR * TC * NW:].copy_(torch.as_tensor(touched.view(np.int32).reshape(-1)))      # parity it & 1 = 1
     tb[:TR * TC * NW] = -1                                                # the other parity must come back cleared
-    _lib.check(L.mpp_maaco_pheromone(m._maps, C.byref(m._colony), _lib.ptr(sl), _lib.ptr(tb), N, 0, TR, 0.1, it, 0, stream),
+    _lib.check(L.mpp_maaco_pheromone(m._maps, C.byref(m._colony), _lib.ptr(sl), _lib.ptr(tb), N, 0, TR, 0.1, it, 0, None, 0, stream),
                "mpp_maaco_pheromone")
     got = m._tau[:R * Cc].cpu().numpy()
     assert np.array_equal(got, want)
@@ -353,7 +353,7 @@ def test_pheromone_kernel_vs_numpy_and_tile_row_slices():
         d_sl = torch.as_tensor(s_sl.view(np.int32).reshape(-1), device=dev)
         d_tb = torch.as_tensor(s_tb.view(np.int32).reshape(-1), device=dev)
         _lib.check(L.mpp_maaco_pheromone(m._maps, C.byref(m._colony), _lib.ptr(d_sl), _lib.ptr(d_tb), N, row0, per, 0.1, it, 1,
-                                         stream), "mpp_maaco_pheromone")
+                                         None, 0, stream), "mpp_maaco_pheromone")
         # what was read (slabs of depositing ants) has been cleared
         left = d_sl.cpu().numpy().view(np.uint32).reshape(per * TC, N, 32)
         assert not left[:, dep != 0.0].any()
