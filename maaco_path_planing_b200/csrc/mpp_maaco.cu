@@ -135,15 +135,18 @@ extern "C" int mpp_maaco_tables(const mpp_map_batch *maps, const mpp_maaco_param
 // sizes
 // ---------------------------------------------------------------------------------------------
 // Ranking buffer layout (uint32 words): [margin | 9*R*C strategy-1 words | margin | pad to even] [9*R*C full entries
-// (2 words)] [pad to 4] [R*C bundles of 4 words: word2 of the three cells P1's moves lead to, ready for one 16-byte load].
-// The margins let the tour kernel read the word of a neighbour cell without bounds checks.
-struct RankLayout { size_t margin, fast_words, bundle_words, total_words; };
+// (2 words)] [pad to 4] [R*C bundles of 4 words: word2 of the three cells P1's moves lead to, ready for one 16-byte load]
+// [R*C x 8 bytes: for each of the eight moves the packed word2 of the cell it leads to (context = that move), what a
+// tier-3 step needs to go on without a dependent load].  The margins let the tour kernel read the word of a neighbour
+// cell without bounds checks.
+struct RankLayout { size_t margin, fast_words, bundle_words, nb8_words, total_words; };
 static RankLayout rank_layout(int R, int C) {
     RankLayout L;
     L.margin = (size_t)(C + 2) * 9;
     L.fast_words = ((size_t)9 * R * C + 2 * L.margin + 1) & ~(size_t)1;
     L.bundle_words = (L.fast_words + (size_t)18 * R * C + 3) & ~(size_t)3;
-    L.total_words = L.bundle_words + (size_t)4 * R * C;
+    L.nb8_words = L.bundle_words + (size_t)4 * R * C;
+    L.total_words = L.nb8_words + (size_t)2 * R * C;
     return L;
 }
 static inline int tiles_r(int R) { return (R + 31) >> 5; }
@@ -182,7 +185,7 @@ extern "C" long long mpp_maaco_touched_words(int tile_rows, int cols, int n_ants
 struct TourArgs {
     const MppMapMeta *meta;      // [n_maps]
     const uint32_t *rank;        // [n_maps][rank_stride] ranking buffers (mpp_maaco_rank), layout: rank_layout()
-    size_t rank_stride, rank_margin, rank_fast_words, rank_bundle_words;
+    size_t rank_stride, rank_margin, rank_fast_words, rank_bundle_words, rank_nb8_words;
     int R, C;
     const double *tau, *E01;
     size_t tau_stride, E01_stride;
@@ -337,6 +340,7 @@ struct Tour1Move {          // one per move (order MAACO.py:98)
 #define T1_DLEN_OFF (4096 + 128)            // double dlen[8]      : 1.0 or sqrt(2) (:293)
 #define T1_FAST_OFF (4096 + 256)            // uint4 fast[4]       : member of P1 -> {dcur, dprow, dc, move | dphi << 8}
 #define T1_FLEN_OFF (4096 + 256 + 64)       // double flen[4]      : step length of that member
+#define T1_FLD_OFF (4096 + 256 + 96)        // uint32 fld[8]      : fields [24:4] of word2 for each order of P1's members (nb8 bytes)
 #define T1_RNG_OFF (4096 + 256 + 128)       // per warp: double2 u[32] (512 B) + uint32 pack[32] + uint32 pack2[32]
 #define T1_RNG_BYTES 768
 #define T1_WIN_OFF (T1_RNG_OFF + (MPP_TOUR1_THREADS / 32) * T1_RNG_BYTES)
@@ -351,10 +355,35 @@ __device__ __forceinline__ uint32_t tour_word2(uint32_t w, int sm0, int sm1, int
     const uint32_t G = A3 ? ((w >> (3u * A3)) & 7u) : 0u;
     return ((w & 7u) ? 1u : 0u) | (A3 << 1) | (((w >> 3) & 0x1FFFFFu) << 4) | (G << 25);
 }
+// The same word in one byte (the nb8 table): [0] ranking n/a, [3:1] A, [6:4] how the ranking orders P1's three members
+// (bit 4: member 0 before 1, bit 5: 0 before 2, bit 6: 1 before 2); the fields follow from the order (tour_fields).
+__host__ __device__ __forceinline__ uint32_t tour_fields(uint32_t order) {
+    const uint32_t b01 = order & 1u, b02 = (order >> 1) & 1u, b12 = (order >> 2) & 1u;
+    const uint32_t p0 = (1u - b01) + (1u - b02), p1 = b01 + (1u - b12), p2 = b02 + b12;   // members ranked before it
+    uint32_t f = 0u;
+    for (uint32_t c = 1; c < 8; ++c) {
+        uint32_t bp = 8u, bi = 0u;
+        if ((c & 1u) && p0 < bp) { bp = p0; bi = 0u; }
+        if ((c & 2u) && p1 < bp) { bp = p1; bi = 1u; }
+        if ((c & 4u) && p2 < bp) { bp = p2; bi = 2u; }
+        f |= (c & ~((1u << bi) - 1u)) << (3u * (c - 1u));
+    }
+    return f;
+}
 // the prefetch of the three possible next cells' word2 (one 16-byte line of the bundle table), pinned where it is issued
 __device__ __forceinline__ uint4 ldg128_pinned(const uint4 *p) {
     uint4 v;
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ldg64_pinned(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg32_nc_pinned(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -408,6 +437,7 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_t
             ((uint4 *)(t1_smem + T1_FAST_OFF))[threadIdx.x] = v;
             ((double *)(t1_smem + T1_FLEN_OFF))[threadIdx.x] = dl;
         }
+        if (threadIdx.x >= 32 && threadIdx.x < 40) ((uint32_t *)(t1_smem + T1_FLD_OFF))[threadIdx.x - 32] = tour_fields(threadIdx.x - 32);
     }
     double2 *const rngu = (double2 *)(t1_smem + T1_RNG_OFF + wib * T1_RNG_BYTES);
     uint32_t *const rngp = (uint32_t *)(t1_smem + T1_RNG_OFF + wib * T1_RNG_BYTES + 512);
@@ -447,6 +477,7 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_t
     const uint32_t *__restrict__ rank_fast = A.rank + (size_t)map * A.rank_stride + A.rank_margin;
     const uint2 *const rank_slow = (const uint2 *)(A.rank + (size_t)map * A.rank_stride + A.rank_fast_words);
     const uint4 *bundle = (const uint4 *)(A.rank + (size_t)map * A.rank_stride + A.rank_bundle_words);
+    const uint2 *const nb8 = (const uint2 *)(A.rank + (size_t)map * A.rank_stride + A.rank_nb8_words);
     {
         unsigned long long bf = (unsigned long long)bundle;
         bf = __shfl_sync(0xffffffffu, bf, 0);
@@ -632,7 +663,13 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_t
             if (m < 0) {
                 // ---- tier 3: all eight moves, strategies 1-3, full ranking entry or the literal rules ----
                 const uint32_t ctx = (n_path >= 2) ? (uint32_t)(prev_m + 1) : 0u;
-                const uint32_t fw = rank_fast[(size_t)cur * 9 + ctx];  // ranking word of (cell, previous move)
+                // everything the step may need from the ranking tables is requested at once (one L2 round trip instead of
+                // up to three in a row): the ranking word and the full entry of (cell, previous move), and the packed word2
+                // of all eight neighbours for the step after this one
+                const uint32_t fw = ldg32_nc_pinned(rank_fast + (size_t)cur * 9 + ctx);
+                const uint2 rws = ldg64_pinned(rank_slow + (size_t)cur * 9 + ctx);
+                uint2 nb = make_uint2(0u, 0u);
+                if (fast_ok) nb = ldg64_pinned(nb8 + cur);
                 const uint32_t pack = lds_u32(rngp_s + slot);
                 const uint2 q0r = lds_u2(prow_s - 8u), q1r = lds_u2(prow_s), q2r = lds_u2(prow_s + 8u);
                 const int rot = lcol - 1;                             // 0..61
@@ -661,7 +698,6 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_t
                         if (pack & (1u << 24)) {
                             // greedy: first arg-max = best-ranked candidate (full entry: permute the candidate flags
                             // into rank order, take the first) and every later candidate
-                            const uint2 rws = rank_slow[(size_t)cur * 9 + ctx];
                             const uint2 sp = lds_u2(sbase_k + T1_SPREAD_OFF + 8u * cand);
                             const uint32_t f0 = __byte_perm(sp.x, sp.y, rws.x & 0xFFFFu), f1 = __byte_perm(sp.x, sp.y, rws.x >> 16);
                             const uint32_t ff = f0 ? f0 : f1;
@@ -676,7 +712,13 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_t
                     const uint4 mvv = lds_u4(sbase_k + T1_MOVE_OFF + 16u * (uint32_t)m);
                     dcur = (int)mvv.x; dpr = (int)mvv.y; dcc = (int)mvv.z; dphi = (int)mvv.w;
                     dl = lds_f64(sbase_k + T1_DLEN_OFF + 8u * (uint32_t)m);
-                    if (fast_ok) fw2 = tour_word2(rank_fast[(size_t)(cur + dcur) * 9 + (m + 1)], k_sm0, k_sm1, k_sm2);
+                    if (fast_ok) {
+                        const uint32_t by = (((m & 4) ? nb.y : nb.x) >> (8 * (m & 3))) & 0xFFu;   // packed word2 of the cell moved to
+                        const uint32_t fl = lds_u32(sbase_k + T1_FLD_OFF + 4u * (by >> 4));
+                        const uint32_t A3n = (by >> 1) & 7u;
+                        const uint32_t Gn = A3n ? ((fl >> (3u * (A3n - 1u))) & 7u) : 0u;
+                        fw2 = (by & 1u) | (A3n << 1) | (fl << 4) | (Gn << 25);
+                    }
                 }
             }
             if (active) {
@@ -748,7 +790,7 @@ extern "C" int mpp_maaco_tours(const mpp_map_batch *maps, const mpp_colony *c, i
     TourArgs A;
     A.meta = maps->meta_dev;
     A.rank = c->rank; A.rank_stride = L.total_words; A.rank_margin = L.margin; A.rank_fast_words = L.fast_words;
-    A.rank_bundle_words = L.bundle_words;
+    A.rank_bundle_words = L.bundle_words; A.rank_nb8_words = L.nb8_words;
     A.R = maps->rows; A.C = maps->cols;
     A.tau = c->tau; A.tau_stride = (size_t)c->tau_stride; A.E01 = c->E01; A.E01_stride = (size_t)c->E01_stride;
     A.it = (uint32_t)iteration; A.q0 = q0; A.alpha = alpha;
@@ -807,7 +849,8 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
                                                              double alpha, int R, int C,
                                                              const MppMapMeta *__restrict__ meta, uint32_t *__restrict__ rank_all,
                                                              size_t rank_stride, size_t rank_margin, size_t rank_fast_words,
-                                                             size_t rank_bundle_words, const int32_t *__restrict__ latch) {
+                                                             size_t rank_bundle_words, size_t rank_nb8_words,
+                                                             const int32_t *__restrict__ latch) {
     // one thread per cell: the eight neighbours' tau / eta' are read once and serve all nine contexts
     const int cell = blockIdx.x * 128 + threadIdx.x;
     if (cell >= R * C) return;
@@ -819,6 +862,7 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
     uint32_t *rank_fast = rank_all + (size_t)map * rank_stride + rank_margin;
     uint2 *rank_slow = (uint2 *)(rank_all + (size_t)map * rank_stride + rank_fast_words);
     uint32_t *bundle = rank_all + (size_t)map * rank_stride + rank_bundle_words;
+    uint8_t *nb8 = (uint8_t *)(rank_all + (size_t)map * rank_stride + rank_nb8_words);
     const uint32_t P1 = meta[map].s1.P1;
     const uint32_t sv = svalid[cell];
     double a0[8], a1[8];                                          // attractiveness without / with the turn factor (:238)
@@ -844,7 +888,7 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
         double cmx = 0.0;
 #pragma unroll
         for (int m = 0; m < 8; ++m) cmx = fmax(cmx, a[m]);
-        uint32_t word = 0xFFFFFFu, perm = 0u, fast = 7u;
+        uint32_t word = 0xFFFFFFu, perm = 0u, fast = 7u, order = 0u;
         if (cmx < 1e-10) {
             word = 0u;
 #pragma unroll
@@ -858,6 +902,7 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
             fast = 0u;                                            // field 0: the ranking applies
             if (p1_three) {
                 const uint32_t p0 = (word >> (3 * s0)) & 7u, p1 = (word >> (3 * s1)) & 7u, p2 = (word >> (3 * s2)) & 7u;
+                order = (p0 < p1 ? 1u : 0u) | (p0 < p2 ? 2u : 0u) | (p1 < p2 ? 4u : 0u);
 #pragma unroll
                 for (uint32_t c = 1; c < 8; ++c) {
                     // best-ranked member of subset c (rank positions are distinct)
@@ -872,14 +917,16 @@ __global__ void __launch_bounds__(128) mpp_maaco_rank_kernel(const uint8_t *__re
         const size_t t = (size_t)cell * 9 + ctx;
         rank_fast[t] = fast | (sv << 24);
         rank_slow[t] = make_uint2(perm, word | (sv << 24));
-        if (p1_three) {
-            // the cell this one is entered from by P1's member k (context = that move): its bundle gets this word
-            const int k = (ctx == s0 + 1) ? 0 : ((ctx == s1 + 1) ? 1 : ((ctx == s2 + 1) ? 2 : -1));
-            if (k >= 0) {
-                const int mv = ctx - 1;
-                const int pr = cell / C - ((int)((0xA940u >> (2 * mv)) & 3u) - 1), pc = cell % C - ((int)((0x9224u >> (2 * mv)) & 3u) - 1);
-                if (pr >= 0 && pr < R && pc >= 0 && pc < C)
-                    bundle[((size_t)pr * C + pc) * 4 + k] = tour_word2(fast | (sv << 24), s0, s1, s2);
+        if (p1_three && ctx > 0) {
+            // the cell this one is entered from by move ctx-1: its nb8 entry gets the packed word, and when the move is
+            // P1's member k its bundle gets the word itself
+            const int mv = ctx - 1;
+            const int pr = cell / C - ((int)((0xA940u >> (2 * mv)) & 3u) - 1), pc = cell % C - ((int)((0x9224u >> (2 * mv)) & 3u) - 1);
+            if (pr >= 0 && pr < R && pc >= 0 && pc < C) {
+                const uint32_t A3 = ((sv >> s0) & 1u) | (((sv >> s1) & 1u) << 1) | (((sv >> s2) & 1u) << 2);
+                nb8[((size_t)pr * C + pc) * 8 + mv] = (uint8_t)((fast & 7u ? 1u : 0u) | (A3 << 1) | (order << 4));
+                const int k = (ctx == s0 + 1) ? 0 : ((ctx == s1 + 1) ? 1 : ((ctx == s2 + 1) ? 2 : -1));
+                if (k >= 0) bundle[((size_t)pr * C + pc) * 4 + k] = tour_word2(fast | (sv << 24), s0, s1, s2);
             }
         }
     }
@@ -893,7 +940,7 @@ extern "C" int mpp_maaco_rank(const mpp_map_batch *maps, const mpp_colony *c, do
     const RankLayout L = rank_layout(maps->rows, maps->cols);
     mpp_maaco_rank_kernel<<<dim3((total + 127) / 128, maps->n_maps), 128, 0, (cudaStream_t)stream>>>(
         maps->svalid_dev, c->tau, (size_t)c->tau_stride, c->E01, (size_t)c->E01_stride, alpha, maps->rows, maps->cols,
-        maps->meta_dev, c->rank, L.total_words, L.margin, L.fast_words, L.bundle_words, c->latch);
+        maps->meta_dev, c->rank, L.total_words, L.margin, L.fast_words, L.bundle_words, L.nb8_words, c->latch);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
