@@ -1124,9 +1124,8 @@ extern "C" int mpp_maaco_best(const mpp_map_batch *maps, const mpp_colony *c, in
 // ---------------------------------------------------------------------------------------------
 #define MPP_PHER_THREADS 256
 #define MPP_PHER_CHUNK 2048                   // ants per list-building round (64 bitmap words)
-#ifndef MPP_PHER_WIDE
-#define MPP_PHER_WIDE 1                       // rounds of 32 ants a warp takes per trip
-#endif
+#define PHER_TRIP 128                         // ants the CTA takes per trip (256 threads x 16 bytes = their 32-byte sectors)
+#define PHER_PITCH 132                        // row pitch of the shared-memory word tile (conflict-free transposing stores)
 
 // MMAS clip + obstacle reset (MAACO.py:312-332) for one cell
 __device__ __forceinline__ double pher_finalize(double t, int r, int c, const uint32_t *occ, int pitch, int R, int C,
@@ -1179,7 +1178,8 @@ __global__ void __launch_bounds__(MPP_PHER_THREADS, MPP_PHER_MINB) mpp_maaco_phe
     const unsigned long long prof_t0 = gtimer();
     unsigned long long prof_hits = 0, prof_rounds = 0, prof_list = 0, prof_loop = 0, prof_tl = 0;
 #endif
-    __shared__ __align__(16) double s_dep[MPP_PHER_THREADS / 32][32 * MPP_PHER_WIDE];   // per warp: the deposits of a trip's ants
+    __shared__ uint32_t s_w[2][8][PHER_PITCH];                        // a trip's row words [row of the group][ant], two trips
+    __shared__ __align__(16) double s_d[2][PHER_TRIP];                // a trip's deposits
     __shared__ int s_wcnt[2];
     if (A.latch && *A.latch) return;
 #ifdef MPP_PHER_ONLY
@@ -1220,7 +1220,6 @@ __global__ void __launch_bounds__(MPP_PHER_THREADS, MPP_PHER_MINB) mpp_maaco_phe
     const double *dep = A.deposit + (size_t)map * A.n_ants;
     double t = 0.0;
     if (live) t = tau[(size_t)r * A.C + c] * (1.0 - A.rho);            // :305
-    double *sd = s_dep[wid];
     for (int w0 = 0; w0 < NW; w0 += MPP_PHER_CHUNK / 32) {
         // ---- the ants of this chunk that have a slab here and deposit, in index order ----
 #ifdef MPP_PHER_PROF
@@ -1249,67 +1248,65 @@ __global__ void __launch_bounds__(MPP_PHER_THREADS, MPP_PHER_MINB) mpp_maaco_phe
 #ifdef MPP_PHER_PROF
         { const unsigned long long g_ = gtimer(); prof_list += g_ - prof_tl; prof_tl = g_; }
 #endif
-        // ---- this warp's row.  A round = 32 ants of the list: lane i loads the row word of the i-th ant's slab and its
-        //      deposit (the next trip's loads are in flight during this one); the 32x32 bit matrix (ant x cell) is transposed across
-        //      the warp, so that lane c (= cell c of the row) holds the set of ants that visited ITS cell, and each lane
-        //      adds the deposits of its own ants in index order (:306, :311).  Near the start and the target every ant
-        //      crosses the same few cells, so some lane usually has all 32 bits set and a round lasts 32 dependent adds
-        //      whatever the form: the fold is straight-line DADDs whose OPERAND is selected (t + 0.0 == t exactly; the
-        //      loop-carried chain is the bare add, 8.2 cycles each: tools/ubench/dadd_chain.cu), the deposits come from
-        //      broadcast 16-byte shared-memory loads.  tools/ubench/fold_round.cu times the forms that were tried
-        //      (compacted (word, deposit) lists with every lane adding every entry: 27-36 cycles per add; this: 14). ----
-        // A trip of the loop takes MPP_PHER_WIDE rounds at once: their loads, transposes and shared-memory traffic are
-        // independent and overlap, only the adds stay in sequence.
-        int a_n[MPP_PHER_WIDE];
-        uint32_t w_n[MPP_PHER_WIDE];
-        double d_n[MPP_PHER_WIDE];
-        auto fetch = [&](int i, int &a, uint32_t &w, double &d) {
-            a = 0; w = 0u; d = 0.0;
-            if (i < k) {
-                a = s_list[i];
-                w = slab_t[(size_t)a * 32];    // (plain load: the 8 row warps of the CTA read the same 32-byte sector)
-                d = dep[a];
+        // ---- the rows.  The CTA takes 128 ants of the list per trip: thread t loads half of the 32-byte sector that holds
+        //      this row group's eight words in ant t/2's slab (one 16-byte load: a warp load covers 16 lines, a per-row
+        //      gather would cover 32 and repeat eight times) and threads 0..127 the deposits, both one trip ahead; they go
+        //      to shared memory [row][ant] (double-buffered: one barrier per trip).  Then each warp folds ITS row: for every
+        //      32 ants, lane i holds the row word of the i-th ant, the 32x32 bit matrix (ant x cell) is transposed across
+        //      the warp so that lane c (= cell c of the row) holds the set of ants that visited its cell, and the lane adds
+        //      the deposits of its own ants in index order (:306, :311).  Near the start and the target every ant crosses
+        //      the same few cells, so some lane usually has all 32 bits set and 32 ants cost 32 dependent adds whatever
+        //      the form: the fold is straight-line DADDs whose OPERAND is selected (t + 0.0 == t exactly; the
+        //      loop-carried chain is the bare add, 8.2 cycles: tools/ubench/dadd_chain.cu), the deposits come from
+        //      broadcast 16-byte shared-memory loads.  (tools/ubench/fold_round.cu, gather_round.cu: the forms that were
+        //      tried -- compacted (word, deposit) lists with every lane adding every entry cost 27-36 cycles per add and
+        //      ant, this 14; a per-warp gather costs 300 cycles of the SM's load path per 32 ants.) ----
+        const int ntrip = (k + PHER_TRIP - 1) / PHER_TRIP;
+        const uint32_t *slab_g = slab_t - wid + (threadIdx.x & 1) * 4;      // this row group's sector, this thread's half
+        uint4 wv = make_uint4(0u, 0u, 0u, 0u);
+        double dv = 0.0;
+        int av = -1;
+        auto issue = [&](int trip) {
+            const int i = trip * PHER_TRIP + (threadIdx.x >> 1);
+            wv = make_uint4(0u, 0u, 0u, 0u); av = -1; dv = 0.0;
+            if (i < k) { av = s_list[i]; wv = *(const uint4 *)(slab_g + (size_t)av * 32); }
+            if (threadIdx.x < PHER_TRIP) {
+                const int i2 = trip * PHER_TRIP + threadIdx.x;
+                if (i2 < k) dv = dep[s_list[i2]];
             }
         };
-#pragma unroll
-        for (int u = 0; u < MPP_PHER_WIDE; ++u) fetch(u * 32 + lane, a_n[u], w_n[u], d_n[u]);
-        for (int base = 0; base < k; base += 32 * MPP_PHER_WIDE) {
-            int a_c[MPP_PHER_WIDE];
-            uint32_t m[MPP_PHER_WIDE], nz[MPP_PHER_WIDE], any = 0u;
-            double d_c[MPP_PHER_WIDE];
-#pragma unroll
-            for (int u = 0; u < MPP_PHER_WIDE; ++u) {
-                a_c[u] = a_n[u]; m[u] = w_n[u]; d_c[u] = d_n[u];
-                fetch(base + 32 * MPP_PHER_WIDE + u * 32 + lane, a_n[u], w_n[u], d_n[u]);   // the next trip's, in flight during this one
-                nz[u] = __ballot_sync(0xffffffffu, m[u] != 0u);
-                any |= nz[u];
+        issue(0);
+        for (int trip = 0; trip < ntrip; ++trip) {
+            const int buf = trip & 1;
+            {
+                uint32_t *dst = &s_w[buf][(threadIdx.x & 1) * 4][threadIdx.x >> 1];
+                dst[0] = wv.x; dst[PHER_PITCH] = wv.y; dst[2 * PHER_PITCH] = wv.z; dst[3 * PHER_PITCH] = wv.w;
+                if (threadIdx.x < PHER_TRIP) s_d[buf][threadIdx.x] = dv;
+                if (A.clear_slabs && (wv.x | wv.y | wv.z | wv.w)) *(uint4 *)(const_cast<uint32_t *>(slab_g) + (size_t)av * 32) = make_uint4(0u, 0u, 0u, 0u);
             }
-            if (!any) continue;
-#pragma unroll
-            for (int u = 0; u < MPP_PHER_WIDE; ++u) {
-                if (A.clear_slabs && m[u] != 0u) slab_t[(size_t)a_c[u] * 32] = 0u;
-                sd[32 * u + lane] = d_c[u];
-            }
-#pragma unroll
-            for (int j = 16, mk = 0x0000FFFF; j; j >>= 1, mk ^= mk << j) {
-#pragma unroll
-                for (int u = 0; u < MPP_PHER_WIDE; ++u) {
-                    const uint32_t y = __shfl_xor_sync(0xffffffffu, m[u], j);
-                    m[u] = (lane & j) ? ((m[u] & ~(uint32_t)mk) | ((y >> j) & (uint32_t)mk)) : ((m[u] & (uint32_t)mk) | ((y << j) & ~(uint32_t)mk));
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < MPP_PHER_WIDE; ++u) {
+            issue(trip + 1);                                           // in flight while this trip is folded
+            __syncthreads();
+#pragma unroll 1
+            for (int r = 0; r < PHER_TRIP / 32; ++r) {
+                if (trip * PHER_TRIP + r * 32 >= k) break;
+                uint32_t m = s_w[buf][wid][r * 32 + lane];
+                const uint32_t nz = __ballot_sync(0xffffffffu, m != 0u);
+                if (!nz) continue;
 #ifdef MPP_PHER_PROF
-                prof_hits += __popc(nz[u]); prof_rounds += 1;
+                prof_hits += __popc(nz); prof_rounds += 1;
 #endif
-                const double2 *sd2 = (const double2 *)(sd + 32 * u);
+#pragma unroll
+                for (int j = 16, mk = 0x0000FFFF; j; j >>= 1, mk ^= mk << j) {
+                    const uint32_t y = __shfl_xor_sync(0xffffffffu, m, j);
+                    m = (lane & j) ? ((m & ~(uint32_t)mk) | ((y >> j) & (uint32_t)mk)) : ((m & (uint32_t)mk) | ((y << j) & ~(uint32_t)mk));
+                }
+                const double2 *sd2 = (const double2 *)(s_d[buf] + r * 32);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    if (!(nz[u] & (0xFFu << (8 * g)))) continue;       // (warp-uniform) none of these eight ants has a word here
+                    if (!(nz & (0xFFu << (8 * g)))) continue;          // (warp-uniform) none of these eight ants has a word here
                     const double2 v0 = sd2[4 * g], v1 = sd2[4 * g + 1], v2 = sd2[4 * g + 2], v3 = sd2[4 * g + 3];
-                    const uint32_t mg = m[u] >> (8 * g);
+                    const uint32_t mg = m >> (8 * g);
+                    // (the operand is selected, not the sum: the loop-carried chain is a bare DADD; t + 0.0 == t exactly)
                     const double a0 = (mg & 1u) ? v0.x : 0.0, a1 = (mg & 2u) ? v0.y : 0.0, a2 = (mg & 4u) ? v1.x : 0.0;
                     const double a3 = (mg & 8u) ? v1.y : 0.0, a4 = (mg & 16u) ? v2.x : 0.0, a5 = (mg & 32u) ? v2.y : 0.0;
                     const double a6 = (mg & 64u) ? v3.x : 0.0, a7 = (mg & 128u) ? v3.y : 0.0;
@@ -1323,7 +1320,6 @@ __global__ void __launch_bounds__(MPP_PHER_THREADS, MPP_PHER_MINB) mpp_maaco_phe
                     t += a7;
                 }
             }
-            __syncwarp();
         }
 #ifdef MPP_PHER_PROF
         prof_loop += gtimer() - prof_tl;
