@@ -150,8 +150,9 @@ def ref_python(kind, size, map_seed, seconds, procs=None):
 
 
 def workload_config(args, world, total, p2p=None):
-    how = "" if world == 1 else ("; per pass the results + move codes and the tau slices are stored straight into the peers' "
-                                 "buffers over NVLink (peer memory) + two device-side barriers" if p2p else
+    how = "" if world == 1 else ("; the tour kernel stores every visited-set slab straight into the rank that updates its tile row "
+                                 "and the update kernel its tau slice into every rank (NVLink peer memory, two device-side "
+                                 "barriers per pass: no pack / all-gather / replay)" if p2p else
                                  "; per pass one all-gather of results + move codes and one all-gather of tau slices (NCCL)")
     return {"workload": f"MAACO colony pass, {total} ants ({total // world}/GPU) on {args.size}x{args.size} "
                         f"blocks(n,0.20,seed=4000), params main.py:34-38 (BASELINE config 4)",

@@ -171,6 +171,19 @@ int mpp_maaco_rank(const mpp_map_batch *maps, const mpp_colony *colony, double a
 int mpp_maaco_tours(const mpp_map_batch *maps, const mpp_colony *colony, int iteration, double q0, double alpha,
                     int n_ants, int ant_offset, int n_ants_total, int ants_per_warp, void *stream);
 
+/* The same for a colony sharded over GPUs that can address each other's memory (NVLink peer memory): besides its local
+ * buffers the kernel stores every visited-set slab straight into the receive buffers of the rank that updates that tile
+ * row -- slabs_peers[g] = rank g's slabs_recv [tile_rows_per_rank x tile cols][n_ants_total][32], touched_peers[g]
+ * its touched_recv (both parities) -- and every result into every rank's table result_peers[g][n_ants_total]; the three
+ * arrays are HOST arrays of n_peers (<= 16) peer-mapped device pointers (they travel in the kernel's parameters).  After
+ * one barrier across the ranks each of them runs mpp_maaco_best and mpp_maaco_pheromone (clear_slabs = 0) on what it
+ * received: no pack / all-gather / replay step.  (The deposit MAACO.py:306-311 stays a sum over ALL ants in global
+ * order on the rank that owns the cell.)  A single map only. */
+int mpp_maaco_tours_p2p(const mpp_map_batch *maps, const mpp_colony *colony, int iteration, double q0, double alpha,
+                        int n_ants, int ant_offset, int n_ants_total, int ants_per_warp,
+                        uint32_t *const *slabs_peers, uint32_t *const *touched_peers,
+                        mpp_ant_result *const *result_peers, int n_peers, int tile_rows_per_rank, void *stream);
+
 /* replaces the order-dependent best tracking MAACO.py:343-358 for one iteration over all n_ants_total results of each
  * map (global ant order) and prepares deposit / okbits (:307-308).  Updates state and appends to log.  colony->moves
  * holds the tours of ants [moves_ant_offset, moves_ant_offset + moves_n_ants) (a sharded colony keeps only its own);

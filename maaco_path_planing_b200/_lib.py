@@ -72,6 +72,8 @@ _SIGS = {
     "mpp_maaco_rank": (c_int, [c_void_p, C.POINTER(Colony), c_double, c_void_p]),
     "mpp_maaco_tours": (c_int, [c_void_p, C.POINTER(Colony), c_int, c_double, c_double, c_int, c_int, c_int, c_int,
                                 c_void_p]),
+    "mpp_maaco_tours_p2p": (c_int, [c_void_p, C.POINTER(Colony), c_int, c_double, c_double, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mpp_maaco_best": (c_int, [c_void_p, C.POINTER(Colony), c_int, c_int, c_int, c_double, c_int, c_void_p]),
     "mpp_maaco_pheromone": (c_int, [c_void_p, C.POINTER(Colony), c_void_p, c_void_p, c_int, c_int, c_int, c_double,
                                     c_int, c_int, c_void_p, c_int, c_void_p]),

@@ -182,6 +182,7 @@ extern "C" long long mpp_maaco_touched_words(int tile_rows, int cols, int n_ants
 //   * the warp's lanes generate Philox blocks together: lane L makes the block of ant L%apw, step s+L/apw.
 // `apw` lanes of each warp own an ant: fewer ants per warp = more warps to spread over the SMs.
 // ---------------------------------------------------------------------------------------------
+#define MPP_MAX_PEERS 16
 struct TourArgs {
     const MppMapMeta *meta;      // [n_maps]
     const uint32_t *rank;        // [n_maps][rank_stride] ranking buffers (mpp_maaco_rank), layout: rank_layout()
@@ -201,6 +202,14 @@ struct TourArgs {
     size_t result_stride;        // results of one map (>= ant_offset + n_ants)
     unsigned long long *steps;
     const int32_t *latch;        // non-zero = a sharded colony's exchange overflowed: every kernel is a no-op until the host rewinds
+    // sharded colony over peer memory (mpp_maaco_tours_p2p): every slab this kernel writes also goes, over NVLink, straight
+    // into the receive buffers of the rank that updates that tile row, and every result into every rank's table
+    // (the pointers travel in the kernel parameters: a slide must not wait for a global load to learn where to store)
+    uint32_t *peer_slabs[MPP_MAX_PEERS];       // slabs_recv of each rank: [its tile rows x TC][n_total][32]
+    uint32_t *peer_touched[MPP_MAX_PEERS];     // touched_recv of each rank (both parities)
+    mpp_ant_result *peer_result[MPP_MAX_PEERS];   // result table of each rank [n_total]
+    int n_peers, rows_per_rank;      // n_peers = 0: not sharded over peer memory; tile rows per rank
+    int n_total;                     // ants of the whole colony
 };
 
 #define MPP_SQRT2 1.4142135623730951  // sqrt(2.0) correctly rounded == math.sqrt(2)
@@ -274,6 +283,9 @@ struct TourSlabs {
     uint32_t *slabs, *touched;   // of this map
     size_t n_ants;
     int NW, TR, TC;
+    const TourArgs *peers;                               // null unless the colony is sharded over peer memory
+    int rows_per_rank, ant_offset, NW_total;
+    size_t n_total, peer_touched_off;                    // this pass's parity inside a rank's touched_recv
 };
 __device__ __forceinline__ uint32_t tour_tile_load(const TourSlabs &V, int a, int trow, int tcx, int lane) {
     if (trow < 0 || trow >= V.TR || tcx < 0 || tcx >= V.TC) return 0u;
@@ -291,6 +303,14 @@ __device__ __forceinline__ void tour_tile_store(const TourSlabs &V, int a, int t
     const int tile = trow * V.TC + tcx;
     V.slabs[((size_t)tile * V.n_ants + a) * 32 + lane] = v;                  // one 128-byte line
     if (lane == 0) atomicOr(V.touched + (size_t)tile * V.NW + (a >> 5), 1u << (a & 31));
+    if (V.peers) {
+        // the same line for the rank that updates this tile row (possibly this one): a peer store + a peer reduction,
+        // neither waited for; a tile that is stored again later in the tour (the ant came back) carries a superset
+        const int g = trow / V.rows_per_rank, tl = (trow - g * V.rows_per_rank) * V.TC + tcx;
+        const size_t ga = (size_t)V.ant_offset + a;
+        V.peers->peer_slabs[g][((size_t)tl * V.n_total + ga) * 32 + lane] = v;
+        if (lane == 0) atomicOr(V.peers->peer_touched[g] + V.peer_touched_off + (size_t)tl * V.NW_total + (ga >> 5), 1u << (ga & 31));
+    }
 }
 
 // a load the compiler may not sink to its use (it would turn "select among three loaded entries" into "one load
@@ -471,6 +491,10 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_t
     V.slabs = A.slabs + (size_t)map * A.slab_stride;
     V.touched = A.touched + (size_t)map * A.touched_stride;
     V.n_ants = (size_t)A.n_ants; V.NW = (A.n_ants + 31) >> 5; V.TR = (R + 31) >> 5; V.TC = TC;
+    V.peers = A.n_peers > 0 ? &A : nullptr;
+    V.rows_per_rank = A.rows_per_rank; V.ant_offset = A.ant_offset; V.n_total = (size_t)A.n_total;
+    V.NW_total = (A.n_total + 31) >> 5;
+    V.peer_touched_off = (size_t)(A.it & 1u) * (size_t)A.rows_per_rank * TC * (size_t)V.NW_total;
     uint8_t *mvp = A.moves + ((size_t)map * A.n_ants + (active ? a : a0)) * A.max_cells;   // next move-code slot
     const double *const tau_m = A.tau + (size_t)map * A.tau_stride;
     const double *const E01_m = A.E01 + (size_t)map * A.E01_stride;
@@ -760,6 +784,7 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_t
         res.n_cells = ok ? n_path : 0;
         res.turns = ok ? (turns > 0 ? turns : 0) : -1;
         A.result[(size_t)map * A.result_stride + A.ant_offset + a] = res;
+        for (int g = 0; g < A.n_peers; ++g) A.peer_result[g][A.ant_offset + a] = res;
         if (A.steps) atomicAdd(A.steps, (unsigned long long)(n_path - 1));
 #ifdef MPP_TOUR_STATS
         int *st = (int *)(A.moves + ((size_t)map * A.n_ants + a + 1) * A.max_cells - 32);
@@ -779,8 +804,10 @@ static int colony_check(const mpp_map_batch *maps, const mpp_colony *c, const ch
     return MPP_OK;
 }
 
-extern "C" int mpp_maaco_tours(const mpp_map_batch *maps, const mpp_colony *c, int iteration, double q0, double alpha,
-                               int n_ants, int ant_offset, int n_ants_total, int ants_per_warp, void *stream) {
+static int tours_launch(const mpp_map_batch *maps, const mpp_colony *c, int iteration, double q0, double alpha,
+                        int n_ants, int ant_offset, int n_ants_total, int ants_per_warp,
+                        uint32_t *const *peer_slabs, uint32_t *const *peer_touched, mpp_ant_result *const *peer_result,
+                        int n_peers, int rows_per_rank, void *stream) {
     int rc = colony_check(maps, c, "mpp_maaco_tours");
     if (rc) return rc;
     MPP_REQUIRE(n_ants > 0 && ant_offset >= 0 && ant_offset + n_ants <= n_ants_total, "mpp_maaco_tours: bad ant range");
@@ -802,6 +829,12 @@ extern "C" int mpp_maaco_tours(const mpp_map_batch *maps, const mpp_colony *c, i
     A.moves = c->moves; A.max_cells = c->max_cells;
     A.result = c->result; A.result_stride = (size_t)n_ants_total;
     A.steps = c->steps; A.latch = c->latch;
+    for (int g = 0; g < MPP_MAX_PEERS; ++g) {
+        A.peer_slabs[g] = g < n_peers ? peer_slabs[g] : nullptr;
+        A.peer_touched[g] = g < n_peers ? peer_touched[g] : nullptr;
+        A.peer_result[g] = g < n_peers ? peer_result[g] : nullptr;
+    }
+    A.n_peers = n_peers; A.rows_per_rank = rows_per_rank; A.n_total = n_ants_total;
     // ants per warp: enough warps for every SM sub-partition first, full warps only for big colonies
     int apw = 16;                                                  // measured (tools/batch_time.py): 16 beats 32 even at 131 k ants
     const char *e = getenv("MPP_TOUR_APW");
@@ -826,6 +859,23 @@ extern "C" int mpp_maaco_tours(const mpp_map_batch *maps, const mpp_colony *c, i
     mpp_maaco_tour1_kernel<<<dim3((warps + wpb - 1) / wpb, maps->n_maps), MPP_TOUR1_THREADS, smem, (cudaStream_t)stream>>>(A, apw);
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
+}
+
+extern "C" int mpp_maaco_tours(const mpp_map_batch *maps, const mpp_colony *c, int iteration, double q0, double alpha,
+                               int n_ants, int ant_offset, int n_ants_total, int ants_per_warp, void *stream) {
+    return tours_launch(maps, c, iteration, q0, alpha, n_ants, ant_offset, n_ants_total, ants_per_warp, nullptr, nullptr,
+                        nullptr, 0, 1, stream);
+}
+
+extern "C" int mpp_maaco_tours_p2p(const mpp_map_batch *maps, const mpp_colony *c, int iteration, double q0, double alpha,
+                                   int n_ants, int ant_offset, int n_ants_total, int ants_per_warp,
+                                   uint32_t *const *slabs_peers, uint32_t *const *touched_peers,
+                                   mpp_ant_result *const *result_peers, int n_peers, int tile_rows_per_rank, void *stream) {
+    MPP_REQUIRE(maps && maps->n_maps == 1, "mpp_maaco_tours_p2p: a sharded colony is one map");
+    MPP_REQUIRE(slabs_peers && touched_peers && result_peers && n_peers > 0 && n_peers <= MPP_MAX_PEERS && tile_rows_per_rank > 0 &&
+                    (long long)n_peers * tile_rows_per_rank >= tiles_r(maps->rows), "mpp_maaco_tours_p2p: bad peer arguments");
+    return tours_launch(maps, c, iteration, q0, alpha, n_ants, ant_offset, n_ants_total, ants_per_warp, slabs_peers,
+                        touched_peers, result_peers, n_peers, tile_rows_per_rank, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -135,7 +135,11 @@ class MAACO:
         self._slabs = torch.empty(L.mpp_maaco_slab_words(self.tile_rows, Cc, nl), dtype=i32, device=dev)
         self._touched = torch.zeros(L.mpp_maaco_touched_words(self.tile_rows, Cc, nl), dtype=i32, device=dev)
         self._moves = torch.zeros(nl * self.max_cells, dtype=u8, device=dev)
-        self._result = torch.zeros((num_ants, 2), dtype=i64, device=dev)   # mpp_ant_result per global ant
+        if self._p2p is not None:
+            self._result = self._p2p["result"]
+            self._result.zero_()
+        else:
+            self._result = torch.zeros((num_ants, 2), dtype=i64, device=dev)   # mpp_ant_result per global ant
         self._deposit = torch.zeros(num_ants, dtype=f64, device=dev)
         self._okbits = torch.zeros((num_ants + 31) // 32, dtype=i32, device=dev)
         self._best_cells = torch.zeros(self.max_cells + 1, dtype=i32, device=dev)
@@ -147,8 +151,12 @@ class MAACO:
         self._latch = None
         if self.world > 1:
             tr = self.tile_rows_per_rank
-            self._slabs_recv = torch.zeros(L.mpp_maaco_slab_words(tr, Cc, num_ants), dtype=i32, device=dev)
-            self._touched_recv = torch.zeros(L.mpp_maaco_touched_words(tr, Cc, num_ants), dtype=i32, device=dev)
+            if self._p2p is not None:
+                self._slabs_recv, self._touched_recv = self._p2p["slabs"], self._p2p["touched"]
+                self._touched_recv.zero_()                           # (slabs need no clearing: valid = touched bit)
+            else:
+                self._slabs_recv = torch.zeros(L.mpp_maaco_slab_words(tr, Cc, num_ants), dtype=i32, device=dev)
+                self._touched_recv = torch.zeros(L.mpp_maaco_touched_words(tr, Cc, num_ants), dtype=i32, device=dev)
             self._latch = torch.zeros(1, dtype=i32, device=dev)
             self._offsets_local = torch.zeros(nl, dtype=i32, device=dev)
             self._offsets = torch.zeros(num_ants, dtype=i32, device=dev)
@@ -158,11 +166,7 @@ class MAACO:
             # headers); an overflow raises the device latch and the pass is repeated with more room
             self._cap_max = _round64k(nl * min(self.max_cells, max(64, 2 * (R + Cc))))
             self._cap = self._cap_max
-            if self._p2p is not None:
-                self._xbuf_local = None                              # every rank writes straight into the peers' buffers
-                self._xbuf_all = self._p2p["xbuf"]
-                self._xbuf_all.zero_()
-            else:
+            if self._p2p is None:
                 self._xbuf_local = torch.zeros(self._xhdr + self._cap_max, dtype=u8, device=dev)
                 self._xbuf_all = torch.zeros(self.world * (self._xhdr + self._cap_max), dtype=u8, device=dev)
             self._ring = [torch.zeros(self.world + 1, dtype=i32).pin_memory() for _ in range(4)]
@@ -176,6 +180,12 @@ class MAACO:
             self._best_cells.data_ptr(), self._log.data_ptr(), self._steps.data_ptr(), self._seeds.data_ptr(),
             self._latch.data_ptr() if self._latch is not None else None)
 
+        if self._p2p is not None:
+            # the peers write into this rank's buffers from their very first tour kernel: nobody starts before every rank
+            # has cleared them
+            import torch.distributed as dist
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.group)
         self.best_path_overall = []
         self.best_path_length_overall = INF
         self.best_path_turns_overall = INF
@@ -184,27 +194,33 @@ class MAACO:
         self.kernel_launches = 0
 
     def _setup_peer_memory(self, npad):
-        """Symmetric (peer-mapped) allocations for the sharded colony's two exchanges: every rank's receive buffer of the
-        tours and every rank's pheromone field, each addressable from all ranks over NVLink.  Then the producers write
-        straight into the peers (mpp_maaco_xpack / mpp_maaco_pheromone with peer pointers) and a pass needs two
-        device-side barriers instead of two NCCL all-gathers.  Returns None when the platform cannot map peer memory
-        (the NCCL all-gathers are then used; same results)."""
+        """Symmetric (peer-mapped) allocations for the sharded colony's two exchanges: every rank's receive buffers of the
+        visited slabs and of the results, and every rank's pheromone field, each addressable from all ranks over NVLink.
+        Then the producers write straight into the peers (mpp_maaco_tours_p2p / mpp_maaco_pheromone with peer pointers)
+        and a pass needs two device-side barriers: no pack, no all-gather, no replay.  Returns None when the platform
+        cannot map peer memory (the NCCL all-gathers of move codes and tau slices are then used; same results)."""
         import torch
         import torch.distributed as dist
         ok = 1
         out = None
         try:
             import torch.distributed._symmetric_memory as symm
-            nl, R, Cc = self.n_local, self.rows, self.cols
-            xhdr = int(_lib.lib().mpp_maaco_xhdr_bytes(nl))
-            cap = _round64k(nl * min(self.max_cells_hint, max(64, 2 * (R + Cc))))
-            xbuf = symm.empty(self.world * (xhdr + cap), dtype=torch.uint8, device=self.device)
+            L = _lib.lib()
+            Cc, tr, N = self.cols, self.tile_rows_per_rank, self.num_ants
+            # what the peers write into: this rank's slice of every ant's visited slabs + the (tile, ant) bitmaps, the
+            # result table, and the pheromone field
+            slabs = symm.empty(int(L.mpp_maaco_slab_words(tr, Cc, N)), dtype=torch.int32, device=self.device)
+            touched = symm.empty(int(L.mpp_maaco_touched_words(tr, Cc, N)), dtype=torch.int32, device=self.device)
+            result = symm.empty((N, 2), dtype=torch.int64, device=self.device)
             tau = symm.empty(npad, dtype=torch.float64, device=self.device)
-            hx = symm.rendezvous(xbuf, self.group)
+            hs = symm.rendezvous(slabs, self.group)
+            hb = symm.rendezvous(touched, self.group)
+            hr = symm.rendezvous(result, self.group)
             ht = symm.rendezvous(tau, self.group)
-            xp = torch.tensor([int(p) for p in hx.buffer_ptrs], dtype=torch.int64, device=self.device)
-            tp = torch.tensor([int(p) for p in ht.buffer_ptrs], dtype=torch.int64, device=self.device)
-            out = dict(xbuf=xbuf, tau=tau, hx=hx, ht=ht, xpeers=xp, tpeers=tp)
+            ptrs = lambda h: torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=self.device)
+            harr = lambda h: (C.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])   # host arrays (kernel parameters)
+            out = dict(slabs=slabs, touched=touched, result=result, tau=tau, hx=hs, ht=ht, hb=hb, hr=hr,
+                       speers=harr(hs), bpeers=harr(hb), rpeers=harr(hr), tpeers=ptrs(ht))
         except Exception as e:                                       # noqa: BLE001 -- any failure = no peer memory here
             ok = 0
             self._p2p_error = f"{type(e).__name__}: {e}"
@@ -259,8 +275,17 @@ class MAACO:
         mark("rank")
         if events and len(events) > 4:
             events[4].record(cur)
-        _lib.check(L.mpp_maaco_tours(self._maps, col, it, self._calculate_adaptive_q0(it), self.alpha, nl, off, N,
-                                     self._apw, stream), "mpp_maaco_tours")
+        p2p = self._p2p if self.world > 1 else None
+        if p2p is not None:
+            # sharded over peer memory: the tour kernel itself delivers every slab to the rank that updates its tile row
+            # and every result to every rank (NVLink stores from the producing kernel)
+            _lib.check(L.mpp_maaco_tours_p2p(self._maps, col, it, self._calculate_adaptive_q0(it), self.alpha, nl, off, N,
+                                             self._apw, p2p["speers"], p2p["bpeers"], p2p["rpeers"], self.world,
+                                             self.tile_rows_per_rank, stream),
+                       "mpp_maaco_tours_p2p")
+        else:
+            _lib.check(L.mpp_maaco_tours(self._maps, col, it, self._calculate_adaptive_q0(it), self.alpha, nl, off, N,
+                                         self._apw, stream), "mpp_maaco_tours")
         mark("tours")
         if events:
             events[1].record(cur)
@@ -271,21 +296,32 @@ class MAACO:
             _lib.check(L.mpp_maaco_pheromone(self._maps, col, _lib.ptr(self._slabs), _lib.ptr(self._touched), N, 0,
                                              self.tile_rows, self.rho, it, 0, None, 0, stream), "mpp_maaco_pheromone")
             self.kernel_launches += 4
+        elif p2p is not None:
+            tr = self.tile_rows_per_rank
+            p2p["hx"].barrier(channel=0)                               # every rank's tours are done: slabs and results have landed
+            mark("exchange")
+            # (the local bitmaps of the next pass: the local update never runs on them, so nobody else clears them)
+            self._touched.view(2, -1)[(it + 1) & 1].zero_()
+            _lib.check(L.mpp_maaco_best(self._maps, col, off, nl, N, self.Q, it, stream), "mpp_maaco_best")
+            mark("best")
+            if events:
+                events[2].record(cur)
+            _lib.check(L.mpp_maaco_pheromone(self._maps, col, _lib.ptr(self._slabs_recv), _lib.ptr(self._touched_recv),
+                                             N, self.rank * tr, tr, self.rho, it, 0, _lib.ptr(p2p["tpeers"]), self.world,
+                                             stream), "mpp_maaco_pheromone")
+            mark("pheromone")
+            p2p["ht"].barrier(channel=0)                               # every rank's slice has landed in every field
+            mark("tau exchange")
+            self.kernel_launches += 4
         else:
-            p2p = self._p2p
-            cap = self._cap_max if p2p is not None else self._cap     # peer memory: no collective to size, fixed slots
+            cap = self._cap
             seg = self._xhdr + cap
             _lib.check(L.mpp_maaco_xpack(self._maps, col, off, nl, N, _lib.ptr(self._offsets_local),
-                                         _lib.ptr(self._xbuf_local), cap, _lib.ptr(p2p["xpeers"]) if p2p else None,
-                                         self.world, self.rank, stream), "mpp_maaco_xpack")
+                                         _lib.ptr(self._xbuf_local), cap, None, self.world, self.rank, stream),
+                       "mpp_maaco_xpack")
             mark("xpack")
-            if p2p is not None:
-                # the pack kernels wrote this rank's results + tours into every peer's buffer: one device-side barrier
-                # (also: every rank is past its tours, so the update may now overwrite the peers' tau)
-                p2p["hx"].barrier(channel=0)
-            else:
-                # ONE all-gather per pass carries the results and the tours (move codes) of every rank
-                dist_mod.exchange_buffers(self._xbuf_all[:self.world * seg], self._xbuf_local[:seg], self.group)
+            # ONE all-gather per pass carries the results and the tours (move codes) of every rank
+            dist_mod.exchange_buffers(self._xbuf_all[:self.world * seg], self._xbuf_local[:seg], self.group)
             mark("exchange")
             tr = self.tile_rows_per_rank
             _lib.check(L.mpp_maaco_xunpack(self._maps, col, _lib.ptr(self._xbuf_all), cap, self.world, nl, it,
@@ -298,15 +334,11 @@ class MAACO:
             if events:
                 events[2].record(cur)
             _lib.check(L.mpp_maaco_pheromone(self._maps, col, _lib.ptr(self._slabs_recv), _lib.ptr(self._touched_recv),
-                                             N, self.rank * tr, tr, self.rho, it, 1,
-                                             _lib.ptr(p2p["tpeers"]) if p2p else None, self.world, stream),
+                                             N, self.rank * tr, tr, self.rho, it, 1, None, self.world, stream),
                        "mpp_maaco_pheromone")
             mark("pheromone")
-            if p2p is not None:
-                p2p["ht"].barrier(channel=0)                           # every rank's slice has landed in every field
-            else:
-                sl = tr * 32 * self.cols
-                dist_mod.gather_tau(self._tau, self._tau[self.rank * sl:(self.rank + 1) * sl], self.group)
+            sl = tr * 32 * self.cols
+            dist_mod.gather_tau(self._tau, self._tau[self.rank * sl:(self.rank + 1) * sl], self.group)
             mark("tau exchange")
             # what the host needs two passes later: every segment's code total (from the gathered headers) + the latch
             slot = it & 3
@@ -349,12 +381,7 @@ class MAACO:
             raise _PathOverflow()
         self._cap_max = max(self._cap_max, _round64k(2 * max(totals)))
         self._cap = self._cap_max
-        if self._p2p is not None:
-            # the peer-mapped receive buffers have a fixed size: from here on the tours travel by NCCL all-gather
-            # (tau stays where it is: a symmetric allocation is an ordinary local tensor as well)
-            self._p2p = None
-            self._xbuf_local = None
-        if self._xbuf_local is None or self._xbuf_local.numel() < self._xhdr + self._cap_max:
+        if self._xbuf_local.numel() < self._xhdr + self._cap_max:
             self._xbuf_local = torch.zeros(self._xhdr + self._cap_max, dtype=torch.uint8, device=self.device)
             self._xbuf_all = torch.zeros(self.world * (self._xhdr + self._cap_max), dtype=torch.uint8, device=self.device)
         self._latch.zero_()

@@ -39,7 +39,14 @@ def main():
     opath, olen, oturns = orc2.solve()
     assert [r * 96 + c for r, c in path] == list(opath) and length == olen and turns == oturns, f"rank {rank} solve"
     # an exchange buffer that is far too small: the device latch stops the colony, the host makes room and repeats
+    # (the all-gather exchange: with peer memory nothing is sized, so nothing can overflow)
+    p2p_env = os.environ.get("MPP_P2P")
+    os.environ["MPP_P2P"] = "0"
     dev3 = MAACO(g, N, K, rng_seed=seed, device=local, group=dist.group.WORLD, verbose=False, **params)
+    if p2p_env is None:
+        del os.environ["MPP_P2P"]
+    else:
+        os.environ["MPP_P2P"] = p2p_env
     dev3._cap = dev3._cap_max = 0
     orc3 = O.MaacoOracle(g, N, K, seed=seed, **params)
     for it in range(1, K + 1):
@@ -49,7 +56,7 @@ def main():
     assert getattr(dev3, "exchange_rewinds", 0) >= 1, "the tiny exchange buffer should have overflowed"
     dist.barrier()
     if rank == 0:
-        print(f"multigpu_check ok: world={world}, {N} ants, {K} passes bit-exact vs oracle")
+        print(f"multigpu_check ok: world={world}, {N} ants, {K} passes bit-exact vs oracle (peer memory: {dev._p2p is not None})")
     dist.destroy_process_group()
 
 
