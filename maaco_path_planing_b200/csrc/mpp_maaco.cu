@@ -13,6 +13,7 @@
 //                                     (the update of pass p clears the buffer pass p+1 will use)
 //   moves    [ant][max_cells] uint8   the tour as move codes (MAACO.py:98 order): the best path is decoded from them,
 //                                     and they are what a sharded colony exchanges
+#include <type_traits>
 #include <cmath>
 #include <cstdlib>
 #include <thread>
@@ -202,13 +203,15 @@ struct TourArgs {
     size_t result_stride;        // results of one map (>= ant_offset + n_ants)
     unsigned long long *steps;
     const int32_t *latch;        // non-zero = a sharded colony's exchange overflowed: every kernel is a no-op until the host rewinds
-    // sharded colony over peer memory (mpp_maaco_tours_p2p): every slab this kernel writes also goes, over NVLink, straight
-    // into the receive buffers of the rank that updates that tile row, and every result into every rank's table
-    // (the pointers travel in the kernel parameters: a slide must not wait for a global load to learn where to store)
+};
+// sharded colony over peer memory (mpp_maaco_tours_p2p, the kernel's P2P instantiation): every slab the kernel writes also
+// goes, over NVLink, straight into the receive buffers of the rank that updates that tile row, and every result into every
+// rank's table (the pointers travel in the kernel parameters: a slide must not wait for a global load to learn where to store)
+struct TourPeers {
     uint32_t *peer_slabs[MPP_MAX_PEERS];       // slabs_recv of each rank: [its tile rows x TC][n_total][32]
     uint32_t *peer_touched[MPP_MAX_PEERS];     // touched_recv of each rank (both parities)
     mpp_ant_result *peer_result[MPP_MAX_PEERS];   // result table of each rank [n_total]
-    int n_peers, rows_per_rank;      // n_peers = 0: not sharded over peer memory; tile rows per rank
+    int n_peers, rows_per_rank;      // tile rows per rank
     int n_total;                     // ants of the whole colony
 };
 
@@ -283,7 +286,7 @@ struct TourSlabs {
     uint32_t *slabs, *touched;   // of this map
     size_t n_ants;
     int NW, TR, TC;
-    const TourArgs *peers;                               // null unless the colony is sharded over peer memory
+    const TourPeers *peers;                              // null unless the colony is sharded over peer memory
     int rows_per_rank, ant_offset, NW_total;
     size_t n_total, peer_touched_off;                    // this pass's parity inside a rank's touched_recv
 };
@@ -410,7 +413,10 @@ __device__ __forceinline__ uint32_t ldg32_nc_pinned(const uint32_t *p) {
 #ifndef MPP_TOUR1_MINB
 #define MPP_TOUR1_MINB 4
 #endif
-__global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_tour1_kernel(const TourArgs A, const int apw) {
+struct TourNoPeers {};
+template <bool P2P>
+__global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB)
+mpp_maaco_tour1_kernel(const TourArgs A, const int apw, const typename std::conditional<P2P, TourPeers, TourNoPeers>::type PA) {
     extern __shared__ __align__(16) uint8_t t1_smem[];
     if (A.latch && *A.latch) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -491,10 +497,14 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_t
     V.slabs = A.slabs + (size_t)map * A.slab_stride;
     V.touched = A.touched + (size_t)map * A.touched_stride;
     V.n_ants = (size_t)A.n_ants; V.NW = (A.n_ants + 31) >> 5; V.TR = (R + 31) >> 5; V.TC = TC;
-    V.peers = A.n_peers > 0 ? &A : nullptr;
-    V.rows_per_rank = A.rows_per_rank; V.ant_offset = A.ant_offset; V.n_total = (size_t)A.n_total;
-    V.NW_total = (A.n_total + 31) >> 5;
-    V.peer_touched_off = (size_t)(A.it & 1u) * (size_t)A.rows_per_rank * TC * (size_t)V.NW_total;
+    V.peers = nullptr;
+    V.rows_per_rank = 1; V.ant_offset = A.ant_offset; V.n_total = 0; V.NW_total = 0; V.peer_touched_off = 0;
+    if constexpr (P2P) {
+        V.peers = &PA;
+        V.rows_per_rank = PA.rows_per_rank; V.n_total = (size_t)PA.n_total;
+        V.NW_total = (PA.n_total + 31) >> 5;
+        V.peer_touched_off = (size_t)(A.it & 1u) * (size_t)PA.rows_per_rank * TC * (size_t)V.NW_total;
+    }
     uint8_t *mvp = A.moves + ((size_t)map * A.n_ants + (active ? a : a0)) * A.max_cells;   // next move-code slot
     const double *const tau_m = A.tau + (size_t)map * A.tau_stride;
     const double *const E01_m = A.E01 + (size_t)map * A.E01_stride;
@@ -784,7 +794,8 @@ __global__ void __launch_bounds__(MPP_TOUR1_THREADS, MPP_TOUR1_MINB) mpp_maaco_t
         res.n_cells = ok ? n_path : 0;
         res.turns = ok ? (turns > 0 ? turns : 0) : -1;
         A.result[(size_t)map * A.result_stride + A.ant_offset + a] = res;
-        for (int g = 0; g < A.n_peers; ++g) A.peer_result[g][A.ant_offset + a] = res;
+        if constexpr (P2P)
+            for (int g = 0; g < PA.n_peers; ++g) PA.peer_result[g][A.ant_offset + a] = res;
         if (A.steps) atomicAdd(A.steps, (unsigned long long)(n_path - 1));
 #ifdef MPP_TOUR_STATS
         int *st = (int *)(A.moves + ((size_t)map * A.n_ants + a + 1) * A.max_cells - 32);
@@ -829,12 +840,13 @@ static int tours_launch(const mpp_map_batch *maps, const mpp_colony *c, int iter
     A.moves = c->moves; A.max_cells = c->max_cells;
     A.result = c->result; A.result_stride = (size_t)n_ants_total;
     A.steps = c->steps; A.latch = c->latch;
+    TourPeers PA;
     for (int g = 0; g < MPP_MAX_PEERS; ++g) {
-        A.peer_slabs[g] = g < n_peers ? peer_slabs[g] : nullptr;
-        A.peer_touched[g] = g < n_peers ? peer_touched[g] : nullptr;
-        A.peer_result[g] = g < n_peers ? peer_result[g] : nullptr;
+        PA.peer_slabs[g] = g < n_peers ? peer_slabs[g] : nullptr;
+        PA.peer_touched[g] = g < n_peers ? peer_touched[g] : nullptr;
+        PA.peer_result[g] = g < n_peers ? peer_result[g] : nullptr;
     }
-    A.n_peers = n_peers; A.rows_per_rank = rows_per_rank; A.n_total = n_ants_total;
+    PA.n_peers = n_peers; PA.rows_per_rank = rows_per_rank; PA.n_total = n_ants_total;
     // ants per warp: enough warps for every SM sub-partition first, full warps only for big colonies
     int apw = 16;                                                  // measured (tools/batch_time.py): 16 beats 32 even at 131 k ants
     const char *e = getenv("MPP_TOUR_APW");
@@ -852,11 +864,14 @@ static int tours_launch(const mpp_map_batch *maps, const mpp_colony *c, int iter
         static size_t smem_set[64] = {0};
         const int dv = maps->device & 63;
         if (smem > smem_set[dv]) {
-            MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MPP_CUDA(cudaFuncSetAttribute(mpp_maaco_tour1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             smem_set[dv] = smem;
         }
     }
-    mpp_maaco_tour1_kernel<<<dim3((warps + wpb - 1) / wpb, maps->n_maps), MPP_TOUR1_THREADS, smem, (cudaStream_t)stream>>>(A, apw);
+    const dim3 grid((warps + wpb - 1) / wpb, maps->n_maps);
+    if (n_peers > 0) mpp_maaco_tour1_kernel<true><<<grid, MPP_TOUR1_THREADS, smem, (cudaStream_t)stream>>>(A, apw, PA);
+    else mpp_maaco_tour1_kernel<false><<<grid, MPP_TOUR1_THREADS, smem, (cudaStream_t)stream>>>(A, apw, TourNoPeers());
     MPP_CUDA(cudaGetLastError());
     return MPP_OK;
 }
