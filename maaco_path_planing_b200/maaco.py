@@ -385,6 +385,9 @@ class MAACO:
             self._xbuf_local = torch.zeros(self._xhdr + self._cap_max, dtype=torch.uint8, device=self.device)
             self._xbuf_all = torch.zeros(self.world * (self._xhdr + self._cap_max), dtype=torch.uint8, device=self.device)
         self._latch.zero_()
+        # the tours of the bad pass DID run (the latch rises behind them): their (tile, ant) bits must not be there when the
+        # pass is repeated, or a window slide would reload the first attempt's slab -- the ant's own future cells -- as visited
+        self._touched.zero_()
         self._enqueued = [e for e in self._enqueued if e[0] < first_bad]
         self.exchange_rewinds = getattr(self, "exchange_rewinds", 0) + 1
         for it in redo:
