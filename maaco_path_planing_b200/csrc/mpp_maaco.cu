@@ -12,7 +12,7 @@
 //   touched  [2][tile][ceil(n_ants/32)] uint32  bit = (tile, ant) has a slab this pass; double buffered by pass parity
 //                                     (the update of pass p clears the buffer pass p+1 will use)
 //   moves    [ant][max_cells] uint8   the tour as move codes (MAACO.py:98 order): the best path is decoded from them,
-//                                     and they are what a sharded colony exchanges
+//                                     and they are what a sharded colony exchanges when it has no peer access
 #include <type_traits>
 #include <cmath>
 #include <cstdlib>
@@ -1180,12 +1180,13 @@ extern "C" int mpp_maaco_best(const mpp_map_batch *maps, const mpp_colony *c, in
 // ---------------------------------------------------------------------------------------------
 // K3: pheromone evaporate + ordered deposit + MMAS clip (MAACO.py:304-332).
 // One CTA per (map, tile, group of 8 tile rows); warp = one row of 32 cells, lane = cell.  The deposit of a cell
-// is a sequential fp64 sum over the ants that visited it, in ant order (:306-311), so each warp walks the ants that
-// (a) have a slab for this tile (`touched`) and (b) deposit at all (`okbits`, from mpp_maaco_best) in index order:
-// 32 ants per round -- lane L loads the row word of ant L's slab -- the non-empty words are compacted with their
-// deposits into a per-warp shared-memory list, and the fold over that list is a bare DADD chain (the operand is
-// selected, t + 0.0 == t exactly).  Only slabs that exist are ever read: the traffic is 128 B per (ant, tile) pair
-// + tau, not a dense bitmap.
+// is a sequential fp64 sum over the ants that visited it, in ant order (:306-311).  The CTA lists the ants that
+// (a) have a slab for this tile (`touched`) and (b) deposit at all (`okbits`, from mpp_maaco_best) in index order and
+// takes them 128 per trip: their 32-byte sectors (this row group's eight words) and their deposits go to shared
+// memory with one 16-byte load per thread; each warp then takes its row 32 ants at a time, transposes the 32 x 32
+// bit matrix (ant x cell) across its lanes and adds, per lane, the deposits of the ants that visited that lane's cell
+// as a bare DADD chain (the operand is selected, t + 0.0 == t exactly).  Only slabs that exist are ever read: the
+// traffic is 128 B per (ant, tile) pair + tau, not a dense bitmap.  (Details and measurements at the kernel.)
 // ---------------------------------------------------------------------------------------------
 #define MPP_PHER_THREADS 256
 #define MPP_PHER_CHUNK 2048                   // ants per list-building round (64 bitmap words)
@@ -1448,9 +1449,11 @@ extern "C" int mpp_maaco_pheromone(const mpp_map_batch *maps, const mpp_colony *
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sharded-colony exchange.  Rank g constructs its ants and ships (a) their 16-byte results and (b) their tours as
-// 1-byte move codes in ONE buffer per pass (one all-gather); every rank then replays the codes of all ants into
-// slabs of ITS slice of tile rows and updates the pheromone of that slice with all ants in global order.
+// Sharded-colony exchange, all-gather form (the fallback: with NVLink peer access the tour kernel's P2P instantiation
+// delivers slabs and results itself, mpp_maaco_tours_p2p, and none of this runs).  Rank g constructs its ants and ships
+// (a) their 16-byte results and (b) their tours as 1-byte move codes in ONE buffer per pass (one all-gather); every rank
+// then replays the codes of all ants into slabs of ITS slice of tile rows and updates the pheromone of that slice with all
+// ants in global order.
 //   exchange buffer of one rank: [n_local x mpp_ant_result][int32 total code bytes, 3 x int32 pad][codes ...]
 // ---------------------------------------------------------------------------------------------
 #define MPP_XHDR(n_local) ((size_t)16 * (size_t)(n_local) + 16)
