@@ -372,7 +372,7 @@ def run_gpu(args):
                      "algorithmic_bytes_per_unit": BYTES_PER_ANT_STEP, "units_per_launch": ant_steps_local / K,
                      "kernel_ms": tour_avg_ms,
                      "rank_kernel_ms": sum(rank_ms) / K,
-                     "pheromone_kernel": {"kernel": "mpp_maaco_pheromone_kernel" + ("" if world == 1 else " + tau all-gather"),
+                     "pheromone_kernel": {"kernel": "mpp_maaco_pheromone_kernel" + ("" if world == 1 else " + tau exchange"),
                                           "ms": sum(pher_ms) / K, "algorithmic_bytes": pher_bytes,
                                           "achieved": pher_bytes / (sum(pher_ms) / K / 1e3) / 1e9, "unit": "GB/s",
                                           "frac": pher_bytes / (sum(pher_ms) / K / 1e3) / 1e9 / peak,
