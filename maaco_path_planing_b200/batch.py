@@ -29,6 +29,22 @@ def shard_maps(n_maps, group=None):
     return min(n_maps, rank * per), min(n_maps, (rank + 1) * per)
 
 
+def _grids_u8(grids):
+    """[n_maps, rows, cols] cell codes as uint8 (what mpp_map_batch_create takes): values clipped to 0..255 like
+    np.clip(int grid), written straight into the byte array (an int64 wave of 128 256x256 maps is 67 MB: the
+    intermediate int64 copies cost more host time than the wave's passes cost on the GPU)."""
+    g = np.asarray(grids)
+    if g.ndim != 3:
+        raise ValueError("grids must be [n_maps, rows, cols]")
+    if g.dtype == np.uint8:
+        return np.ascontiguousarray(g)
+    if g.dtype.kind not in "iub":
+        g = g.astype(int)                                                     # (the reference indexes int grids)
+    g8 = np.empty(g.shape, np.uint8)
+    np.clip(g, 0, 255, out=g8, casting="unsafe")
+    return g8
+
+
 class MAACOBatch:
     """M same-shape maps that share start and target, one colony of `num_ants` ants per map, solved together.
     Same parameters as MAACO (MAACO.py:11-14); `seeds` = one Philox seed per map."""
@@ -38,11 +54,9 @@ class MAACOBatch:
                  reuse=None):
         import torch
         L = _lib.lib()
-        g = np.ascontiguousarray(np.asarray(grids, dtype=int))
-        if g.ndim != 3:
-            raise ValueError("grids must be [n_maps, rows, cols]")
-        self.n_maps, self.rows, self.cols = g.shape
-        flat = g.reshape(self.n_maps, -1)
+        g8 = _grids_u8(grids)
+        self.n_maps, self.rows, self.cols = g8.shape
+        flat = g8.reshape(self.n_maps, -1)
         if not (flat == START_NODE_VAL).any(axis=1).all():
             raise ValueError("MAACO: Start node not found.")                  # MAACO.py:35-36
         if not (flat == TARGET_NODE_VAL).any(axis=1).all():
@@ -50,7 +64,6 @@ class MAACOBatch:
         _lib.require_device()
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
-        g8 = np.ascontiguousarray(np.clip(g, 0, 255), dtype=np.uint8)
         h = C.c_void_p()
         _lib.check(L.mpp_map_batch_create(g8.ctypes.data_as(C.c_void_p), self.n_maps, self.rows, self.cols,
                                           self.device_index, C.byref(h)), "mpp_map_batch_create")
@@ -163,7 +176,8 @@ class MAACOBatch:
         out = []
         for k in range(M):
             nb = int(st["best_n_cells"][k])
-            path = [(int(c) // self.cols, int(c) % self.cols) for c in best[k, :nb]]
+            pr, pc = np.divmod(best[k, :nb], self.cols)
+            path = list(zip(pr.tolist(), pc.tolist()))
             turns = int(st["best_turns"][k]) if st["best_turns"][k] >= 0 else INF
             curve = [float(v) if v != INF else None for v in log[k, :, 2]]
             out.append((path, float(st["best_len"][k]), turns, curve))
@@ -218,11 +232,9 @@ class MPABatch:
         import torch
         from .engine import make_policy
         L = _lib.lib()
-        g = np.ascontiguousarray(np.asarray(grids, dtype=int))
-        if g.ndim != 3:
-            raise ValueError("grids must be [n_maps, rows, cols]")
-        self.n_maps, self.rows, self.cols = g.shape
-        flat = g.reshape(self.n_maps, -1)
+        g8 = _grids_u8(grids)
+        self.n_maps, self.rows, self.cols = g8.shape
+        flat = g8.reshape(self.n_maps, -1)
         if not (flat == START_NODE_VAL).any(axis=1).all():
             raise ValueError("MPA: Start node not found in grid.")            # MPA.py:36-37
         if not (flat == TARGET_NODE_VAL).any(axis=1).all():
@@ -230,7 +242,7 @@ class MPABatch:
         _lib.require_device()
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
-        self._grids8 = np.ascontiguousarray(np.clip(g, 0, 255), dtype=np.uint8)
+        self._grids8 = g8
         h = C.c_void_p()
         _lib.check(L.mpp_map_batch_create(self._grids8.ctypes.data_as(C.c_void_p), self.n_maps, self.rows, self.cols,
                                           self.device_index, C.byref(h)), "mpp_map_batch_create")
