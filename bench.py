@@ -149,15 +149,21 @@ def ref_python(kind, size, map_seed, seconds, procs=None):
                       f"reference, {seconds:.0f} s each ({wall:.0f} s wall incl. interpreter start + table build)"}
 
 
-def workload_config(args, world, total, p2p=None):
-    how = "" if world == 1 else ("; the tour kernel stores every visited-set slab straight into the rank that updates its tile row "
-                                 "and the update kernel its tau slice into every rank (NVLink peer memory, two device-side "
-                                 "barriers per pass: no pack / all-gather / replay)" if p2p else
-                                 "; per pass one all-gather of results + move codes and one all-gather of tau slices (NCCL)")
+def workload_config(args, world, total):
+    """The same dict in both arms (the driver compares them); how the GPU arm exchanges is reported under "exchange"."""
     return {"workload": f"MAACO colony pass, {total} ants ({total // world}/GPU) on {args.size}x{args.size} "
                         f"blocks(n,0.20,seed=4000), params main.py:34-38 (BASELINE config 4)",
             "ants_total": total, "grid": [args.size, args.size], "l2": "flushed (256 MiB write) between timed steps",
-            "parallelism": f"colony sharded over {world} GPU(s)" + how}
+            "parallelism": f"colony sharded over {world} GPU(s)"}
+
+
+def exchange_note(world, p2p):
+    if world == 1:
+        return "none (one GPU)"
+    return ("the tour kernel stores every visited-set slab straight into the rank that updates its tile row and the update "
+            "kernel its tau slice into every rank (NVLink peer memory, two device-side barriers per pass: no pack / "
+            "all-gather / replay)" if p2p else
+            "per pass one all-gather of results + move codes and one all-gather of tau slices (NCCL)")
 
 
 def run_reference(args):
@@ -362,7 +368,8 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "path evals/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, world, total_ants, getattr(solver, "_p2p", None) is not None),
+        "config": workload_config(args, world, total_ants),
+        "exchange": exchange_note(world, getattr(solver, "_p2p", None) is not None),
         "e2e": e2e,
         "gpu_launches": launches_timed,
         "clocks": clocks,
